@@ -1,0 +1,450 @@
+"""Python mirror of the reference's Go package `conv` (dsp/conv/*.go) on top of the C ABI.
+
+Same names, argument meaning and error behaviour as the Go API, so the parity tests read like
+the reference's own tests:
+
+    result = conv.Convolve(signal, kernel)            # conv.go:194
+    c = conv.NewOverlapSave(kernel, 0); y = c.Process(x)   # overlap_save.go:53,126
+    idx, val = conv.FindPeak(conv.Correlate(a, b))    # correlate.go:16,200
+
+Go returns (value, error); here errors are raised as ConvError whose `.sentinel` is one of the
+Err* objects below (`errors_is(err, ErrEmptyInput)` mirrors errors.Is).  All arithmetic runs in
+libalgodsp_cuda on the GPU -- there is no CPU path in this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+# ---------------------------------------------------------------- errors (conv.go:41-46, partitioned.go:11-15)
+
+
+class _Sentinel:
+    def __init__(self, name, text):
+        self.name, self.text = name, text
+
+    def __repr__(self):
+        return self.name
+
+
+ErrEmptyInput = _Sentinel("ErrEmptyInput", "conv: empty input")
+ErrEmptyKernel = _Sentinel("ErrEmptyKernel", "conv: empty kernel")
+ErrLengthMismatch = _Sentinel("ErrLengthMismatch", "conv: buffer length mismatch")
+ErrInvalidBlockSize = _Sentinel("ErrInvalidBlockSize", "conv: invalid block size")
+ErrInvalidBlockOrder = _Sentinel("ErrInvalidBlockOrder", "conv: invalid block order")
+ErrEmptyImpulseResponse = _Sentinel("ErrEmptyImpulseResponse", "conv: empty impulse response")
+ErrStageIndexOutOfRange = _Sentinel("ErrStageIndexOutOfRange", "conv: stage index out of range")
+ErrInvalidArgument = _Sentinel("ErrInvalidArgument", "algodsp: invalid argument")
+ErrCUDA = _Sentinel("ErrCUDA", "algodsp: CUDA error")
+ErrOutOfMemory = _Sentinel("ErrOutOfMemory", "algodsp: out of memory")
+
+_SENTINELS = {
+    L.ERR_EMPTY_INPUT: ErrEmptyInput, L.ERR_EMPTY_KERNEL: ErrEmptyKernel, L.ERR_LENGTH_MISMATCH: ErrLengthMismatch,
+    L.ERR_INVALID_BLOCK_SIZE: ErrInvalidBlockSize, L.ERR_INVALID_BLOCK_ORDER: ErrInvalidBlockOrder,
+    L.ERR_EMPTY_IR: ErrEmptyImpulseResponse, L.ERR_STAGE_INDEX: ErrStageIndexOutOfRange,
+    L.ERR_INVALID_ARG: ErrInvalidArgument, L.ERR_CUDA: ErrCUDA, L.ERR_OOM: ErrOutOfMemory,
+}
+
+
+class ConvError(Exception):
+    def __init__(self, status, detail=""):
+        self.status = status
+        self.sentinel = _SENTINELS.get(status, ErrInvalidArgument)
+        msg = self.sentinel.text + (f": {detail}" if detail else "")
+        super().__init__(msg)
+
+
+def errors_is(err, sentinel) -> bool:
+    """errors.Is(err, sentinel)."""
+    return isinstance(err, ConvError) and err.sentinel is sentinel
+
+
+def _check(st):
+    if st != L.OK:
+        detail = L.last_error() if st in (L.ERR_CUDA, L.ERR_OOM, L.ERR_INVALID_ARG) else ""
+        raise ConvError(st, detail)
+
+
+# ---------------------------------------------------------------- Mode (conv.go:57-69)
+ModeFull, ModeSame, ModeValid = 0, 1, 2
+
+# ---------------------------------------------------------------- context
+
+
+class Context:
+    """One GPU (adsp_ctx): streams, twiddle tables, L2-resident scratch, staging buffers."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        _check(L.load().adsp_ctx_create(int(device), C.byref(self._h)))
+        self.device = device
+
+    @property
+    def handle(self):
+        return self._h
+
+    def sync(self):
+        _check(L.load().adsp_ctx_sync(self._h))
+
+    def launch_count(self) -> int:
+        return int(L.load().adsp_ctx_launch_count(self._h))
+
+    def stream(self) -> int:
+        return int(L.load().adsp_ctx_stream(self._h) or 0)
+
+    def close(self):
+        if self._h:
+            L.load().adsp_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx: dict[int, Context] = {}
+
+
+def default_context(device: int = 0) -> Context:
+    ctx = _default_ctx.get(device)
+    if ctx is None:
+        ctx = _default_ctx[device] = Context(device)
+    return ctx
+
+
+def _ctx(ctx):
+    return (ctx or default_context()).handle
+
+
+def _f64(x):
+    return np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+
+
+def _as(x, dtype):
+    return np.ascontiguousarray(x, dtype=dtype).reshape(-1)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a.size else C.c_void_p(0)
+
+
+def _binary(name, a, b, ctx=None, dtype=np.float64):
+    a, b = _as(a, dtype), _as(b, dtype)
+    out = np.empty(max(a.size + b.size - 1, 1), dtype=dtype)
+    _check(getattr(L.load(), name)(_ctx(ctx), _p(a), a.size, _p(b), b.size, _p(out)))
+    return out[: a.size + b.size - 1]
+
+
+# ---------------------------------------------------------------- package-level functions
+
+
+def Direct(a, b, ctx=None):
+    """Direct(a, b) -- conv.go:76."""
+    return _binary("adsp_direct", a, b, ctx)
+
+
+def DirectTo(dst, a, b, ctx=None):
+    """DirectTo(dst, a, b) -- conv.go:97 (dst must have len(a)+len(b)-1 elements)."""
+    dst[:] = Direct(a, b, ctx)
+
+
+def DirectCircular(a, b, ctx=None):
+    """DirectCircular(a, b) -- conv.go:158."""
+    a, b = _f64(a), _f64(b)
+    out = np.empty(max(a.size, 1), dtype=np.float64)
+    _check(L.load().adsp_direct_circular(_ctx(ctx), _p(a), a.size, _p(b), b.size, _p(out)))
+    return out[: a.size]
+
+
+def Convolve(a, b, ctx=None):
+    """Convolve(a, b): direct iff the shorter operand has <= 64 taps, else FFT -- conv.go:194."""
+    return _binary("adsp_convolve", a, b, ctx)
+
+
+def trimToMode(full, lenA, lenB, mode):
+    """trimToMode -- conv.go:229."""
+    s, l = C.c_int64(), C.c_int64()
+    L.load().adsp_trim_mode(lenA, lenB, int(mode), C.byref(s), C.byref(l))
+    return full[s.value: s.value + l.value]
+
+
+def ConvolveMode(a, b, mode, ctx=None):
+    """ConvolveMode -- conv.go:219."""
+    return trimToMode(Convolve(a, b, ctx), len(a), len(b), mode)
+
+
+def OverlapAddConvolve(signal, kernel, ctx=None):
+    """OverlapAddConvolve -- overlap_add.go:221."""
+    return _binary("adsp_overlap_add_convolve", signal, kernel, ctx)
+
+
+def OverlapSaveConvolve(signal, kernel, ctx=None):
+    """OverlapSaveConvolve -- overlap_save.go:313."""
+    return _binary("adsp_overlap_save_convolve", signal, kernel, ctx)
+
+
+def OverlapAddConvolveTo(output, signal, kernel, ctx=None):
+    """OverlapAddConvolveTo -- overlap_add.go:297."""
+    oa = NewOverlapAdd(kernel, 0, ctx=ctx)
+    oa.ProcessTo(output, signal)
+
+
+def Correlate(a, b, ctx=None):
+    """Correlate(a, b) = Convolve(a, reverse(b)) -- correlate.go:16."""
+    return _binary("adsp_correlate", a, b, ctx)
+
+
+def CorrelateDirect(a, b, ctx=None):
+    """CorrelateDirect -- correlate.go:31."""
+    return _binary("adsp_correlate_direct", a, b, ctx)
+
+
+def CorrelateFFT(a, b, ctx=None):
+    """CorrelateFFT -- correlate.go:111."""
+    return _binary("adsp_correlate_fft", a, b, ctx)
+
+
+def CorrelateMode(a, b, mode, ctx=None):
+    """CorrelateMode -- correlate.go:45."""
+    return trimToMode(Correlate(a, b, ctx), len(a), len(b), mode)
+
+
+def AutoCorrelate(a, ctx=None):
+    """AutoCorrelate -- correlate.go:57."""
+    return Correlate(a, a, ctx)
+
+
+def AutoCorrelateNormalized(a, ctx=None):
+    """AutoCorrelateNormalized -- correlate.go:63."""
+    a = _f64(a)
+    out = np.empty(max(2 * a.size - 1, 1), dtype=np.float64)
+    _check(L.load().adsp_autocorrelate_normalized(_ctx(ctx), _p(a), a.size, _p(out)))
+    return out[: 2 * a.size - 1]
+
+
+def CorrelateNormalized(a, b, ctx=None):
+    """CorrelateNormalized -- correlate.go:86."""
+    return _binary("adsp_correlate_normalized", a, b, ctx)
+
+
+def FindPeak(corr, ctx=None):
+    """FindPeak -- correlate.go:200: (index, value) of the signed maximum, (-1, 0) if empty."""
+    c = _f64(corr)
+    idx, val = C.c_int64(), C.c_double()
+    _check(L.load().adsp_find_peak(_ctx(ctx), _p(c), c.size, C.byref(idx), C.byref(val)))
+    return idx.value, val.value
+
+
+def LagFromIndex(index, lenB):
+    """LagFromIndex -- correlate.go:221."""
+    return int(L.load().adsp_lag_from_index(index, lenB))
+
+
+def IndexFromLag(lag, lenB):
+    """IndexFromLag -- correlate.go:227."""
+    return int(L.load().adsp_index_from_lag(lag, lenB))
+
+
+def nextPowerOf2(n):
+    """nextPowerOf2 -- conv.go:250."""
+    return int(L.load().adsp_next_pow2(n))
+
+
+def isPowerOf2(n):
+    """isPowerOf2 -- conv.go:264."""
+    return bool(L.load().adsp_is_pow2(n))
+
+
+# f32 twins (optional fp32 mode)
+def Direct32(a, b, ctx=None):
+    return _binary("adsp_direct_f32", a, b, ctx, np.float32)
+
+
+def Convolve32(a, b, ctx=None):
+    return _binary("adsp_convolve_f32", a, b, ctx, np.float32)
+
+
+def Correlate32(a, b, ctx=None):
+    return _binary("adsp_correlate_f32", a, b, ctx, np.float32)
+
+
+# batched forms (configs 2 and 4)
+def DirectBatch(a2d, b, ctx=None):
+    """Direct over the rows of a2d; b is one kernel (1-D) or one per row (2-D)."""
+    a = np.ascontiguousarray(a2d, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    batch, n = a.shape
+    m = b.shape[-1]
+    out = np.empty((batch, n + m - 1), dtype=np.float64)
+    bs = m if b.ndim == 2 else 0
+    _check(L.load().adsp_direct_batch(_ctx(ctx), _p(a), n, n, _p(b), m, bs, batch, _p(out), n + m - 1))
+    return out
+
+
+def CorrelateBatch(a2d, b2d, want_output=True, ctx=None):
+    """Correlate row p of a2d with row p of b2d; returns (out or None, peak_index, peak_value)."""
+    a = np.ascontiguousarray(a2d, dtype=np.float64)
+    b = np.ascontiguousarray(b2d, dtype=np.float64)
+    pairs, n = a.shape
+    m = b.shape[1]
+    out = np.empty((pairs, n + m - 1), dtype=np.float64) if want_output else None
+    pi = np.empty(pairs, dtype=np.int64)
+    pv = np.empty(pairs, dtype=np.float64)
+    _check(L.load().adsp_correlate_batch(_ctx(ctx), _p(a), n, n, _p(b), m, m, pairs,
+                                         _p(out) if out is not None else C.c_void_p(0), n + m - 1, _p(pi), _p(pv)))
+    return out, pi, pv
+
+
+# ---------------------------------------------------------------- reusable convolvers
+
+
+class _Plan:
+    _dtype = np.float64
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        self._ctx_obj = None
+
+    def _np(self, x):
+        return _as(x, self._dtype)
+
+    def KernelLen(self):
+        return int(L.load().adsp_plan_kernel_len(self._h))
+
+    def FFTSize(self):
+        return int(L.load().adsp_plan_fft_size(self._h))
+
+    def Reset(self):
+        L.load().adsp_plan_reset(self._h)
+
+    def internal_geometry(self):
+        v = [C.c_int64() for _ in range(5)]
+        L.load().adsp_plan_internal_geometry(self._h, *[C.byref(x) for x in v])
+        return dict(zip(("fft_n", "n1", "n2", "step", "partitions"), (x.value for x in v)))
+
+    def Process(self, input):
+        """Process(input) -> full linear convolution, len(input)+KernelLen()-1 samples."""
+        x = self._np(input)
+        out = np.empty(max(x.size + self.KernelLen() - 1, 1), dtype=self._dtype)
+        n_out = x.size + self.KernelLen() - 1
+        _check(L.load().adsp_plan_process(self._h, _p(x), x.size, _p(out), n_out))
+        return out[:n_out]
+
+    def ProcessTo(self, output, input):
+        """ProcessTo(output, input): ErrLengthMismatch unless len(output) == len(input)+K-1."""
+        x = self._np(input)
+        if not (isinstance(output, np.ndarray) and output.dtype == self._dtype and output.flags.c_contiguous):
+            raise TypeError("output must be a contiguous numpy array of the plan's dtype")
+        _check(L.load().adsp_plan_process(self._h, _p(x), x.size, _p(output), output.size))
+
+    def ProcessBatch(self, x2d):
+        """All rows of x2d (channels x n) in one call."""
+        x = np.ascontiguousarray(x2d, dtype=self._dtype)
+        ch, n = x.shape
+        out = np.empty((ch, n + self.KernelLen() - 1), dtype=self._dtype)
+        _check(L.load().adsp_plan_process_batch(self._h, _p(x), n, ch, n, _p(out), out.shape[1]))
+        return out
+
+    def process_device(self, in_ptr, n, channels, in_stride, out_ptr, out_stride):
+        """Device-resident call (raw device pointers); asynchronous on the context stream."""
+        _check(L.load().adsp_plan_process_device(self._h, C.c_void_p(in_ptr), n, channels, in_stride, C.c_void_p(out_ptr), out_stride))
+
+    def sync(self):
+        _check(L.load().adsp_plan_sync(self._h))
+
+    def Close(self):
+        if self._h:
+            L.load().adsp_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.Close()
+        except Exception:
+            pass
+
+
+class OverlapSave(_Plan):
+    """OverlapSave -- overlap_save.go:32."""
+
+    def __init__(self, kernel, fftSize=0, ctx=None, dtype=np.float64):
+        super().__init__()
+        self._dtype = np.dtype(dtype).type
+        self._ctx_obj = ctx or default_context()
+        k = self._np(kernel)
+        prec = L.F64 if self._dtype == np.float64 else L.F32
+        _check(L.load().adsp_overlap_save_create(self._ctx_obj.handle, _p(k), k.size, int(fftSize), prec, C.byref(self._h)))
+
+    def StepSize(self):
+        return int(L.load().adsp_plan_step_size(self._h))
+
+
+class OverlapAdd(_Plan):
+    """OverlapAdd -- overlap_add.go:24."""
+
+    def __init__(self, kernel, blockSize=0, ctx=None, dtype=np.float64):
+        super().__init__()
+        self._dtype = np.dtype(dtype).type
+        self._ctx_obj = ctx or default_context()
+        k = self._np(kernel)
+        prec = L.F64 if self._dtype == np.float64 else L.F32
+        _check(L.load().adsp_overlap_add_create(self._ctx_obj.handle, _p(k), k.size, int(blockSize), prec, C.byref(self._h)))
+
+    def BlockSize(self):
+        return int(L.load().adsp_plan_block_size(self._h))
+
+
+def NewOverlapSave(kernel, fftSize=0, ctx=None, dtype=np.float64):
+    """NewOverlapSave(kernel, fftSize) -- overlap_save.go:53."""
+    return OverlapSave(kernel, fftSize, ctx, dtype)
+
+
+def NewOverlapAdd(kernel, blockSize=0, ctx=None, dtype=np.float64):
+    """NewOverlapAdd(kernel, blockSize) -- overlap_add.go:44."""
+    return OverlapAdd(kernel, blockSize, ctx, dtype)
+
+
+class PartitionedConvolution(_Plan):
+    """PartitionedConvolutionT -- partitioned.go:27 (f64: PartitionedConvolution, f32: PartitionedConvolution32)."""
+
+    def __init__(self, kernel, minBlockOrder, maxBlockOrder, ctx=None, dtype=np.float64):
+        super().__init__()
+        self._dtype = np.dtype(dtype).type
+        self._ctx_obj = ctx or default_context()
+        k = self._np(kernel)
+        prec = L.F64 if self._dtype == np.float64 else L.F32
+        _check(L.load().adsp_partitioned_create(self._ctx_obj.handle, _p(k), k.size, int(minBlockOrder), int(maxBlockOrder),
+                                                prec, C.byref(self._h)))
+
+    def ProcessBlock(self, input, output):
+        """ProcessBlock(input, output): equal lengths; output delayed by Latency() samples."""
+        x = self._np(input)
+        if not (isinstance(output, np.ndarray) and output.dtype == self._dtype and output.flags.c_contiguous):
+            raise TypeError("output must be a contiguous numpy array of the plan's dtype")
+        _check(L.load().adsp_partitioned_process_block(self._h, _p(x), x.size, _p(output), output.size))
+
+    def Latency(self):
+        return int(L.load().adsp_partitioned_latency(self._h))
+
+    def StageCount(self):
+        return int(L.load().adsp_partitioned_stage_count(self._h))
+
+    def StageInfo(self, index):
+        ps, bc = C.c_int(), C.c_int()
+        _check(L.load().adsp_partitioned_stage_info(self._h, int(index), C.byref(ps), C.byref(bc)))
+        return ps.value, bc.value
+
+
+def NewPartitionedConvolution(kernel, minBlockOrder, maxBlockOrder, ctx=None):
+    """NewPartitionedConvolution -- partitioned.go:335."""
+    return PartitionedConvolution(kernel, minBlockOrder, maxBlockOrder, ctx, np.float64)
+
+
+def NewPartitionedConvolution32(kernel, minBlockOrder, maxBlockOrder, ctx=None):
+    """NewPartitionedConvolution32 -- partitioned.go:340."""
+    return PartitionedConvolution(kernel, minBlockOrder, maxBlockOrder, ctx, np.float32)

@@ -1,0 +1,852 @@
+// api.cu -- the C ABI of libalgodsp_cuda (include/algodsp_cuda.h): context, plans, one-shot
+// functions.  Host-side bookkeeping only; all arithmetic runs in the sm_100a kernels of
+// conv_kernels.cuh / aux_kernels.cuh.  There is no CPU fallback anywhere in this file.
+#include <algorithm>
+#include <cmath>
+
+#include "aux_kernels.cuh"
+#include "engine.cuh"
+
+namespace adsp {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string &msg) { g_last_error = msg; }
+
+adsp_status cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    g_last_error = buf;
+    cudaGetLastError();  // clear non-sticky error state
+    return (e == cudaErrorMemoryAllocation) ? ADSP_ERR_OOM : ADSP_ERR_CUDA;
+}
+
+adsp_status DevBuf::reserve(size_t bytes) {
+    if (bytes <= cap) return ADSP_OK;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    const size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); if (e != cudaSuccess) { p = nullptr; return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__); } cap = bytes; return ADSP_OK; }
+    cap = want;
+    return ADSP_OK;
+}
+void DevBuf::release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+
+adsp_status PinnedBuf::reserve(size_t bytes) {
+    if (bytes <= cap) return ADSP_OK;
+    if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+    cudaError_t e = cudaMallocHost(&p, bytes);
+    if (e != cudaSuccess) { p = nullptr; return cuda_fail(e, "cudaMallocHost", __FILE__, __LINE__); }
+    cap = bytes;
+    return ADSP_OK;
+}
+void PinnedBuf::release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+
+static long long next_pow2_ll(long long n) {
+    if (n <= 1) return 1;
+    long long p = 1;
+    while (p < n) p *= 2;
+    return p;
+}
+
+static long long env_ll(const char *name, long long dflt) {
+    const char *v = getenv(name);
+    if (!v || !*v) return dflt;
+    return atoll(v);
+}
+
+// Internal transform size for K taps.  The API only fixes results, so the GPU is free to use a
+// larger transform than the reference's nextPow2(2K): a longer block wastes less of each
+// transform on the K-1 discarded samples.
+FftChoice choose_fft(long long K) {
+    FftChoice c;
+    const long long NMAX = env_ll("ADSP_MAX_FFT", 1LL << 20);
+    long long Kp = K;
+    if (K - 1 > NMAX / 2) {
+        c.parts = (int)((K + NMAX / 2 - 1) / (NMAX / 2));
+        Kp = (K + c.parts - 1) / c.parts;
+    }
+    c.part_len = Kp;
+    long long N = next_pow2_ll(8 * Kp);
+    const long long forced = env_ll("ADSP_FFT_N", 0);
+    if (forced > 0) N = forced;
+    if (N < 256) N = 256;
+    if (N > NMAX) N = NMAX;
+    while (N < 2 * Kp && N < (1LL << 22)) N *= 2;
+    c.N = N;
+    int lg = 0;
+    while ((1LL << lg) < N) lg++;
+    c.lgN = lg;
+    if (N <= 4096) { c.N1 = 1; c.N2 = (int)N; }
+    else {
+        long long n2 = env_ll("ADSP_FFT_N2", 4096);
+        if (n2 > N / 16) n2 = N / 16;
+        if (n2 < 256) n2 = 256;
+        while (N / n2 > 1024) n2 *= 2;
+        c.N2 = (int)n2;
+        c.N1 = (int)(N / n2);
+    }
+    // discard count rounded up to 32 samples so block starts stay 256-byte aligned
+    long long D = ((Kp - 1 + 31) / 32) * 32;
+    if (D >= N) D = Kp - 1;
+    c.D = D;
+    c.S = N - D;
+    return c;
+}
+
+template <typename T>
+adsp_status direct_device(adsp_ctx *ctx, const T *d_a, long long n, long long a_stride, const T *d_b, long long m,
+                          long long b_stride, long long batch, T *d_out, long long out_stride) {
+    const long long out_len = n + m - 1;
+    const long long tiles = (out_len + DIRECT_TILE - 1) / DIRECT_TILE;
+    const long long grid = tiles * batch;
+    if (grid <= 0) return ADSP_OK;
+    if (grid > 0x7fffffffLL) { set_error("direct: grid too large"); return ADSP_ERR_INVALID_ARG; }
+    static const bool exact = env_ll("ADSP_DIRECT_EXACT", 0) != 0;
+    if (exact)
+        direct_conv_kernel<T, false><<<(unsigned)grid, DIRECT_THREADS, 0, ctx->main>>>(d_a, n, a_stride, d_b, m, b_stride, d_out, out_stride, tiles);
+    else
+        direct_conv_kernel<T, true><<<(unsigned)grid, DIRECT_THREADS, 0, ctx->main>>>(d_a, n, a_stride, d_b, m, b_stride, d_out, out_stride, tiles);
+    count_launch(ctx);
+    ADSP_CUDA(cudaGetLastError());
+    return ADSP_OK;
+}
+template adsp_status direct_device<double>(adsp_ctx *, const double *, long long, long long, const double *, long long, long long, long long, double *, long long);
+template adsp_status direct_device<float>(adsp_ctx *, const float *, long long, long long, const float *, long long, long long, long long, float *, long long);
+
+// FindPeak on device vectors; results land in d_v[batch], d_i[batch]
+template <typename T>
+static adsp_status peak_device(adsp_ctx *ctx, const T *d_x, long long len, long long stride, long long batch, T *d_v,
+                               long long *d_i) {
+    if (batch <= 0) return ADSP_OK;
+    int nparts = (int)std::min<long long>(64, (len + 256 * 8 - 1) / (256 * 8));
+    if (nparts < 1) nparts = 1;
+    const size_t need = (size_t)batch * nparts * (sizeof(T) + sizeof(long long));
+    ADSP_TRY(ctx->d_small.reserve(need + 64));
+    long long *pi = (long long *)ctx->d_small.p;
+    T *pv = (T *)((char *)ctx->d_small.p + (size_t)batch * nparts * sizeof(long long));
+    dim3 g1((unsigned)nparts, (unsigned)batch);
+    peak_partial_kernel<T><<<g1, 256, 0, ctx->main>>>(d_x, len, stride, pv, pi);
+    peak_final_kernel<T><<<(unsigned)batch, 32, 0, ctx->main>>>(d_x, stride, pv, pi, nparts, batch, d_v, d_i);
+    count_launch(ctx, 2);
+    ADSP_CUDA(cudaGetLastError());
+    return ADSP_OK;
+}
+
+// ---------------------------------------------------------------- host <-> device transfer helpers
+static bool is_pinned_host(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// copy rows of `width` elements between host (stride hs) and device (stride ds)
+static adsp_status copy2d(adsp_ctx *ctx, void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes,
+                          size_t rows, cudaMemcpyKind kind) {
+    if (rows == 0 || width_bytes == 0) return ADSP_OK;
+    if (rows == 1 || (dpitch == width_bytes && spitch == width_bytes))
+        ADSP_CUDA(cudaMemcpyAsync(dst, src, width_bytes * rows, kind, ctx->main));
+    else
+        ADSP_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, rows, kind, ctx->main));
+    return ADSP_OK;
+}
+
+}  // namespace adsp
+
+using namespace adsp;
+
+// ================================================================ plans
+enum PlanKind { PLAN_OLS = 0, PLAN_OLA = 1, PLAN_PART = 2 };
+
+struct PartStage { int part_size; int count; int start_pos; };
+
+struct adsp_plan {
+    adsp_ctx *ctx = nullptr;
+    PlanKind kind = PLAN_OLS;
+    adsp_precision prec = ADSP_F64;
+    long long K = 0;
+    long long ref_fft = 0, ref_step = 0, ref_block = 0;  // what the Go getters report
+    FftChoice ch;
+    std::vector<FftConv<double>> fc64;
+    std::vector<FftConv<float>> fc32;
+    // partitioned (streaming) state
+    int latency = 0, min_order = 0, max_order = 0;
+    std::vector<PartStage> stages;
+    DevBuf hist[2];      // last K-1+latency input samples, ping-pong
+    int hist_cur = 0;
+    long long hist_len = 0;
+    DevBuf blk_in, blk_out;
+};
+
+template <typename T> static std::vector<FftConv<T>> &plan_fc(adsp_plan *p);
+template <> std::vector<FftConv<double>> &plan_fc<double>(adsp_plan *p) { return p->fc64; }
+template <> std::vector<FftConv<float>> &plan_fc<float>(adsp_plan *p) { return p->fc32; }
+
+template <typename T> static adsp_status plan_build(adsp_plan *p, const T *host_kernel) {
+    adsp_ctx *ctx = p->ctx;
+    ADSP_TRY(ctx->d_k.reserve((size_t)p->K * sizeof(T)));
+    ADSP_CUDA(cudaMemcpyAsync(ctx->d_k.p, host_kernel, (size_t)p->K * sizeof(T), cudaMemcpyHostToDevice, ctx->main));
+    p->ch = choose_fft(p->K);
+    auto &v = plan_fc<T>(p);
+    v.resize((size_t)p->ch.parts);
+    for (int i = 0; i < p->ch.parts; i++) {
+        const long long k0 = (long long)i * p->ch.part_len;
+        const long long kp = std::min<long long>(p->ch.part_len, p->K - k0);
+        ADSP_TRY(v[(size_t)i].init(ctx, (const T *)ctx->d_k.p + k0, kp, p->ch));
+    }
+    return ADSP_OK;
+}
+
+template <typename T>
+static adsp_status plan_run_device(adsp_plan *p, const T *d_in, long long n, long long channels, long long in_stride,
+                                   T *d_out, long long out_stride) {
+    auto &v = plan_fc<T>(p);
+    const long long out_len = n + p->K - 1;
+    if (v.size() == 1) return v[0].run(d_in, n, channels, in_stride, d_out, out_stride, out_len, 0, 0, false);
+    ADSP_CUDA(cudaMemset2DAsync(d_out, (size_t)out_stride * sizeof(T), 0, (size_t)out_len * sizeof(T), (size_t)channels, p->ctx->main));
+    for (size_t i = 0; i < v.size(); i++) {
+        const long long k0 = (long long)i * p->ch.part_len;
+        ADSP_TRY(v[i].run(d_in, n, channels, in_stride, d_out, out_stride, n + v[i].K - 1, 0, k0, true));
+    }
+    return ADSP_OK;
+}
+
+// host-pointer batch: stage through device buffers owned by the context
+template <typename T>
+static adsp_status plan_run_host(adsp_plan *p, const T *in, long long n, long long channels, long long in_stride,
+                                 T *out, long long out_stride) {
+    adsp_ctx *ctx = p->ctx;
+    const long long out_len = n + p->K - 1;
+    // device layout: dense rows padded to 32 elements so every channel starts 256-byte aligned
+    const long long dis = ((n + 31) / 32) * 32, dos = ((out_len + 31) / 32) * 32;
+    ADSP_TRY(ctx->d_in.reserve((size_t)dis * channels * sizeof(T)));
+    ADSP_TRY(ctx->d_out.reserve((size_t)dos * channels * sizeof(T)));
+    ADSP_TRY(copy2d(ctx, ctx->d_in.p, (size_t)dis * sizeof(T), in, (size_t)in_stride * sizeof(T), (size_t)n * sizeof(T),
+                    (size_t)channels, cudaMemcpyHostToDevice));
+    ADSP_TRY(plan_run_device<T>(p, (const T *)ctx->d_in.p, n, channels, dis, (T *)ctx->d_out.p, dos));
+    ADSP_TRY(copy2d(ctx, out, (size_t)out_stride * sizeof(T), ctx->d_out.p, (size_t)dos * sizeof(T),
+                    (size_t)out_len * sizeof(T), (size_t)channels, cudaMemcpyDeviceToHost));
+    ADSP_CUDA(cudaStreamSynchronize(ctx->main));
+    return ADSP_OK;
+}
+
+// ================================================================ C ABI
+extern "C" {
+
+const char *adsp_version(void) { return "algodsp_cuda 0.1 (sm_100a)"; }
+
+const char *adsp_status_string(adsp_status st) {
+    switch (st) {
+    case ADSP_OK: return "ok";
+    case ADSP_ERR_EMPTY_INPUT: return "conv: empty input";
+    case ADSP_ERR_EMPTY_KERNEL: return "conv: empty kernel";
+    case ADSP_ERR_LENGTH_MISMATCH: return "conv: buffer length mismatch";
+    case ADSP_ERR_INVALID_BLOCK_SIZE: return "conv: invalid block size";
+    case ADSP_ERR_INVALID_BLOCK_ORDER: return "conv: invalid block order";
+    case ADSP_ERR_EMPTY_IR: return "conv: empty impulse response";
+    case ADSP_ERR_STAGE_INDEX: return "conv: stage index out of range";
+    case ADSP_ERR_INVALID_ARG: return "algodsp: invalid argument";
+    case ADSP_ERR_CUDA: return "algodsp: CUDA error";
+    case ADSP_ERR_OOM: return "algodsp: out of memory";
+    }
+    return "algodsp: unknown status";
+}
+
+size_t adsp_last_error(char *buf, size_t buflen) {
+    const std::string &s = g_last_error;
+    if (buf && buflen) {
+        const size_t n = std::min(buflen - 1, s.size());
+        memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return s.size();
+}
+
+int adsp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+adsp_status adsp_ctx_create(int device, adsp_ctx **out) {
+    if (!out) return ADSP_ERR_INVALID_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error("no CUDA device available: libalgodsp_cuda has no CPU fallback");
+        cudaGetLastError();
+        return ADSP_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) { set_error("device index out of range"); return ADSP_ERR_INVALID_ARG; }
+    ADSP_CUDA(cudaSetDevice(device));
+    adsp_ctx *c = new adsp_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    ADSP_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    c->l2_bytes = (size_t)prop.l2CacheSize;
+    long long budget_mb = env_ll("ADSP_SCRATCH_MB", 0);
+    if (budget_mb <= 0) budget_mb = (long long)(c->l2_bytes >> 20) * 5 / 8;  // leave room for the IR spectrum + streams
+    if (budget_mb < 8) budget_mb = 8;
+    c->scratch_budget = (size_t)budget_mb << 20;
+    ADSP_CUDA(cudaStreamCreateWithFlags(&c->main, cudaStreamNonBlocking));
+    ADSP_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < kWorkerStreams; i++) {
+        ADSP_CUDA(cudaStreamCreateWithFlags(&c->worker[i], cudaStreamNonBlocking));
+        ADSP_CUDA(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+    }
+    *out = c;
+    return ADSP_OK;
+}
+
+void adsp_ctx_destroy(adsp_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto &kv : c->tw_tables) cudaFree(kv.second);
+    for (auto &kv : c->tw4_tables) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
+    c->scratch.release(); c->d_in.release(); c->d_out.release(); c->d_k.release(); c->d_tmp.release(); c->d_small.release();
+    for (int i = 0; i < 2; i++) { c->h_in[i].release(); c->h_out[i].release(); }
+    c->h_small.release();
+    for (int i = 0; i < kWorkerStreams; i++) { cudaStreamDestroy(c->worker[i]); cudaEventDestroy(c->ev_join[i]); }
+    cudaEventDestroy(c->ev_fork);
+    cudaStreamDestroy(c->main);
+    delete c;
+}
+
+adsp_status adsp_ctx_sync(adsp_ctx *c) {
+    if (!c) return ADSP_ERR_INVALID_ARG;
+    ADSP_CUDA(cudaSetDevice(c->device));
+    ADSP_CUDA(cudaStreamSynchronize(c->main));
+    return ADSP_OK;
+}
+
+uint64_t adsp_ctx_launch_count(adsp_ctx *c) { return c ? c->launches.load() : 0; }
+void *adsp_ctx_stream(adsp_ctx *c) { return c ? (void *)c->main : nullptr; }
+
+adsp_status adsp_host_alloc_pinned(size_t bytes, void **out) {
+    if (!out) return ADSP_ERR_INVALID_ARG;
+    ADSP_CUDA(cudaMallocHost(out, bytes ? bytes : 1));
+    return ADSP_OK;
+}
+void adsp_host_free_pinned(void *p) { if (p) cudaFreeHost(p); }
+
+adsp_status adsp_device_alloc(adsp_ctx *c, size_t bytes, void **out) {
+    if (!c || !out) return ADSP_ERR_INVALID_ARG;
+    ADSP_CUDA(cudaSetDevice(c->device));
+    ADSP_CUDA(cudaMalloc(out, bytes ? bytes : 1));
+    return ADSP_OK;
+}
+void adsp_device_free(adsp_ctx *c, void *p) { if (c && p) { cudaSetDevice(c->device); cudaFree(p); } }
+
+adsp_status adsp_memcpy_h2d(adsp_ctx *c, void *dst, const void *src, size_t bytes) {
+    if (!c) return ADSP_ERR_INVALID_ARG;
+    ADSP_CUDA(cudaSetDevice(c->device));
+    ADSP_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->main));
+    ADSP_CUDA(cudaStreamSynchronize(c->main));
+    return ADSP_OK;
+}
+adsp_status adsp_memcpy_d2h(adsp_ctx *c, void *dst, const void *src, size_t bytes) {
+    if (!c) return ADSP_ERR_INVALID_ARG;
+    ADSP_CUDA(cudaSetDevice(c->device));
+    ADSP_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->main));
+    ADSP_CUDA(cudaStreamSynchronize(c->main));
+    return ADSP_OK;
+}
+
+// ---------------------------------------------------------------- sizing helpers
+int64_t adsp_next_pow2(int64_t n) { return next_pow2_ll(n); }
+int adsp_is_pow2(int64_t n) { return n > 0 && (n & (n - 1)) == 0; }
+
+adsp_status adsp_ols_sizes(int64_t K, int64_t fft, int64_t *fft_out, int64_t *step_out) {
+    if (K <= 0) return ADSP_ERR_EMPTY_KERNEL;
+    if (fft <= 0) fft = std::max<int64_t>(next_pow2_ll(2 * K), 256);
+    if (!adsp_is_pow2(fft)) {
+        set_error("conv: invalid block size: fftSize must be power of 2, got " + std::to_string(fft));
+        return ADSP_ERR_INVALID_BLOCK_SIZE;
+    }
+    if (fft < 2 * K) fft = next_pow2_ll(2 * K);
+    if (fft_out) *fft_out = fft;
+    if (step_out) *step_out = fft - K + 1;
+    return ADSP_OK;
+}
+
+adsp_status adsp_ola_sizes(int64_t K, int64_t block, int64_t *block_out, int64_t *fft_out) {
+    if (K <= 0) return ADSP_ERR_EMPTY_KERNEL;
+    if (block <= 0) block = std::max<int64_t>(next_pow2_ll(K), 256);
+    if (block_out) *block_out = block;
+    if (fft_out) *fft_out = next_pow2_ll(block + K - 1);
+    return ADSP_OK;
+}
+
+void adsp_trim_mode(int64_t la, int64_t lb, adsp_mode mode, int64_t *start, int64_t *len) {
+    int64_t s = 0, l = la + lb - 1;
+    if (mode == ADSP_MODE_SAME) { s = (lb - 1) / 2; l = la; }
+    else if (mode == ADSP_MODE_VALID) {
+        if (la >= lb) { s = lb - 1; l = la - s; }
+        else { s = la - 1; l = lb - s; }
+    }
+    if (start) *start = s;
+    if (len) *len = l;
+}
+
+int64_t adsp_lag_from_index(int64_t index, int64_t len_b) { return index - (len_b - 1); }
+int64_t adsp_index_from_lag(int64_t lag, int64_t len_b) { return lag + (len_b - 1); }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- one-shot implementations
+namespace {
+
+enum OneShot { OS_DIRECT, OS_CONVOLVE, OS_FFT, OS_CORRELATE, OS_CORRELATE_DIRECT, OS_CORRELATE_FFT };
+
+// a (n), b (m) host -> out (n+m-1) host.  `post`: 0 none, 1 divide by ||a||*||b||, 2 divide by out[n-1]
+template <typename T>
+adsp_status oneshot(adsp_ctx *ctx, OneShot op, const T *a, int64_t n, const T *b, int64_t m, T *out, int post) {
+    if (!ctx) return ADSP_ERR_INVALID_ARG;
+    const bool corr = (op == OS_CORRELATE || op == OS_CORRELATE_DIRECT || op == OS_CORRELATE_FFT);
+    if (corr) { if (n <= 0 || m <= 0) return ADSP_ERR_EMPTY_INPUT; }   // correlate.go:17-19
+    else {
+        if (n <= 0) return ADSP_ERR_EMPTY_INPUT;                       // conv.go:77-83,195-201
+        if (m <= 0) return ADSP_ERR_EMPTY_KERNEL;
+    }
+    if (!a || !b || !out) return ADSP_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ADSP_CUDA(cudaSetDevice(ctx->device));
+    const int64_t out_len = n + m - 1;
+    ADSP_TRY(ctx->d_in.reserve((size_t)n * sizeof(T)));
+    ADSP_TRY(ctx->d_tmp.reserve((size_t)m * sizeof(T) * 2));
+    ADSP_TRY(ctx->d_out.reserve((size_t)out_len * sizeof(T)));
+    T *da = (T *)ctx->d_in.p, *db = (T *)ctx->d_tmp.p, *dbr = db + m, *dout = (T *)ctx->d_out.p;
+    ADSP_CUDA(cudaMemcpyAsync(da, a, (size_t)n * sizeof(T), cudaMemcpyHostToDevice, ctx->main));
+    ADSP_CUDA(cudaMemcpyAsync(db, b, (size_t)m * sizeof(T), cudaMemcpyHostToDevice, ctx->main));
+    const T *dk = db;
+    if (corr) {  // reverse b: correlate.go:22-25
+        reverse_kernel<T><<<(unsigned)((m + 255) / 256), 256, 0, ctx->main>>>(db, m, m, dbr, m, 1);
+        count_launch(ctx);
+        dk = dbr;
+    }
+    bool use_direct = (op == OS_DIRECT || op == OS_CORRELATE_DIRECT);
+    const T *sig = da; int64_t sn = n; const T *ker = dk; int64_t km = m;
+    if (op == OS_CONVOLVE || op == OS_CORRELATE) {
+        if (m > n) { sig = dk; sn = m; ker = da; km = n; }   // conv.go:204-206 swap so the signal is longer
+        if (km <= 64) use_direct = true;                     // conv.go:209-211 (code wins over doc: <= 64)
+    }
+    if (use_direct) ADSP_TRY(direct_device<T>(ctx, sig, sn, 0, ker, km, 0, 1, dout, 0));
+    else ADSP_TRY(fft_convolve_device<T>(ctx, sig, sn, 1, 0, ker, km, dout, 0));
+    if (post) {
+        ADSP_TRY(ctx->d_small.reserve(64));
+        T *dden = (T *)ctx->d_small.p;
+        if (post == 1) { norm_product_kernel<T><<<1, 1024, 0, ctx->main>>>(da, n, db, m, dden); count_launch(ctx); }
+        else ADSP_CUDA(cudaMemcpyAsync(dden, dout + (n - 1), sizeof(T), cudaMemcpyDeviceToDevice, ctx->main));
+        scale_by_inverse_kernel<T><<<(unsigned)((out_len + 255) / 256), 256, 0, ctx->main>>>(dout, out_len, dden);
+        count_launch(ctx);
+    }
+    ADSP_CUDA(cudaMemcpyAsync(out, dout, (size_t)out_len * sizeof(T), cudaMemcpyDeviceToHost, ctx->main));
+    ADSP_CUDA(cudaStreamSynchronize(ctx->main));
+    return ADSP_OK;
+}
+
+template <typename T>
+adsp_status plan_create(adsp_ctx *ctx, PlanKind kind, const T *kernel, int64_t K, int64_t size_arg, adsp_plan **out) {
+    if (!out) return ADSP_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (!ctx) return ADSP_ERR_INVALID_ARG;
+    if (K <= 0 || !kernel) return ADSP_ERR_EMPTY_KERNEL;   // overlap_save.go:54-56, overlap_add.go:45-47
+    int64_t f = 0, s = 0, bsz = 0;
+    if (kind == PLAN_OLS) ADSP_TRY(adsp_ols_sizes(K, size_arg, &f, &s));
+    else ADSP_TRY(adsp_ola_sizes(K, size_arg, &bsz, &f));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ADSP_CUDA(cudaSetDevice(ctx->device));
+    adsp_plan *p = new adsp_plan();
+    p->ctx = ctx; p->kind = kind; p->prec = sizeof(T) == 8 ? ADSP_F64 : ADSP_F32; p->K = K;
+    p->ref_fft = f; p->ref_step = s; p->ref_block = bsz;
+    adsp_status st = plan_build<T>(p, kernel);
+    if (st != ADSP_OK) { adsp_plan_destroy(p); return st; }
+    *out = p;
+    return ADSP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+adsp_status adsp_direct(adsp_ctx *c, const double *a, int64_t n, const double *b, int64_t m, double *out) { return oneshot<double>(c, OS_DIRECT, a, n, b, m, out, 0); }
+adsp_status adsp_convolve(adsp_ctx *c, const double *a, int64_t n, const double *b, int64_t m, double *out) { return oneshot<double>(c, OS_CONVOLVE, a, n, b, m, out, 0); }
+adsp_status adsp_overlap_add_convolve(adsp_ctx *c, const double *s, int64_t n, const double *k, int64_t m, double *out) {
+    if (m <= 0) return ADSP_ERR_EMPTY_KERNEL;   // overlap_add.go:222-224 (kernel checked first)
+    return oneshot<double>(c, OS_FFT, s, n, k, m, out, 0);
+}
+adsp_status adsp_overlap_save_convolve(adsp_ctx *c, const double *s, int64_t n, const double *k, int64_t m, double *out) {
+    if (m <= 0) return ADSP_ERR_EMPTY_KERNEL;   // overlap_save.go:314-316
+    return oneshot<double>(c, OS_FFT, s, n, k, m, out, 0);
+}
+adsp_status adsp_correlate(adsp_ctx *c, const double *a, int64_t n, const double *b, int64_t m, double *out) { return oneshot<double>(c, OS_CORRELATE, a, n, b, m, out, 0); }
+adsp_status adsp_correlate_direct(adsp_ctx *c, const double *a, int64_t n, const double *b, int64_t m, double *out) { return oneshot<double>(c, OS_CORRELATE_DIRECT, a, n, b, m, out, 0); }
+adsp_status adsp_correlate_fft(adsp_ctx *c, const double *a, int64_t n, const double *b, int64_t m, double *out) { return oneshot<double>(c, OS_CORRELATE_FFT, a, n, b, m, out, 0); }
+adsp_status adsp_correlate_normalized(adsp_ctx *c, const double *a, int64_t n, const double *b, int64_t m, double *out) { return oneshot<double>(c, OS_CORRELATE, a, n, b, m, out, 1); }
+adsp_status adsp_autocorrelate_normalized(adsp_ctx *c, const double *a, int64_t n, double *out) { return oneshot<double>(c, OS_CORRELATE, a, n, a, n, out, 2); }
+adsp_status adsp_direct_f32(adsp_ctx *c, const float *a, int64_t n, const float *b, int64_t m, float *out) { return oneshot<float>(c, OS_DIRECT, a, n, b, m, out, 0); }
+adsp_status adsp_convolve_f32(adsp_ctx *c, const float *a, int64_t n, const float *b, int64_t m, float *out) { return oneshot<float>(c, OS_CONVOLVE, a, n, b, m, out, 0); }
+adsp_status adsp_correlate_f32(adsp_ctx *c, const float *a, int64_t n, const float *b, int64_t m, float *out) { return oneshot<float>(c, OS_CORRELATE, a, n, b, m, out, 0); }
+
+adsp_status adsp_direct_circular(adsp_ctx *ctx, const double *a, int64_t n, const double *b, int64_t m, double *out) {
+    if (!ctx) return ADSP_ERR_INVALID_ARG;
+    if (n <= 0 || m <= 0) return ADSP_ERR_EMPTY_INPUT;        // conv.go:159-161
+    if (n != m) return ADSP_ERR_LENGTH_MISMATCH;              // conv.go:163-165
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ADSP_CUDA(cudaSetDevice(ctx->device));
+    ADSP_TRY(ctx->d_in.reserve((size_t)n * 2 * sizeof(double)));
+    ADSP_TRY(ctx->d_out.reserve((size_t)n * sizeof(double)));
+    double *da = (double *)ctx->d_in.p, *db = da + n, *dout = (double *)ctx->d_out.p;
+    ADSP_CUDA(cudaMemcpyAsync(da, a, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->main));
+    ADSP_CUDA(cudaMemcpyAsync(db, b, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->main));
+    direct_circular_kernel<double><<<(unsigned)((n + 127) / 128), 128, 0, ctx->main>>>(da, db, dout, n);
+    count_launch(ctx);
+    ADSP_CUDA(cudaMemcpyAsync(out, dout, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->main));
+    ADSP_CUDA(cudaStreamSynchronize(ctx->main));
+    return ADSP_OK;
+}
+
+adsp_status adsp_find_peak(adsp_ctx *ctx, const double *corr, int64_t len, int64_t *index, double *value) {
+    if (!ctx || !index || !value) return ADSP_ERR_INVALID_ARG;
+    if (len <= 0) { *index = -1; *value = 0; return ADSP_OK; }   // correlate.go:201-203
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ADSP_CUDA(cudaSetDevice(ctx->device));
+    ADSP_TRY(ctx->d_in.reserve((size_t)len * sizeof(double)));
+    ADSP_TRY(ctx->d_tmp.reserve(64));
+    ADSP_CUDA(cudaMemcpyAsync(ctx->d_in.p, corr, (size_t)len * sizeof(double), cudaMemcpyHostToDevice, ctx->main));
+    double *dv = (double *)ctx->d_tmp.p;
+    long long *di = (long long *)(dv + 1);
+    ADSP_TRY(peak_device<double>(ctx, (const double *)ctx->d_in.p, len, len, 1, dv, di));
+    long long hi = -1; double hv = 0;
+    ADSP_CUDA(cudaMemcpyAsync(&hv, dv, sizeof(double), cudaMemcpyDeviceToHost, ctx->main));
+    ADSP_CUDA(cudaMemcpyAsync(&hi, di, sizeof(long long), cudaMemcpyDeviceToHost, ctx->main));
+    ADSP_CUDA(cudaStreamSynchronize(ctx->main));
+    *index = hi; *value = hv;
+    return ADSP_OK;
+}
+
+// ---------------------------------------------------------------- batched one-shots
+adsp_status adsp_direct_batch_device(adsp_ctx *ctx, const void *a, int64_t n, int64_t a_stride, const void *b, int64_t m,
+                                     int64_t b_stride, int64_t batch, void *out, int64_t out_stride, adsp_precision prec) {
+    if (!ctx) return ADSP_ERR_INVALID_ARG;
+    if (n <= 0) return ADSP_ERR_EMPTY_INPUT;
+    if (m <= 0) return ADSP_ERR_EMPTY_KERNEL;
+    if (batch <= 0) return ADSP_OK;
+    ADSP_CUDA(cudaSetDevice(ctx->device));
+    if (prec == ADSP_F64) return direct_device<double>(ctx, (const double *)a, n, a_stride, (const double *)b, m, b_stride, batch, (double *)out, out_stride);
+    return direct_device<float>(ctx, (const float *)a, n, a_stride, (const float *)b, m, b_stride, batch, (float *)out, out_stride);
+}
+
+adsp_status adsp_direct_batch(adsp_ctx *ctx, const double *a, int64_t n, int64_t a_stride, const double *b, int64_t m,
+                              int64_t b_stride, int64_t batch, double *out, int64_t out_stride) {
+    if (!ctx) return ADSP_ERR_INVALID_ARG;
+    if (n <= 0) return ADSP_ERR_EMPTY_INPUT;
+    if (m <= 0) return ADSP_ERR_EMPTY_KERNEL;
+    if (batch <= 0) return ADSP_OK;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ADSP_CUDA(cudaSetDevice(ctx->device));
+    const int64_t out_len = n + m - 1;
+    const int64_t nb = b_stride == 0 ? 1 : batch;
+    ADSP_TRY(ctx->d_in.reserve((size_t)n * batch * sizeof(double)));
+    ADSP_TRY(ctx->d_tmp.reserve((size_t)m * nb * sizeof(double)));
+    ADSP_TRY(ctx->d_out.reserve((size_t)out_len * batch * sizeof(double)));
+    ADSP_TRY(copy2d(ctx, ctx->d_in.p, (size_t)n * 8, a, (size_t)a_stride * 8, (size_t)n * 8, (size_t)batch, cudaMemcpyHostToDevice));
+    ADSP_TRY(copy2d(ctx, ctx->d_tmp.p, (size_t)m * 8, b, (size_t)(b_stride ? b_stride : m) * 8, (size_t)m * 8, (size_t)nb, cudaMemcpyHostToDevice));
+    ADSP_TRY(direct_device<double>(ctx, (const double *)ctx->d_in.p, n, n, (const double *)ctx->d_tmp.p, m, b_stride ? m : 0, batch,
+                                   (double *)ctx->d_out.p, out_len));
+    ADSP_TRY(copy2d(ctx, out, (size_t)out_stride * 8, ctx->d_out.p, (size_t)out_len * 8, (size_t)out_len * 8, (size_t)batch, cudaMemcpyDeviceToHost));
+    ADSP_CUDA(cudaStreamSynchronize(ctx->main));
+    return ADSP_OK;
+}
+
+}  // extern "C"
+
+// correlate batch: every pair has its own kernel (reversed b), so spectra are per pair.
+// v1: loop over pairs with the one-shot FFT engine (sharing the transform tables); the peak search
+// runs batched at the end when the full outputs are kept, per pair otherwise.
+namespace {
+template <typename T>
+adsp_status correlate_batch_dev(adsp_ctx *ctx, const T *a, int64_t n, int64_t a_stride, const T *b, int64_t m,
+                                int64_t b_stride, int64_t pairs, T *out, int64_t out_stride, long long *peak_i, T *peak_v) {
+    const int64_t out_len = n + m - 1;
+    ADSP_TRY(ctx->d_tmp.reserve((size_t)(m + (out ? 0 : out_len)) * sizeof(T)));
+    T *dbr = (T *)ctx->d_tmp.p;
+    T *tmp_out = out ? nullptr : dbr + m;
+    for (int64_t p = 0; p < pairs; p++) {
+        const T *ap = a + p * a_stride;
+        const T *bp = b + p * b_stride;
+        T *op = out ? out + p * out_stride : tmp_out;
+        reverse_kernel<T><<<(unsigned)((m + 255) / 256), 256, 0, ctx->main>>>(bp, m, m, dbr, m, 1);
+        count_launch(ctx);
+        const T *sig = ap; int64_t sn = n; const T *ker = dbr; int64_t km = m;
+        if (m > n) { sig = dbr; sn = m; ker = ap; km = n; }
+        if (km <= 64) ADSP_TRY(direct_device<T>(ctx, sig, sn, 0, ker, km, 0, 1, op, 0));
+        else ADSP_TRY(fft_convolve_device<T>(ctx, sig, sn, 1, 0, ker, km, op, 0));
+        if (peak_i && peak_v && !out) ADSP_TRY(peak_device<T>(ctx, op, out_len, out_len, 1, peak_v + p, peak_i + p));
+    }
+    if (peak_i && peak_v && out) ADSP_TRY(peak_device<T>(ctx, out, out_len, out_stride, pairs, peak_v, peak_i));
+    return ADSP_OK;
+}
+}  // namespace
+
+extern "C" {
+
+adsp_status adsp_correlate_batch_device(adsp_ctx *ctx, const void *a, int64_t n, int64_t a_stride, const void *b, int64_t m,
+                                        int64_t b_stride, int64_t pairs, void *out, int64_t out_stride,
+                                        void *peak_index_dev, void *peak_value_dev, adsp_precision prec) {
+    if (!ctx) return ADSP_ERR_INVALID_ARG;
+    if (n <= 0 || m <= 0) return ADSP_ERR_EMPTY_INPUT;
+    if (pairs <= 0) return ADSP_OK;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ADSP_CUDA(cudaSetDevice(ctx->device));
+    if (prec == ADSP_F64)
+        return correlate_batch_dev<double>(ctx, (const double *)a, n, a_stride, (const double *)b, m, b_stride, pairs,
+                                           (double *)out, out_stride, (long long *)peak_index_dev, (double *)peak_value_dev);
+    return correlate_batch_dev<float>(ctx, (const float *)a, n, a_stride, (const float *)b, m, b_stride, pairs, (float *)out,
+                                      out_stride, (long long *)peak_index_dev, (float *)peak_value_dev);
+}
+
+adsp_status adsp_correlate_batch(adsp_ctx *ctx, const double *a, int64_t n, int64_t a_stride, const double *b, int64_t m,
+                                 int64_t b_stride, int64_t pairs, double *out, int64_t out_stride, int64_t *peak_index,
+                                 double *peak_value) {
+    if (!ctx) return ADSP_ERR_INVALID_ARG;
+    if (n <= 0 || m <= 0) return ADSP_ERR_EMPTY_INPUT;
+    if (pairs <= 0) return ADSP_OK;
+    const int64_t out_len = n + m - 1;
+    void *da = nullptr, *db = nullptr, *dout = nullptr, *dpi = nullptr, *dpv = nullptr;
+    adsp_status st = ADSP_OK;
+    ADSP_CUDA(cudaSetDevice(ctx->device));
+    do {
+        if ((st = adsp_device_alloc(ctx, (size_t)n * pairs * 8, &da)) != ADSP_OK) break;
+        if ((st = adsp_device_alloc(ctx, (size_t)m * pairs * 8, &db)) != ADSP_OK) break;
+        if (out && (st = adsp_device_alloc(ctx, (size_t)out_len * pairs * 8, &dout)) != ADSP_OK) break;
+        if ((st = adsp_device_alloc(ctx, (size_t)pairs * 8, &dpi)) != ADSP_OK) break;
+        if ((st = adsp_device_alloc(ctx, (size_t)pairs * 8, &dpv)) != ADSP_OK) break;
+        if ((st = copy2d(ctx, da, (size_t)n * 8, a, (size_t)a_stride * 8, (size_t)n * 8, (size_t)pairs, cudaMemcpyHostToDevice)) != ADSP_OK) break;
+        if ((st = copy2d(ctx, db, (size_t)m * 8, b, (size_t)b_stride * 8, (size_t)m * 8, (size_t)pairs, cudaMemcpyHostToDevice)) != ADSP_OK) break;
+        st = adsp_correlate_batch_device(ctx, da, n, n, db, m, m, pairs, dout, out_len, (peak_index && peak_value) ? dpi : nullptr,
+                                         (peak_index && peak_value) ? dpv : nullptr, ADSP_F64);
+        if (st != ADSP_OK) break;
+        if (out && (st = copy2d(ctx, out, (size_t)out_stride * 8, dout, (size_t)out_len * 8, (size_t)out_len * 8, (size_t)pairs, cudaMemcpyDeviceToHost)) != ADSP_OK) break;
+        if (peak_index && peak_value) {
+            cudaMemcpyAsync(peak_index, dpi, (size_t)pairs * 8, cudaMemcpyDeviceToHost, ctx->main);
+            cudaMemcpyAsync(peak_value, dpv, (size_t)pairs * 8, cudaMemcpyDeviceToHost, ctx->main);
+        }
+        cudaError_t e = cudaStreamSynchronize(ctx->main);
+        if (e != cudaSuccess) st = cuda_fail(e, "sync", __FILE__, __LINE__);
+    } while (0);
+    adsp_device_free(ctx, da); adsp_device_free(ctx, db); adsp_device_free(ctx, dout); adsp_device_free(ctx, dpi); adsp_device_free(ctx, dpv);
+    return st;
+}
+
+// ---------------------------------------------------------------- plans
+adsp_status adsp_overlap_save_create(adsp_ctx *ctx, const void *kernel, int64_t K, int64_t fft_size, adsp_precision prec, adsp_plan **out) {
+    if (prec == ADSP_F64) return plan_create<double>(ctx, PLAN_OLS, (const double *)kernel, K, fft_size, out);
+    return plan_create<float>(ctx, PLAN_OLS, (const float *)kernel, K, fft_size, out);
+}
+adsp_status adsp_overlap_add_create(adsp_ctx *ctx, const void *kernel, int64_t K, int64_t block_size, adsp_precision prec, adsp_plan **out) {
+    if (prec == ADSP_F64) return plan_create<double>(ctx, PLAN_OLA, (const double *)kernel, K, block_size, out);
+    return plan_create<float>(ctx, PLAN_OLA, (const float *)kernel, K, block_size, out);
+}
+
+void adsp_plan_destroy(adsp_plan *p) {
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->main);
+    for (auto &f : p->fc64) f.destroy();
+    for (auto &f : p->fc32) f.destroy();
+    p->hist[0].release(); p->hist[1].release(); p->blk_in.release(); p->blk_out.release();
+    delete p;
+}
+
+int64_t adsp_plan_kernel_len(const adsp_plan *p) { return p ? p->K : 0; }
+int64_t adsp_plan_fft_size(const adsp_plan *p) { return p ? p->ref_fft : 0; }
+int64_t adsp_plan_step_size(const adsp_plan *p) { return p ? p->ref_step : 0; }
+int64_t adsp_plan_block_size(const adsp_plan *p) { return p ? p->ref_block : 0; }
+void adsp_plan_internal_geometry(const adsp_plan *p, int64_t *fft_n, int64_t *n1, int64_t *n2, int64_t *step, int64_t *parts) {
+    if (!p) return;
+    if (fft_n) *fft_n = p->ch.N;
+    if (n1) *n1 = p->ch.N1;
+    if (n2) *n2 = p->ch.N2;
+    if (step) *step = p->ch.S;
+    if (parts) *parts = p->ch.parts;
+}
+
+adsp_status adsp_plan_process_device(adsp_plan *p, const void *in, int64_t n, int64_t channels, int64_t in_stride,
+                                     void *out, int64_t out_stride) {
+    if (!p || p->kind == PLAN_PART) return ADSP_ERR_INVALID_ARG;
+    if (n <= 0) return ADSP_ERR_EMPTY_INPUT;
+    if (channels <= 0) return ADSP_OK;
+    if (!in || !out) return ADSP_ERR_INVALID_ARG;
+    ADSP_CUDA(cudaSetDevice(p->ctx->device));
+    if (p->prec == ADSP_F64) return plan_run_device<double>(p, (const double *)in, n, channels, in_stride, (double *)out, out_stride);
+    return plan_run_device<float>(p, (const float *)in, n, channels, in_stride, (float *)out, out_stride);
+}
+
+adsp_status adsp_plan_process_batch(adsp_plan *p, const void *in, int64_t n, int64_t channels, int64_t in_stride,
+                                    void *out, int64_t out_stride) {
+    if (!p || p->kind == PLAN_PART) return ADSP_ERR_INVALID_ARG;
+    if (n <= 0) return ADSP_ERR_EMPTY_INPUT;        // overlap_save.go:127-129
+    if (channels <= 0) return ADSP_OK;
+    if (!in || !out) return ADSP_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(p->ctx->mu);
+    ADSP_CUDA(cudaSetDevice(p->ctx->device));
+    if (p->prec == ADSP_F64) return plan_run_host<double>(p, (const double *)in, n, channels, in_stride, (double *)out, out_stride);
+    return plan_run_host<float>(p, (const float *)in, n, channels, in_stride, (float *)out, out_stride);
+}
+
+adsp_status adsp_plan_process(adsp_plan *p, const void *in, int64_t n, void *out, int64_t out_len) {
+    if (!p) return ADSP_ERR_INVALID_ARG;
+    if (out_len != n + p->K - 1 && n > 0) {           // overlap_save.go:259-262
+        set_error("conv: buffer length mismatch: expected " + std::to_string(n + p->K - 1) + ", got " + std::to_string(out_len));
+        return ADSP_ERR_LENGTH_MISMATCH;
+    }
+    return adsp_plan_process_batch(p, in, n, 1, n, out, out_len);
+}
+
+adsp_status adsp_plan_sync(adsp_plan *p) { return p ? adsp_ctx_sync(p->ctx) : ADSP_ERR_INVALID_ARG; }
+
+}  // extern "C"
+
+// ================================================================ partitioned (streaming) convolution
+namespace {
+
+int trunc_log2(long long n) { int r = 0; while (n > 1) { n >>= 1; r++; } return r; }
+long long bits_upto(int n) { return (2LL << n) - 1; }
+
+// Stage layout of the reference's non-uniform partitioning (reported by StageCount/StageInfo).
+// Follows the arithmetic of partitionIR, dsp/conv/partitioned.go:269-332.
+std::vector<PartStage> partition_layout(long long kernel_len_padded, int min_order, int max_order) {
+    const long long min_block = 1LL << min_order;
+    int max_ir = trunc_log2(kernel_len_padded + min_block) - 1;
+    long long res = kernel_len_padded - (bits_upto(max_ir) - bits_upto(min_order - 1));
+    if (res > 0 && ((res >> max_ir) & 1) == 0 && max_ir > min_order) max_ir--;
+    if (max_ir > max_order) max_ir = max_order;
+    res = kernel_len_padded - (bits_upto(max_ir) - bits_upto(min_order - 1));
+    std::vector<PartStage> st;
+    long long start = 0;
+    for (int order = min_order; order < max_ir; order++) {
+        const int count = 1 + (int)((res >> order) & 1);
+        st.push_back({1 << order, count, (int)start});
+        start += (long long)count << order;
+        res -= (long long)(count - 1) << order;
+    }
+    int count = 1;
+    if (max_ir > 0) count = (int)std::max<long long>(1, 1 + res / (1LL << max_ir));
+    st.push_back({1 << max_ir, count, (int)start});
+    return st;
+}
+
+// ProcessBlock semantics (partitioned.go:348-396): output sample t of the stream equals the full
+// linear convolution at t - latency (zero before).  The device keeps the last K-1+latency input
+// samples; a call with n samples evaluates n "valid" outputs from [history | block].
+template <typename T>
+adsp_status part_process(adsp_plan *p, const T *in, int64_t n, T *out) {
+    adsp_ctx *ctx = p->ctx;
+    const long long HL = p->hist_len;  // K - 1 + latency
+    ADSP_TRY(p->blk_in.reserve((size_t)(HL + n) * sizeof(T)));
+    ADSP_TRY(p->blk_out.reserve((size_t)n * sizeof(T)));
+    T *buf = (T *)p->blk_in.p;
+    T *hist = (T *)p->hist[p->hist_cur].p;
+    T *hist_next = (T *)p->hist[p->hist_cur ^ 1].p;
+    ADSP_CUDA(cudaMemcpyAsync(buf, hist, (size_t)HL * sizeof(T), cudaMemcpyDeviceToDevice, ctx->main));
+    ADSP_CUDA(cudaMemcpyAsync(buf + HL, in, (size_t)n * sizeof(T), cudaMemcpyHostToDevice, ctx->main));
+    // outputs y[t0 + o], o < n, t0 = pos - latency; buf[0] is x[t0 - (K-1)]
+    auto &v = plan_fc<T>(p);
+    T *dout = (T *)p->blk_out.p;
+    if (v.size() == 1) {
+        ADSP_TRY(v[0].run(buf, HL + n, 1, 0, dout, 0, n, p->K - 1, 0, false));
+    } else {
+        ADSP_CUDA(cudaMemsetAsync(dout, 0, (size_t)n * sizeof(T), ctx->main));
+        for (size_t i = 0; i < v.size(); i++) {
+            const long long k0 = (long long)i * p->ch.part_len;
+            // partition i sees the input delayed by k0: shift the window start back by k0
+            ADSP_TRY(v[i].run(buf, HL + n, 1, 0, dout, 0, n, p->K - 1 - k0, 0, true));
+        }
+    }
+    ADSP_CUDA(cudaMemcpyAsync(out, dout, (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, ctx->main));
+    ADSP_CUDA(cudaMemcpyAsync(hist_next, buf + n, (size_t)HL * sizeof(T), cudaMemcpyDeviceToDevice, ctx->main));
+    p->hist_cur ^= 1;
+    ADSP_CUDA(cudaStreamSynchronize(ctx->main));
+    return ADSP_OK;
+}
+
+template <typename T>
+adsp_status part_create(adsp_ctx *ctx, const T *kernel, int64_t K, int min_order, int max_order, adsp_plan **out) {
+    if (!out) return ADSP_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (!ctx) return ADSP_ERR_INVALID_ARG;
+    if (K <= 0 || !kernel) return ADSP_ERR_EMPTY_IR;                          // partitioned.go:215-217
+    if (min_order < 1) { set_error("conv: invalid block order: minBlockOrder must be >= 1"); return ADSP_ERR_INVALID_BLOCK_ORDER; }
+    if (max_order < min_order) { set_error("conv: invalid block order: maxBlockOrder must be >= minBlockOrder"); return ADSP_ERR_INVALID_BLOCK_ORDER; }
+    if (min_order > 24) { set_error("conv: invalid block order: too large"); return ADSP_ERR_INVALID_BLOCK_ORDER; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ADSP_CUDA(cudaSetDevice(ctx->device));
+    adsp_plan *p = new adsp_plan();
+    p->ctx = ctx; p->kind = PLAN_PART; p->prec = sizeof(T) == 8 ? ADSP_F64 : ADSP_F32; p->K = K;
+    p->latency = 1 << min_order; p->min_order = min_order; p->max_order = max_order;
+    const long long padded = ((K + p->latency - 1) / p->latency) * p->latency;
+    p->stages = partition_layout(padded, min_order, max_order);
+    p->hist_len = K - 1 + p->latency;
+    adsp_status st = plan_build<T>(p, kernel);
+    for (int i = 0; i < 2 && st == ADSP_OK; i++) {
+        st = p->hist[i].reserve((size_t)p->hist_len * sizeof(T));
+        if (st == ADSP_OK && cudaMemsetAsync(p->hist[i].p, 0, (size_t)p->hist_len * sizeof(T), ctx->main) != cudaSuccess) st = ADSP_ERR_CUDA;
+    }
+    if (st != ADSP_OK) { adsp_plan_destroy(p); return st; }
+    *out = p;
+    return ADSP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+adsp_status adsp_partitioned_create(adsp_ctx *ctx, const void *kernel, int64_t K, int min_order, int max_order,
+                                    adsp_precision prec, adsp_plan **out) {
+    if (prec == ADSP_F64) return part_create<double>(ctx, (const double *)kernel, K, min_order, max_order, out);
+    return part_create<float>(ctx, (const float *)kernel, K, min_order, max_order, out);
+}
+
+adsp_status adsp_partitioned_process_block(adsp_plan *p, const void *in, int64_t n, void *out, int64_t n_out) {
+    if (!p || p->kind != PLAN_PART) return ADSP_ERR_INVALID_ARG;
+    if (n != n_out) {                                                        // partitioned.go:349-352
+        set_error("conv: buffer length mismatch: input length " + std::to_string(n) + " != output length " + std::to_string(n_out));
+        return ADSP_ERR_LENGTH_MISMATCH;
+    }
+    if (n <= 0) return ADSP_OK;
+    if (!in || !out) return ADSP_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(p->ctx->mu);
+    ADSP_CUDA(cudaSetDevice(p->ctx->device));
+    if (p->prec == ADSP_F64) return part_process<double>(p, (const double *)in, n, (double *)out);
+    return part_process<float>(p, (const float *)in, n, (float *)out);
+}
+
+void adsp_plan_reset(adsp_plan *p) {
+    if (!p) return;
+    if (p->kind == PLAN_PART) {                                              // partitioned.go:399-407
+        cudaSetDevice(p->ctx->device);
+        const size_t es = p->prec == ADSP_F64 ? 8 : 4;
+        for (int i = 0; i < 2; i++) cudaMemsetAsync(p->hist[i].p, 0, (size_t)p->hist_len * es, p->ctx->main);
+        cudaStreamSynchronize(p->ctx->main);
+    }
+    // OverlapSave/OverlapAdd keep no state across Process calls (overlap_save.go:136-138, overlap_add.go:185-187)
+}
+
+int adsp_partitioned_latency(const adsp_plan *p) { return p ? p->latency : 0; }
+int adsp_partitioned_stage_count(const adsp_plan *p) { return p ? (int)p->stages.size() : 0; }
+adsp_status adsp_partitioned_stage_info(const adsp_plan *p, int index, int *part_size, int *block_count) {
+    if (!p) return ADSP_ERR_INVALID_ARG;
+    if (index < 0 || index >= (int)p->stages.size()) {
+        set_error("conv: stage index out of range: index " + std::to_string(index) + ", have " + std::to_string(p->stages.size()) + " stages");
+        return ADSP_ERR_STAGE_INDEX;
+    }
+    if (part_size) *part_size = p->stages[(size_t)index].part_size;
+    if (block_count) *block_count = p->stages[(size_t)index].count;
+    return ADSP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,117 @@
+// engine.cuh -- host-side engine shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/algodsp_cuda.h"
+#include "conv_kernels.cuh"
+
+namespace adsp {
+
+void set_error(const std::string &msg);
+adsp_status cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define ADSP_CUDA(call)                                                        \
+    do {                                                                       \
+        cudaError_t e__ = (call);                                              \
+        if (e__ != cudaSuccess) return ::adsp::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+#define ADSP_TRY(call)                       \
+    do {                                     \
+        adsp_status s__ = (call);            \
+        if (s__ != ADSP_OK) return s__;      \
+    } while (0)
+
+constexpr int kWorkerStreams = 3;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    adsp_status reserve(size_t bytes);
+    void release();
+};
+
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    adsp_status reserve(size_t bytes);
+    void release();
+};
+
+// Internal transform geometry chosen for a kernel length (free to differ from the reference's
+// FFTSize()/StepSize(), which are reported from the reference formulas).
+struct FftChoice {
+    long long N = 0;       // transform length
+    int N1 = 1, N2 = 0;    // N = N1*N2 (N1 == 1: single-kernel path)
+    int lgN = 0;
+    long long D = 0, S = 0;  // discard / step per block
+    int parts = 1;           // IR partitions (only when K-1 exceeds half the largest transform)
+    long long part_len = 0;  // taps per partition
+};
+
+FftChoice choose_fft(long long K);
+
+}  // namespace adsp
+
+struct adsp_ctx {
+    int device = 0;
+    int sm_count = 0;
+    size_t l2_bytes = 0;
+    cudaStream_t main = nullptr;
+    cudaStream_t worker[adsp::kWorkerStreams] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr;
+    cudaEvent_t ev_join[adsp::kWorkerStreams] = {nullptr, nullptr, nullptr};
+    std::mutex mu;  // serialises calls that use the context's staging / scratch buffers
+    std::map<std::pair<int, int>, void *> tw_tables;                     // (L, prec) -> device table
+    std::map<std::pair<int, int>, std::pair<void *, void *>> tw4_tables;  // (lgN, prec) -> (hi, lo)
+    adsp::DevBuf scratch;              // four-step intermediates (L2 resident by construction)
+    adsp::DevBuf d_in, d_out, d_k, d_tmp, d_small;
+    adsp::PinnedBuf h_in[2], h_out[2], h_small;
+    std::atomic<uint64_t> launches{0};
+    size_t scratch_budget = 0;  // bytes of scratch allowed in flight (fits L2)
+};
+
+namespace adsp {
+
+// Device-resident FFT convolver for one (partition of an) impulse response.
+template <typename T> struct FftConv {
+    adsp_ctx *ctx = nullptr;
+    long long K = 0;  // taps of this partition
+    FftChoice ch;
+    cpx<T> *H = nullptr;  // cached spectrum (four-step order, scaled 1/N)
+    const cpx<T> *tw_rows = nullptr, *tw_cols = nullptr, *tw_hi = nullptr, *tw_lo = nullptr;
+
+    adsp_status init(adsp_ctx *c, const T *d_kernel, long long K_, const FftChoice &choice);
+    void destroy();
+    // y[ch][out_shift + o] (=|+=) conv(x[ch], h)[o + in_shift'], see ConvGeom
+    adsp_status run(const T *d_x, long long n, long long channels, long long in_stride, T *d_y,
+                    long long out_stride, long long out_len, long long in_shift, long long out_shift,
+                    bool accumulate);
+};
+
+template <typename T> adsp_status get_tw_table(adsp_ctx *ctx, int L, const cpx<T> **out);
+template <typename T> adsp_status get_tw4_tables(adsp_ctx *ctx, int lgN, const cpx<T> **hi, const cpx<T> **lo);
+
+// full linear convolution of `channels` signals with one kernel (device pointers), any K:
+// splits long kernels into partitions.  Builds the spectra on the fly (one-shot use).
+template <typename T>
+adsp_status fft_convolve_device(adsp_ctx *ctx, const T *d_x, long long n, long long channels, long long in_stride,
+                                const T *d_k, long long K, T *d_y, long long out_stride);
+
+template <typename T>
+adsp_status direct_device(adsp_ctx *ctx, const T *d_a, long long n, long long a_stride, const T *d_b, long long m,
+                          long long b_stride, long long batch, T *d_out, long long out_stride);
+
+inline void count_launch(adsp_ctx *ctx, int n = 1) { ctx->launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+}  // namespace adsp

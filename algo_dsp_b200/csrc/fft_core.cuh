@@ -1,0 +1,197 @@
+// fft_core.cuh -- register/shared-memory Stockham FFT building blocks for sm_100a.
+//
+// Replaces the third-party CPU FFT the reference calls (algo-fft Plan.Forward/Inverse,
+// call sites dsp/conv/overlap_save.go:166,177; overlap_add.go:138,149; correlate.go:143-164;
+// partitioned.go:145,154,170).  Contract kept: forward unnormalised, inverse 1/N (the 1/N is
+// folded into the cached IR spectrum by the callers).
+//
+// Design: every thread owns E=16 complex points of one transform in registers.  A transform of
+// length L = R0 * 16^P (R0 in {2,4,8,16}) is P+1 passes: one twiddle-free radix-R0 pass, then P
+// radix-16 passes, exchanging through shared memory between passes (Stockham autosort, so the
+// result is in natural order and thread j again owns points j + q*L/16 -- the same ownership as
+// on entry, which lets forward -> spectral multiply -> inverse chain in registers).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace adsp {
+
+template <typename T> struct cpx_of;
+template <> struct cpx_of<double> { using type = double2; };
+template <> struct cpx_of<float> { using type = float2; };
+template <typename T> using cpx = typename cpx_of<T>::type;
+
+template <typename C> __device__ __forceinline__ C cadd(C a, C b) { C r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
+template <typename C> __device__ __forceinline__ C csub(C a, C b) { C r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
+template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
+    C r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
+}
+// a * w (forward) or a * conj(w) (inverse)
+template <bool INV, typename C> __device__ __forceinline__ C cmul_tw(C a, C w) {
+    C r;
+    if (INV) { r.x = a.x * w.x + a.y * w.y; r.y = a.y * w.x - a.x * w.y; }
+    else     { r.x = a.x * w.x - a.y * w.y; r.y = a.x * w.y + a.y * w.x; }
+    return r;
+}
+// multiply by -i (forward) / +i (inverse)
+template <bool INV, typename C> __device__ __forceinline__ C mul_mi(C a) {
+    C r;
+    if (INV) { r.x = -a.y; r.y = a.x; }
+    else     { r.x = a.y;  r.y = -a.x; }
+    return r;
+}
+
+// ---------------------------------------------------------------- small DFTs in registers
+template <bool INV, typename C> __device__ __forceinline__ void dft2(C &a0, C &a1) {
+    C t = csub(a0, a1); a0 = cadd(a0, a1); a1 = t;
+}
+template <bool INV, typename C> __device__ __forceinline__ void dft4(C &a0, C &a1, C &a2, C &a3) {
+    C t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = mul_mi<INV>(csub(a1, a3));
+    a0 = cadd(t0, t2); a1 = cadd(t1, t3); a2 = csub(t0, t2); a3 = csub(t1, t3);
+}
+
+template <typename C> struct real_of;
+template <> struct real_of<double2> { using type = double; };
+template <> struct real_of<float2> { using type = float; };
+
+template <bool INV, typename C> __device__ __forceinline__ C mkc(double re, double im_fwd) {
+    using T = typename real_of<C>::type;
+    C r; r.x = (T)re; r.y = (T)(INV ? -im_fwd : im_fwd); return r;
+}
+
+// v: R elements at stride S (compile time), natural order in and out.
+template <int R, int S, bool INV, typename C> struct Dft;
+
+template <int S, bool INV, typename C> struct Dft<2, S, INV, C> {
+    static __device__ __forceinline__ void run(C *v) { dft2<INV>(v[0], v[S]); }
+};
+template <int S, bool INV, typename C> struct Dft<4, S, INV, C> {
+    static __device__ __forceinline__ void run(C *v) { dft4<INV>(v[0], v[S], v[2 * S], v[3 * S]); }
+};
+template <int S, bool INV, typename C> struct Dft<8, S, INV, C> {
+    static __device__ __forceinline__ void run(C *v) {
+        constexpr double h = 0.70710678118654752440;
+        C y0[4] = { v[0], v[2 * S], v[4 * S], v[6 * S] };
+        C y1[4] = { v[S], v[3 * S], v[5 * S], v[7 * S] };
+        dft4<INV>(y0[0], y0[1], y0[2], y0[3]);
+        dft4<INV>(y1[0], y1[1], y1[2], y1[3]);
+        y1[1] = cmul(y1[1], mkc<INV, C>(h, -h));
+        y1[2] = mul_mi<INV>(y1[2]);
+        y1[3] = cmul(y1[3], mkc<INV, C>(-h, -h));
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            v[k * S] = cadd(y0[k], y1[k]);
+            v[(k + 4) * S] = csub(y0[k], y1[k]);
+        }
+    }
+};
+template <int S, bool INV, typename C> struct Dft<16, S, INV, C> {
+    static __device__ __forceinline__ void run(C *v) {
+        constexpr double h = 0.70710678118654752440;
+        constexpr double c1 = 0.92387953251128675613;  // cos(pi/8)
+        constexpr double s1 = 0.38268343236508977173;  // sin(pi/8)
+        C y[4][4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            y[q][0] = v[q * S]; y[q][1] = v[(q + 4) * S]; y[q][2] = v[(q + 8) * S]; y[q][3] = v[(q + 12) * S];
+            dft4<INV>(y[q][0], y[q][1], y[q][2], y[q][3]);
+        }
+        // y[q][k] *= W16^(q*k)
+        y[1][1] = cmul(y[1][1], mkc<INV, C>(c1, -s1));
+        y[1][2] = cmul(y[1][2], mkc<INV, C>(h, -h));
+        y[1][3] = cmul(y[1][3], mkc<INV, C>(s1, -c1));
+        y[2][1] = cmul(y[2][1], mkc<INV, C>(h, -h));
+        y[2][2] = mul_mi<INV>(y[2][2]);
+        y[2][3] = cmul(y[2][3], mkc<INV, C>(-h, -h));
+        y[3][1] = cmul(y[3][1], mkc<INV, C>(s1, -c1));
+        y[3][2] = cmul(y[3][2], mkc<INV, C>(-h, -h));
+        y[3][3] = cmul(y[3][3], mkc<INV, C>(-c1, s1));
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            dft4<INV>(y[0][k], y[1][k], y[2][k], y[3][k]);
+            v[k * S] = y[0][k]; v[(k + 4) * S] = y[1][k]; v[(k + 8) * S] = y[2][k]; v[(k + 12) * S] = y[3][k];
+        }
+    }
+};
+
+// ---------------------------------------------------------------- transform geometry
+constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n >> 1); }
+
+template <int L> struct FftShape {
+    static_assert(L >= 16 && (L & (L - 1)) == 0, "L must be a power of two >= 16");
+    static constexpr int LG = ilog2(L);
+    static constexpr int P = (LG - 1) / 4;        // number of twiddled radix-16 passes
+    static constexpr int R0 = L >> (4 * P);       // first (twiddle-free) radix: 2,4,8,16
+    static constexpr int TPF = L / 16;            // threads per transform
+    static constexpr int TW_ENTRIES = L - R0;     // total twiddle-table entries
+};
+
+// Address policies ---------------------------------------------------------------------------
+// Row layout: one transform contiguous in shared memory; per-exchange XOR swizzle on the
+// 16-byte (fp64) / 8-byte (fp32) element index keeps every 128-bit access conflict free
+// (validated by tools/bank_sim.py).
+template <typename T, int R0> struct RowAddr {
+    static constexpr int MASK = (sizeof(T) == 8) ? 7 : 15;
+    static constexpr int S1 = (R0 == 16) ? 4 : (R0 == 8) ? 3 : (R0 == 4) ? 2 : ((sizeof(T) == 8) ? 3 : 2);
+    int base;  // element offset of this transform's row inside the CTA buffer
+    __device__ __forceinline__ int at(int idx, int exch) const {
+        const int s = (exch == 0) ? S1 : 4;
+        return base + (idx ^ ((idx >> s) & MASK));
+    }
+};
+// Column layout: TC transforms interleaved (column index fastest): conflict free as is.
+template <int TC> struct ColAddr {
+    int c;
+    __device__ __forceinline__ int at(int idx, int /*exch*/) const { return idx * TC + c; }
+};
+
+// ---------------------------------------------------------------- the in-CTA transform
+// e[q] holds point (j + q*TPF) of the transform on entry and on exit (natural order).
+// tw: twiddle tables for this L (layout: pass t (1..P), NS = R0*16^(t-1):
+//     tw[off_t + (r-1)*NS + k] = exp(-2*pi*i * r*k / (16*NS)), r = 1..15, k < NS).
+// All threads of the CTA must call this together (it uses __syncthreads).
+template <typename T, int L, bool INV, typename Addr>
+__device__ __forceinline__ void cta_fft(cpx<T> (&e)[16], cpx<T> *buf, const Addr &addr,
+                                        const cpx<T> *__restrict__ tw, int j) {
+    using C = cpx<T>;
+    using Sh = FftShape<L>;
+    constexpr int R0 = Sh::R0, P = Sh::P, TPF = Sh::TPF, S0 = 16 / R0;
+
+    // pass 0: radix R0, no twiddles
+#pragma unroll
+    for (int u = 0; u < S0; u++) Dft<R0, S0, INV, C>::run(&e[u]);
+    if (P == 0) return;
+
+    __syncthreads();  // buffer may still be read by the previous user
+#pragma unroll
+    for (int u = 0; u < S0; u++) {
+        const int b = j + u * TPF;
+#pragma unroll
+        for (int r = 0; r < R0; r++) buf[addr.at(R0 * b + r, 0)] = e[u + r * S0];
+    }
+    __syncthreads();
+
+    int ns = R0;
+    int off = 0;
+#pragma unroll
+    for (int t = 1; t <= P; t++) {
+#pragma unroll
+        for (int q = 0; q < 16; q++) e[q] = buf[addr.at(j + q * TPF, t - 1)];
+        const int k = j & (ns - 1);
+        const C *twp = tw + off + k;
+#pragma unroll
+        for (int r = 1; r < 16; r++) e[r] = cmul_tw<INV>(e[r], __ldg(&twp[(r - 1) * ns]));
+        Dft<16, 1, INV, C>::run(&e[0]);
+        if (t < P) {
+            __syncthreads();
+            const int j0 = (j - k) * 16 + k;
+#pragma unroll
+            for (int r = 0; r < 16; r++) buf[addr.at(j0 + r * ns, t)] = e[r];
+            __syncthreads();
+        }
+        off += 15 * ns;
+        ns *= 16;
+    }
+}
+
+}  // namespace adsp

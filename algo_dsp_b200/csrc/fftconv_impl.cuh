@@ -1,0 +1,330 @@
+// fftconv_impl.cuh -- FftConv<T>: table construction, IR-spectrum caching and kernel dispatch.
+// Included by fftconv_f64.cu / fftconv_f32.cu with ADSP_REAL defined (one TU per precision so
+// the template-heavy kernels compile in parallel).
+#pragma once
+#include <cmath>
+
+#include "engine.cuh"
+
+namespace adsp {
+
+// ------------------------------------------------------------------ twiddle tables (host, long double)
+static inline void unit_root(long long num, long long den, long double *re, long double *im) {
+    // exp(-2*pi*i*num/den), exact octant reduction so that table entries are correctly rounded
+    num %= den;
+    const long double PI = 3.14159265358979323846264338327950288L;
+    // reduce to [0, den/8] using symmetries when den is a multiple of 8
+    long double c, s;
+    if (den % 8 == 0) {
+        const long long e = den / 8;
+        const long long oct = num / e;
+        const long long rem = num % e;
+        long double a;
+        // angle within octant, measured from the nearest axis
+        if (oct % 2 == 0) a = 2.0L * PI * (long double)rem / (long double)den;
+        else a = 2.0L * PI * (long double)(e - rem) / (long double)den;
+        const long double ca = cosl(a), sa = sinl(a);
+        switch (oct) {
+        case 0: c = ca;  s = sa;  break;
+        case 1: c = sa;  s = ca;  break;
+        case 2: c = -sa; s = ca;  break;
+        case 3: c = -ca; s = sa;  break;
+        case 4: c = -ca; s = -sa; break;
+        case 5: c = -sa; s = -ca; break;
+        case 6: c = sa;  s = -ca; break;
+        default: c = ca; s = -sa; break;
+        }
+    } else {
+        const long double a = 2.0L * PI * (long double)num / (long double)den;
+        c = cosl(a); s = sinl(a);
+    }
+    *re = c;
+    *im = -s;
+}
+
+template <typename T> adsp_status get_tw_table(adsp_ctx *ctx, int L, const cpx<T> **out) {
+    const int prec = sizeof(T) == 8 ? 0 : 1;
+    auto key = std::make_pair(L, prec);
+    auto it = ctx->tw_tables.find(key);
+    if (it != ctx->tw_tables.end()) { *out = (const cpx<T> *)it->second; return ADSP_OK; }
+    int lg = 0;
+    while ((1 << lg) < L) lg++;
+    const int P = (lg - 1) / 4;
+    const int R0 = L >> (4 * P);
+    const int entries = L - R0;
+    std::vector<cpx<T>> h((size_t)(entries > 0 ? entries : 1));
+    int off = 0, ns = R0;
+    for (int t = 1; t <= P; t++) {
+        for (int r = 1; r < 16; r++)
+            for (int k = 0; k < ns; k++) {
+                long double re, im;
+                unit_root((long long)r * k, 16LL * ns, &re, &im);
+                h[(size_t)off + (size_t)(r - 1) * ns + k].x = (T)re;
+                h[(size_t)off + (size_t)(r - 1) * ns + k].y = (T)im;
+            }
+        off += 15 * ns;
+        ns *= 16;
+    }
+    void *d = nullptr;
+    ADSP_CUDA(cudaMalloc(&d, h.size() * sizeof(cpx<T>)));
+    ADSP_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(cpx<T>), cudaMemcpyHostToDevice));
+    ctx->tw_tables[key] = d;
+    *out = (const cpx<T> *)d;
+    return ADSP_OK;
+}
+
+template <typename T> adsp_status get_tw4_tables(adsp_ctx *ctx, int lgN, const cpx<T> **hi, const cpx<T> **lo) {
+    const int prec = sizeof(T) == 8 ? 0 : 1;
+    auto key = std::make_pair(lgN, prec);
+    auto it = ctx->tw4_tables.find(key);
+    if (it != ctx->tw4_tables.end()) {
+        *hi = (const cpx<T> *)it->second.first;
+        *lo = (const cpx<T> *)it->second.second;
+        return ADSP_OK;
+    }
+    const long long N = 1LL << lgN;
+    const long long nhi = (N >> 10) > 0 ? (N >> 10) : 1;
+    std::vector<cpx<T>> hhi((size_t)nhi), hlo(1024);
+    for (long long a = 0; a < nhi; a++) {
+        long double re, im;
+        unit_root(a << 10, N, &re, &im);
+        hhi[(size_t)a].x = (T)re; hhi[(size_t)a].y = (T)im;
+    }
+    for (long long b = 0; b < 1024; b++) {
+        long double re, im;
+        unit_root(b, N, &re, &im);
+        hlo[(size_t)b].x = (T)re; hlo[(size_t)b].y = (T)im;
+    }
+    void *dhi = nullptr, *dlo = nullptr;
+    ADSP_CUDA(cudaMalloc(&dhi, hhi.size() * sizeof(cpx<T>)));
+    ADSP_CUDA(cudaMalloc(&dlo, hlo.size() * sizeof(cpx<T>)));
+    ADSP_CUDA(cudaMemcpy(dhi, hhi.data(), hhi.size() * sizeof(cpx<T>), cudaMemcpyHostToDevice));
+    ADSP_CUDA(cudaMemcpy(dlo, hlo.data(), hlo.size() * sizeof(cpx<T>), cudaMemcpyHostToDevice));
+    ctx->tw4_tables[key] = std::make_pair(dhi, dlo);
+    *hi = (const cpx<T> *)dhi;
+    *lo = (const cpx<T> *)dlo;
+    return ADSP_OK;
+}
+
+// ------------------------------------------------------------------ kernel dispatch
+template <typename K> static adsp_status set_smem(K kern, size_t bytes) {
+    if (bytes > 48 * 1024) ADSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return ADSP_OK;
+}
+// the opt-in shared-memory attribute is per (function, device): remember it per device
+struct AttrOnce {
+    bool done[64] = {};
+    bool need(int dev) { if (dev < 0 || dev >= 64) return true; if (done[dev]) return false; done[dev] = true; return true; }
+};
+
+template <typename T, int L, bool SPEC>
+static adsp_status launch_full_t(adsp_ctx *ctx, cudaStream_t st, const ConvGeom &g, const T *x, T *y, const cpx<T> *H,
+                                 cpx<T> *spec, T scale, const cpx<T> *tw, long long npairs) {
+    constexpr int ROWS = 256 / FftShape<L>::TPF;
+    const size_t smem = (size_t)ROWS * L * sizeof(cpx<T>);
+    static AttrOnce once;
+    if (once.need(ctx->device)) ADSP_TRY(set_smem(fftconv_full<T, L, SPEC>, smem));
+    const long long grid = (npairs + ROWS - 1) / ROWS;
+    fftconv_full<T, L, SPEC><<<(unsigned)grid, 256, smem, st>>>(g, x, y, H, spec, scale, tw, npairs);
+    count_launch(ctx);
+    ADSP_CUDA(cudaGetLastError());
+    return ADSP_OK;
+}
+
+template <typename T, bool SPEC>
+static adsp_status launch_full(adsp_ctx *ctx, cudaStream_t st, int L, const ConvGeom &g, const T *x, T *y,
+                               const cpx<T> *H, cpx<T> *spec, T scale, const cpx<T> *tw, long long npairs) {
+    switch (L) {
+    case 256:  return launch_full_t<T, 256, SPEC>(ctx, st, g, x, y, H, spec, scale, tw, npairs);
+    case 512:  return launch_full_t<T, 512, SPEC>(ctx, st, g, x, y, H, spec, scale, tw, npairs);
+    case 1024: return launch_full_t<T, 1024, SPEC>(ctx, st, g, x, y, H, spec, scale, tw, npairs);
+    case 2048: return launch_full_t<T, 2048, SPEC>(ctx, st, g, x, y, H, spec, scale, tw, npairs);
+    case 4096: return launch_full_t<T, 4096, SPEC>(ctx, st, g, x, y, H, spec, scale, tw, npairs);
+    default: set_error("unsupported single-kernel FFT length"); return ADSP_ERR_INVALID_ARG;
+    }
+}
+
+template <typename T, int L, bool SPEC>
+static adsp_status launch_rows_t(adsp_ctx *ctx, cudaStream_t st, cpx<T> *scratch, const cpx<T> *H, cpx<T> *spec,
+                                 T scale, int N1, const cpx<T> *tw, int pairs) {
+    constexpr int ROWS = 256 / FftShape<L>::TPF;
+    const size_t smem = (size_t)ROWS * L * sizeof(cpx<T>);
+    static AttrOnce once;
+    if (once.need(ctx->device)) ADSP_TRY(set_smem(fftconv_rows<T, L, SPEC>, smem));
+    dim3 grid((unsigned)(N1 / ROWS > 0 ? N1 / ROWS : 1), (unsigned)pairs);
+    fftconv_rows<T, L, SPEC><<<grid, 256, smem, st>>>(scratch, H, spec, scale, N1, tw);
+    count_launch(ctx);
+    ADSP_CUDA(cudaGetLastError());
+    return ADSP_OK;
+}
+
+template <typename T, bool SPEC>
+static adsp_status launch_rows(adsp_ctx *ctx, cudaStream_t st, int L, cpx<T> *scratch, const cpx<T> *H, cpx<T> *spec,
+                               T scale, int N1, const cpx<T> *tw, int pairs) {
+    switch (L) {
+    case 256:  return launch_rows_t<T, 256, SPEC>(ctx, st, scratch, H, spec, scale, N1, tw, pairs);
+    case 512:  return launch_rows_t<T, 512, SPEC>(ctx, st, scratch, H, spec, scale, N1, tw, pairs);
+    case 1024: return launch_rows_t<T, 1024, SPEC>(ctx, st, scratch, H, spec, scale, N1, tw, pairs);
+    case 2048: return launch_rows_t<T, 2048, SPEC>(ctx, st, scratch, H, spec, scale, N1, tw, pairs);
+    case 4096: return launch_rows_t<T, 4096, SPEC>(ctx, st, scratch, H, spec, scale, N1, tw, pairs);
+    default: set_error("unsupported row FFT length"); return ADSP_ERR_INVALID_ARG;
+    }
+}
+
+template <typename T, int N1>
+static adsp_status launch_cols_t(adsp_ctx *ctx, cudaStream_t st, bool inverse, const ConvGeom &g, const T *x, T *y,
+                                 cpx<T> *scratch, int N2, int lgN, const cpx<T> *tw, const cpx<T> *hi,
+                                 const cpx<T> *lo, long long pair0, int pairs) {
+    using CS = ColShape<N1>;
+    const size_t smem = (FftShape<N1>::P > 0) ? (size_t)CS::SMEM_ELEMS * sizeof(cpx<T>) : 0;
+    static AttrOnce once;
+    if (once.need(ctx->device)) {
+        ADSP_TRY(set_smem(fftconv_cols_fwd<T, N1>, smem));
+        ADSP_TRY(set_smem(fftconv_cols_inv<T, N1>, smem));
+    }
+    dim3 grid((unsigned)(N2 / CS::TC), (unsigned)pairs);
+    if (!inverse)
+        fftconv_cols_fwd<T, N1><<<grid, CS::THREADS, smem, st>>>(g, x, scratch, N2, lgN, tw, hi, lo, pair0);
+    else
+        fftconv_cols_inv<T, N1><<<grid, CS::THREADS, smem, st>>>(g, scratch, x, y, N2, lgN, tw, hi, lo, pair0);
+    count_launch(ctx);
+    ADSP_CUDA(cudaGetLastError());
+    return ADSP_OK;
+}
+
+template <typename T>
+static adsp_status launch_cols(adsp_ctx *ctx, cudaStream_t st, int N1, bool inverse, const ConvGeom &g, const T *x, T *y,
+                               cpx<T> *scratch, int N2, int lgN, const cpx<T> *tw, const cpx<T> *hi, const cpx<T> *lo,
+                               long long pair0, int pairs) {
+    switch (N1) {
+    case 16:   return launch_cols_t<T, 16>(ctx, st, inverse, g, x, y, scratch, N2, lgN, tw, hi, lo, pair0, pairs);
+    case 32:   return launch_cols_t<T, 32>(ctx, st, inverse, g, x, y, scratch, N2, lgN, tw, hi, lo, pair0, pairs);
+    case 64:   return launch_cols_t<T, 64>(ctx, st, inverse, g, x, y, scratch, N2, lgN, tw, hi, lo, pair0, pairs);
+    case 128:  return launch_cols_t<T, 128>(ctx, st, inverse, g, x, y, scratch, N2, lgN, tw, hi, lo, pair0, pairs);
+    case 256:  return launch_cols_t<T, 256>(ctx, st, inverse, g, x, y, scratch, N2, lgN, tw, hi, lo, pair0, pairs);
+    case 512:  return launch_cols_t<T, 512>(ctx, st, inverse, g, x, y, scratch, N2, lgN, tw, hi, lo, pair0, pairs);
+    case 1024: return launch_cols_t<T, 1024>(ctx, st, inverse, g, x, y, scratch, N2, lgN, tw, hi, lo, pair0, pairs);
+    default: set_error("unsupported column FFT length"); return ADSP_ERR_INVALID_ARG;
+    }
+}
+
+// ------------------------------------------------------------------ FftConv
+template <typename T>
+adsp_status FftConv<T>::init(adsp_ctx *c, const T *d_kernel, long long K_, const FftChoice &choice) {
+    ctx = c;
+    K = K_;
+    ch = choice;
+    const size_t hbytes = (size_t)ch.N * sizeof(cpx<T>);
+    ADSP_CUDA(cudaMalloc((void **)&H, hbytes));
+    ADSP_TRY(get_tw_table<T>(ctx, ch.N2, &tw_rows));
+    // geometry that presents the kernel as one zero-padded block (im part absent -> 0)
+    ConvGeom g{};
+    g.n = K; g.out_len = ch.N; g.in_stride = 0; g.out_stride = 0; g.S = ch.N; g.D = 0;
+    g.total_blocks = 1; g.in_shift = 0; g.out_shift = 0; g.nblk = 1; g.accumulate = 0;
+    const T scale = (T)(1.0L / (long double)ch.N);
+    if (ch.N1 == 1) {
+        ADSP_TRY((launch_full<T, true>(ctx, ctx->main, ch.N2, g, d_kernel, (T *)nullptr, (const cpx<T> *)nullptr, H,
+                                       scale, tw_rows, 1)));
+    } else {
+        ADSP_TRY(get_tw_table<T>(ctx, ch.N1, &tw_cols));
+        ADSP_TRY(get_tw4_tables<T>(ctx, ch.lgN, &tw_hi, &tw_lo));
+        ADSP_TRY(ctx->scratch.reserve(hbytes));
+        cpx<T> *scr = (cpx<T> *)ctx->scratch.p;
+        ADSP_TRY(launch_cols<T>(ctx, ctx->main, ch.N1, false, g, d_kernel, (T *)nullptr, scr, ch.N2, ch.lgN, tw_cols,
+                                tw_hi, tw_lo, 0, 1));
+        ADSP_TRY((launch_rows<T, true>(ctx, ctx->main, ch.N2, scr, (const cpx<T> *)nullptr, H, scale, ch.N1, tw_rows, 1)));
+    }
+    ADSP_CUDA(cudaStreamSynchronize(ctx->main));
+    return ADSP_OK;
+}
+
+template <typename T> void FftConv<T>::destroy() {
+    if (H) cudaFree(H);
+    H = nullptr;
+}
+
+template <typename T>
+adsp_status FftConv<T>::run(const T *d_x, long long n, long long channels, long long in_stride, T *d_y,
+                            long long out_stride, long long out_len, long long in_shift, long long out_shift,
+                            bool accumulate) {
+    ConvGeom g{};
+    g.n = n; g.out_len = out_len; g.in_stride = in_stride; g.out_stride = out_stride;
+    g.S = ch.S; g.D = ch.D;
+    g.nblk = (int)((out_len + ch.S - 1) / ch.S);
+    g.total_blocks = channels * (long long)g.nblk;
+    g.in_shift = in_shift; g.out_shift = out_shift; g.accumulate = accumulate ? 1 : 0;
+    const long long npairs = (g.total_blocks + 1) / 2;
+    if (npairs <= 0) return ADSP_OK;
+
+    if (ch.N1 == 1)
+        return launch_full<T, false>(ctx, ctx->main, ch.N2, g, d_x, d_y, H, (cpx<T> *)nullptr, (T)0, tw_rows, npairs);
+
+    // four-step: groups of pairs sized so that the intermediates of all in-flight groups stay in L2
+    const size_t per_pair = (size_t)ch.N * sizeof(cpx<T>);
+    long long G = (long long)(ctx->scratch_budget / kWorkerStreams / per_pair);
+    if (G < 1) G = 1;
+    if (G > npairs) G = npairs;
+    if (G > 32768) G = 32768;
+    const int nslots = (npairs > G) ? kWorkerStreams : 1;
+    ADSP_TRY(ctx->scratch.reserve((size_t)nslots * (size_t)G * per_pair));
+    cpx<T> *scr = (cpx<T> *)ctx->scratch.p;
+
+    if (nslots > 1) {
+        ADSP_CUDA(cudaEventRecord(ctx->ev_fork, ctx->main));
+        for (int s = 0; s < nslots; s++) ADSP_CUDA(cudaStreamWaitEvent(ctx->worker[s], ctx->ev_fork, 0));
+    }
+    long long grp = 0;
+    for (long long pair0 = 0; pair0 < npairs; pair0 += G, grp++) {
+        const int gp = (int)((npairs - pair0 < G) ? (npairs - pair0) : G);
+        const int slot = (int)(grp % nslots);
+        cudaStream_t st = (nslots > 1) ? ctx->worker[slot] : ctx->main;
+        cpx<T> *sl = scr + (size_t)slot * (size_t)G * (size_t)ch.N;
+        ADSP_TRY(launch_cols<T>(ctx, st, ch.N1, false, g, d_x, d_y, sl, ch.N2, ch.lgN, tw_cols, tw_hi, tw_lo, pair0, gp));
+        ADSP_TRY((launch_rows<T, false>(ctx, st, ch.N2, sl, H, (cpx<T> *)nullptr, (T)0, ch.N1, tw_rows, gp)));
+        ADSP_TRY(launch_cols<T>(ctx, st, ch.N1, true, g, d_x, d_y, sl, ch.N2, ch.lgN, tw_cols, tw_hi, tw_lo, pair0, gp));
+    }
+    if (nslots > 1) {
+        for (int s = 0; s < nslots; s++) {
+            ADSP_CUDA(cudaEventRecord(ctx->ev_join[s], ctx->worker[s]));
+            ADSP_CUDA(cudaStreamWaitEvent(ctx->main, ctx->ev_join[s], 0));
+        }
+    }
+    return ADSP_OK;
+}
+
+template <typename T>
+adsp_status fft_convolve_device(adsp_ctx *ctx, const T *d_x, long long n, long long channels, long long in_stride,
+                                const T *d_k, long long K, T *d_y, long long out_stride) {
+    const FftChoice ch = choose_fft(K);
+    const long long out_len = n + K - 1;
+    if (ch.parts == 1) {
+        FftConv<T> fc;
+        adsp_status st = fc.init(ctx, d_k, K, ch);
+        if (st == ADSP_OK) st = fc.run(d_x, n, channels, in_stride, d_y, out_stride, out_len, 0, 0, false);
+        if (st == ADSP_OK) { cudaError_t e = cudaStreamSynchronize(ctx->main); if (e != cudaSuccess) st = cuda_fail(e, "sync", __FILE__, __LINE__); }
+        fc.destroy();
+        return st;
+    }
+    // long kernel: sum over IR partitions, each delayed by p*part_len
+    ADSP_CUDA(cudaMemset2DAsync(d_y, (size_t)out_stride * sizeof(T), 0, (size_t)out_len * sizeof(T), (size_t)channels, ctx->main));
+    for (int p = 0; p < ch.parts; p++) {
+        const long long k0 = (long long)p * ch.part_len;
+        const long long kp = (K - k0 < ch.part_len) ? (K - k0) : ch.part_len;
+        if (kp <= 0) break;
+        FftConv<T> fc;
+        adsp_status st = fc.init(ctx, d_k + k0, kp, ch);
+        if (st == ADSP_OK) st = fc.run(d_x, n, channels, in_stride, d_y, out_stride, n + kp - 1, 0, k0, true);
+        if (st == ADSP_OK) { cudaError_t e = cudaStreamSynchronize(ctx->main); if (e != cudaSuccess) st = cuda_fail(e, "sync", __FILE__, __LINE__); }
+        fc.destroy();
+        if (st != ADSP_OK) return st;
+    }
+    return ADSP_OK;
+}
+
+template struct FftConv<ADSP_REAL>;
+template adsp_status get_tw_table<ADSP_REAL>(adsp_ctx *, int, const cpx<ADSP_REAL> **);
+template adsp_status get_tw4_tables<ADSP_REAL>(adsp_ctx *, int, const cpx<ADSP_REAL> **, const cpx<ADSP_REAL> **);
+template adsp_status fft_convolve_device<ADSP_REAL>(adsp_ctx *, const ADSP_REAL *, long long, long long, long long,
+                                                    const ADSP_REAL *, long long, ADSP_REAL *, long long);
+
+}  // namespace adsp
