@@ -49,7 +49,7 @@ static long long next_pow2_ll(long long n) {
     return p;
 }
 
-static long long env_ll(const char *name, long long dflt) {
+long long env_ll(const char *name, long long dflt) {
     const char *v = getenv(name);
     if (!v || !*v) return dflt;
     return atoll(v);

@@ -74,6 +74,8 @@ fftconv_full(ConvGeom g, const T *__restrict__ x, T *__restrict__ y,
     constexpr int ROWS = 256 / TPF;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C *buf = reinterpret_cast<C *>(smem_raw);
+    C *stw = buf + ROWS * L;
+    load_tw_smem<T, L>(stw, tw, threadIdx.x, 256);  // visible after the first __syncthreads in cta_fft
 
     const int row = threadIdx.x / TPF;
     const int j = threadIdx.x % TPF;
@@ -90,7 +92,15 @@ fftconv_full(ConvGeom g, const T *__restrict__ x, T *__restrict__ y,
         e[q].x = (i >= a.lo && i < a.hi) ? ld_stream(a.in + i) : (T)0;
         e[q].y = (i >= b.lo && i < b.hi) ? ld_stream(b.in + i) : (T)0;
     }
-    cta_fft<T, L, false>(e, buf, addr, tw, j);
+    // prefetch this thread's 16 spectrum values into the slots it has just emptied (no barrier
+    // needed: same thread writes and reads them); overlaps with the last forward pass
+    auto prefetch_h = [&](C *b) {
+        if (!SPECTRUM) {
+#pragma unroll
+            for (int q = 0; q < 16; q++) cp_async_elem(&b[addr.at(j + q * TPF, Sh::P - 1)], &H[j + q * TPF]);
+        }
+    };
+    cta_fft<T, L, false>(e, buf, addr, stw, j, prefetch_h);
     if (SPECTRUM) {
         if (pair < npairs) {
 #pragma unroll
@@ -101,9 +111,10 @@ fftconv_full(ConvGeom g, const T *__restrict__ x, T *__restrict__ y,
         }
         return;
     }
+    cp_async_wait_all();
 #pragma unroll
-    for (int q = 0; q < 16; q++) e[q] = cmul(e[q], __ldg(&H[j + q * TPF]));
-    cta_fft<T, L, true>(e, buf, addr, tw, j);
+    for (int q = 0; q < 16; q++) e[q] = cmul(e[q], buf[addr.at(j + q * TPF, Sh::P - 1)]);
+    cta_fft<T, L, true>(e, buf, addr, stw, j);
 #pragma unroll
     for (int q = 0; q < 16; q++) {
         const long long o = (long long)(j + q * TPF) - g.D;
@@ -148,12 +159,13 @@ template <int N1> struct ColShape {
     static constexpr int TC = (N1 <= 256) ? (256 / TPF) : ((N1 == 512) ? 16 : 8);  // columns per tile
     static constexpr int THREADS = TPF * TC;
     static constexpr int SMEM_ELEMS = N1 * TC;
+    static constexpr int MIN_CTAS = (THREADS <= 256) ? 2 : 1;
 };
 
 // Forward column pass.  grid = (N2/TC, pairs in this group).  Writes A[k1][n2] * W_N^(k1*n2)
 // to scratch (row-major N1 x N2 per pair).
 template <typename T, int N1>
-__global__ void __launch_bounds__(ColShape<N1>::THREADS)
+__global__ void __launch_bounds__(ColShape<N1>::THREADS, ColShape<N1>::MIN_CTAS)
 fftconv_cols_fwd(ConvGeom g, const T *__restrict__ x, cpx<T> *__restrict__ scratch, int N2, int lgN,
                  const cpx<T> *__restrict__ tw, const cpx<T> *__restrict__ tw_hi,
                  const cpx<T> *__restrict__ tw_lo, long long pair0) {
@@ -163,11 +175,19 @@ fftconv_cols_fwd(ConvGeom g, const T *__restrict__ x, cpx<T> *__restrict__ scrat
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C *buf = reinterpret_cast<C *>(smem_raw);
 
+    C *stw = buf + ((FftShape<N1>::P > 0) ? CS::SMEM_ELEMS : 0);
+    load_tw_smem<T, N1>(stw, tw, threadIdx.x, CS::THREADS);
+
     const int c = threadIdx.x % TC;
     const int j = threadIdx.x / TC;
     const int n2 = blockIdx.x * TC + c;
     const long long pair = pair0 + blockIdx.y;
     ColAddr<TC> addr{c};
+
+    // four-step twiddle seeds, fetched first so their latency hides behind the data loads
+    const unsigned maskN = (1u << lgN) - 1u;
+    const C tw_base = twiddle_n<T>(tw_hi, tw_lo, ((unsigned)n2 * (unsigned)j) & maskN);
+    const C tw_rho = twiddle_n<T>(tw_hi, tw_lo, ((unsigned)n2 * (unsigned)TPF) & maskN);
 
     const BlockIO<T> a = block_io<T>(g, x, (T *)nullptr, 2 * pair);
     const BlockIO<T> b = block_io<T>(g, x, (T *)nullptr, 2 * pair + 1);
@@ -179,13 +199,11 @@ fftconv_cols_fwd(ConvGeom g, const T *__restrict__ x, cpx<T> *__restrict__ scrat
         e[q].x = (i >= a.lo && i < a.hi) ? ld_stream(a.in + i) : (T)0;
         e[q].y = (i >= b.lo && i < b.hi) ? ld_stream(b.in + i) : (T)0;
     }
-    cta_fft<T, N1, false>(e, buf, addr, tw, j);
+    cta_fft<T, N1, false>(e, buf, addr, stw, j);
 
     // four-step twiddle: k1 = j + r*TPF  ->  W_N^(n2*j) * (W_N^(n2*TPF))^r
-    const unsigned maskN = (1u << lgN) - 1u;
     C gtw[16];
-    geometric16(twiddle_n<T>(tw_hi, tw_lo, ((unsigned)n2 * (unsigned)j) & maskN),
-                twiddle_n<T>(tw_hi, tw_lo, ((unsigned)n2 * (unsigned)TPF) & maskN), gtw);
+    geometric16(tw_base, tw_rho, gtw);
     C *dst = scratch + (size_t)blockIdx.y * ((size_t)N1 * N2) + n2;
 #pragma unroll
     for (int r = 0; r < 16; r++) dst[(size_t)(j + r * TPF) * N2] = cmul(e[r], gtw[r]);
@@ -205,6 +223,8 @@ fftconv_rows(cpx<T> *__restrict__ scratch, const cpx<T> *__restrict__ H, cpx<T> 
     constexpr int ROWS = 256 / TPF;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C *buf = reinterpret_cast<C *>(smem_raw);
+    C *stw = buf + ROWS * L;
+    load_tw_smem<T, L>(stw, tw, threadIdx.x, 256);
 
     const int row = threadIdx.x / TPF;
     const int j = threadIdx.x % TPF;
@@ -216,7 +236,13 @@ fftconv_rows(cpx<T> *__restrict__ scratch, const cpx<T> *__restrict__ H, cpx<T> 
     C e[16];
 #pragma unroll
     for (int q = 0; q < 16; q++) e[q] = p[q * TPF];
-    cta_fft<T, L, false>(e, buf, addr, tw, j);
+    auto prefetch_h = [&](C *b) {
+        if (!SPECTRUM) {
+#pragma unroll
+            for (int q = 0; q < 16; q++) cp_async_elem(&b[addr.at(j + q * TPF, Sh::P - 1)], &H[hoff + q * TPF]);
+        }
+    };
+    cta_fft<T, L, false>(e, buf, addr, stw, j, prefetch_h);
     if (SPECTRUM) {
 #pragma unroll
         for (int q = 0; q < 16; q++) {
@@ -225,9 +251,10 @@ fftconv_rows(cpx<T> *__restrict__ scratch, const cpx<T> *__restrict__ H, cpx<T> 
         }
         return;
     }
+    cp_async_wait_all();
 #pragma unroll
-    for (int q = 0; q < 16; q++) e[q] = cmul(e[q], __ldg(&H[hoff + q * TPF]));
-    cta_fft<T, L, true>(e, buf, addr, tw, j);
+    for (int q = 0; q < 16; q++) e[q] = cmul(e[q], buf[addr.at(j + q * TPF, Sh::P - 1)]);
+    cta_fft<T, L, true>(e, buf, addr, stw, j);
 #pragma unroll
     for (int q = 0; q < 16; q++) p[q * TPF] = e[q];
 }
@@ -235,7 +262,7 @@ fftconv_rows(cpx<T> *__restrict__ scratch, const cpx<T> *__restrict__ H, cpx<T> 
 // Inverse column pass: conj four-step twiddle, N1-point inverse, keep positions >= D, split
 // re/im to the two real output blocks.
 template <typename T, int N1>
-__global__ void __launch_bounds__(ColShape<N1>::THREADS)
+__global__ void __launch_bounds__(ColShape<N1>::THREADS, ColShape<N1>::MIN_CTAS)
 fftconv_cols_inv(ConvGeom g, const cpx<T> *__restrict__ scratch, const T *__restrict__ x, T *__restrict__ y,
                  int N2, int lgN, const cpx<T> *__restrict__ tw, const cpx<T> *__restrict__ tw_hi,
                  const cpx<T> *__restrict__ tw_lo, long long pair0) {
@@ -244,6 +271,9 @@ fftconv_cols_inv(ConvGeom g, const cpx<T> *__restrict__ scratch, const T *__rest
     constexpr int TPF = CS::TPF, TC = CS::TC;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C *buf = reinterpret_cast<C *>(smem_raw);
+
+    C *stw = buf + ((FftShape<N1>::P > 0) ? CS::SMEM_ELEMS : 0);
+    load_tw_smem<T, N1>(stw, tw, threadIdx.x, CS::THREADS);
 
     const int c = threadIdx.x % TC;
     const int j = threadIdx.x / TC;
@@ -259,7 +289,7 @@ fftconv_cols_inv(ConvGeom g, const cpx<T> *__restrict__ scratch, const T *__rest
     C e[16];
 #pragma unroll
     for (int q = 0; q < 16; q++) e[q] = cmul_tw<true>(src[(size_t)(j + q * TPF) * N2], gtw[q]);
-    cta_fft<T, N1, true>(e, buf, addr, tw, j);
+    cta_fft<T, N1, true>(e, buf, addr, stw, j);
 
     const BlockIO<T> a = block_io<T>(g, x, y, 2 * pair);
     const BlockIO<T> b = block_io<T>(g, x, y, 2 * pair + 1);

@@ -117,13 +117,25 @@ template <int S, bool INV, typename C> struct Dft<16, S, INV, C> {
 // ---------------------------------------------------------------- transform geometry
 constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n >> 1); }
 
+// Twiddle storage for a twiddled radix-16 pass with NS sub-transform length:
+//   NS <= 16 : all 15 powers, [15][NS]  (direct shared-memory lookups)
+//   NS  > 16 : first power only, [NS]; powers 2..15 are formed in registers by a short product
+//              tree (depth <= 6).  Keeps the per-CTA table small enough for shared memory so no
+//              twiddle ever costs a global-memory round trip.
+constexpr int tw_pass_entries(int ns) { return ns <= 16 ? 15 * ns : ns; }
+constexpr int tw_total_entries(int r0, int p) {
+    int n = 0, ns = r0;
+    for (int t = 0; t < p; t++) { n += tw_pass_entries(ns); ns *= 16; }
+    return n;
+}
+
 template <int L> struct FftShape {
     static_assert(L >= 16 && (L & (L - 1)) == 0, "L must be a power of two >= 16");
     static constexpr int LG = ilog2(L);
     static constexpr int P = (LG - 1) / 4;        // number of twiddled radix-16 passes
     static constexpr int R0 = L >> (4 * P);       // first (twiddle-free) radix: 2,4,8,16
     static constexpr int TPF = L / 16;            // threads per transform
-    static constexpr int TW_ENTRIES = L - R0;     // total twiddle-table entries
+    static constexpr int TW_ENTRIES = tw_total_entries(R0, P);  // compact table size (elements)
 };
 
 // Address policies ---------------------------------------------------------------------------
@@ -145,14 +157,26 @@ template <int TC> struct ColAddr {
     __device__ __forceinline__ int at(int idx, int /*exch*/) const { return idx * TC + c; }
 };
 
+struct NoHook {
+    template <typename C> __device__ __forceinline__ void operator()(C * /*buf*/) const {}
+};
+
+// cooperative copy of the compact twiddle table (global -> shared); caller syncs afterwards
+template <typename T, int L>
+__device__ __forceinline__ void load_tw_smem(cpx<T> *stw, const cpx<T> *__restrict__ gtw, int tid, int nthreads) {
+    for (int i = tid; i < FftShape<L>::TW_ENTRIES; i += nthreads) stw[i] = __ldg(&gtw[i]);
+}
+
 // ---------------------------------------------------------------- the in-CTA transform
 // e[q] holds point (j + q*TPF) of the transform on entry and on exit (natural order).
-// tw: twiddle tables for this L (layout: pass t (1..P), NS = R0*16^(t-1):
-//     tw[off_t + (r-1)*NS + k] = exp(-2*pi*i * r*k / (16*NS)), r = 1..15, k < NS).
+// stw: compact twiddle table for this L in SHARED memory (see tw_pass_entries; entry for power r,
+//      position k of a pass with NS: exp(-2*pi*i * r*k / (16*NS))).
+// hook(buf): called once, right after the last pass has read its inputs from `buf` (the calling
+//      thread may then reuse exactly the slots it read: addr.at(j + q*TPF, P-1)).
 // All threads of the CTA must call this together (it uses __syncthreads).
-template <typename T, int L, bool INV, typename Addr>
+template <typename T, int L, bool INV, typename Addr, typename Hook = NoHook>
 __device__ __forceinline__ void cta_fft(cpx<T> (&e)[16], cpx<T> *buf, const Addr &addr,
-                                        const cpx<T> *__restrict__ tw, int j) {
+                                        const cpx<T> *stw, int j, const Hook &hook = Hook()) {
     using C = cpx<T>;
     using Sh = FftShape<L>;
     constexpr int R0 = Sh::R0, P = Sh::P, TPF = Sh::TPF, S0 = 16 / R0;
@@ -177,10 +201,35 @@ __device__ __forceinline__ void cta_fft(cpx<T> (&e)[16], cpx<T> *buf, const Addr
     for (int t = 1; t <= P; t++) {
 #pragma unroll
         for (int q = 0; q < 16; q++) e[q] = buf[addr.at(j + q * TPF, t - 1)];
+        if (t == P) hook(buf);
         const int k = j & (ns - 1);
-        const C *twp = tw + off + k;
+        if (ns <= 16) {
+            const C *twp = stw + off + k;
 #pragma unroll
-        for (int r = 1; r < 16; r++) e[r] = cmul_tw<INV>(e[r], __ldg(&twp[(r - 1) * ns]));
+            for (int r = 1; r < 16; r++) e[r] = cmul_tw<INV>(e[r], twp[(r - 1) * ns]);
+        } else {
+            const C w1 = stw[off + k];
+            const C w2 = cmul(w1, w1), w4 = cmul(w2, w2), w8 = cmul(w4, w4);
+            e[1] = cmul_tw<INV>(e[1], w1);
+            e[2] = cmul_tw<INV>(e[2], w2);
+            e[3] = cmul_tw<INV>(e[3], cmul(w2, w1));
+            e[4] = cmul_tw<INV>(e[4], w4);
+            e[5] = cmul_tw<INV>(e[5], cmul(w4, w1));
+            const C w6 = cmul(w4, w2);
+            e[6] = cmul_tw<INV>(e[6], w6);
+            e[7] = cmul_tw<INV>(e[7], cmul(w6, w1));
+            e[8] = cmul_tw<INV>(e[8], w8);
+            e[9] = cmul_tw<INV>(e[9], cmul(w8, w1));
+            const C w10 = cmul(w8, w2);
+            e[10] = cmul_tw<INV>(e[10], w10);
+            e[11] = cmul_tw<INV>(e[11], cmul(w10, w1));
+            const C w12 = cmul(w8, w4);
+            e[12] = cmul_tw<INV>(e[12], w12);
+            e[13] = cmul_tw<INV>(e[13], cmul(w12, w1));
+            const C w14 = cmul(w12, w2);
+            e[14] = cmul_tw<INV>(e[14], w14);
+            e[15] = cmul_tw<INV>(e[15], cmul(w14, w1));
+        }
         Dft<16, 1, INV, C>::run(&e[0]);
         if (t < P) {
             __syncthreads();
@@ -189,9 +238,17 @@ __device__ __forceinline__ void cta_fft(cpx<T> (&e)[16], cpx<T> *buf, const Addr
             for (int r = 0; r < 16; r++) buf[addr.at(j0 + r * ns, t)] = e[r];
             __syncthreads();
         }
-        off += 15 * ns;
+        off += tw_pass_entries(ns);
         ns *= 16;
     }
 }
+
+// 16-byte / 8-byte asynchronous global -> shared copy (LDGSTS), used to prefetch the spectrum
+template <typename C> __device__ __forceinline__ void cp_async_elem(C *smem_dst, const C *gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    if (sizeof(C) == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 }  // namespace adsp

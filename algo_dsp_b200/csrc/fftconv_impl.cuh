@@ -51,18 +51,19 @@ template <typename T> adsp_status get_tw_table(adsp_ctx *ctx, int L, const cpx<T
     while ((1 << lg) < L) lg++;
     const int P = (lg - 1) / 4;
     const int R0 = L >> (4 * P);
-    const int entries = L - R0;
+    const int entries = tw_total_entries(R0, P);
     std::vector<cpx<T>> h((size_t)(entries > 0 ? entries : 1));
     int off = 0, ns = R0;
     for (int t = 1; t <= P; t++) {
-        for (int r = 1; r < 16; r++)
+        const int rmax = (ns <= 16) ? 15 : 1;  // compact layout, see tw_pass_entries()
+        for (int r = 1; r <= rmax; r++)
             for (int k = 0; k < ns; k++) {
                 long double re, im;
                 unit_root((long long)r * k, 16LL * ns, &re, &im);
                 h[(size_t)off + (size_t)(r - 1) * ns + k].x = (T)re;
                 h[(size_t)off + (size_t)(r - 1) * ns + k].y = (T)im;
             }
-        off += 15 * ns;
+        off += tw_pass_entries(ns);
         ns *= 16;
     }
     void *d = nullptr;
@@ -121,7 +122,7 @@ template <typename T, int L, bool SPEC>
 static adsp_status launch_full_t(adsp_ctx *ctx, cudaStream_t st, const ConvGeom &g, const T *x, T *y, const cpx<T> *H,
                                  cpx<T> *spec, T scale, const cpx<T> *tw, long long npairs) {
     constexpr int ROWS = 256 / FftShape<L>::TPF;
-    const size_t smem = (size_t)ROWS * L * sizeof(cpx<T>);
+    const size_t smem = ((size_t)ROWS * L + FftShape<L>::TW_ENTRIES) * sizeof(cpx<T>);
     static AttrOnce once;
     if (once.need(ctx->device)) ADSP_TRY(set_smem(fftconv_full<T, L, SPEC>, smem));
     const long long grid = (npairs + ROWS - 1) / ROWS;
@@ -148,7 +149,7 @@ template <typename T, int L, bool SPEC>
 static adsp_status launch_rows_t(adsp_ctx *ctx, cudaStream_t st, cpx<T> *scratch, const cpx<T> *H, cpx<T> *spec,
                                  T scale, int N1, const cpx<T> *tw, int pairs) {
     constexpr int ROWS = 256 / FftShape<L>::TPF;
-    const size_t smem = (size_t)ROWS * L * sizeof(cpx<T>);
+    const size_t smem = ((size_t)ROWS * L + FftShape<L>::TW_ENTRIES) * sizeof(cpx<T>);
     static AttrOnce once;
     if (once.need(ctx->device)) ADSP_TRY(set_smem(fftconv_rows<T, L, SPEC>, smem));
     dim3 grid((unsigned)(N1 / ROWS > 0 ? N1 / ROWS : 1), (unsigned)pairs);
@@ -176,7 +177,7 @@ static adsp_status launch_cols_t(adsp_ctx *ctx, cudaStream_t st, bool inverse, c
                                  cpx<T> *scratch, int N2, int lgN, const cpx<T> *tw, const cpx<T> *hi,
                                  const cpx<T> *lo, long long pair0, int pairs) {
     using CS = ColShape<N1>;
-    const size_t smem = (FftShape<N1>::P > 0) ? (size_t)CS::SMEM_ELEMS * sizeof(cpx<T>) : 0;
+    const size_t smem = (FftShape<N1>::P > 0) ? ((size_t)CS::SMEM_ELEMS + FftShape<N1>::TW_ENTRIES) * sizeof(cpx<T>) : 16;
     static AttrOnce once;
     if (once.need(ctx->device)) {
         ADSP_TRY(set_smem(fftconv_cols_fwd<T, N1>, smem));
@@ -261,7 +262,10 @@ adsp_status FftConv<T>::run(const T *d_x, long long n, long long channels, long 
 
     // four-step: groups of pairs sized so that the intermediates of all in-flight groups stay in L2
     const size_t per_pair = (size_t)ch.N * sizeof(cpx<T>);
-    long long G = (long long)(ctx->scratch_budget / kWorkerStreams / per_pair);
+    size_t budget = ctx->scratch_budget;
+    const long long mb = env_ll("ADSP_SCRATCH_MB", 0);  // tuning override
+    if (mb > 0) budget = (size_t)mb << 20;
+    long long G = (long long)(budget / kWorkerStreams / per_pair);
     if (G < 1) G = 1;
     if (G > npairs) G = npairs;
     if (G > 32768) G = 32768;

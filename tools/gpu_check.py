@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from algo_dsp_b200 import conv
 from oracle import oracle as O
-from tests import siggen as G
+from algo_dsp_b200 import siggen as G
 
 def rel(y, r): return G.rel_l2(y, r)
 rng = np.random.default_rng(0)

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 from algo_dsp_b200 import conv
-from tests import siggen as G
+from algo_dsp_b200 import siggen as G
 
 def run(K, n, channels, dtype=np.float64, iters=5, env=None, check=None):
     env = env or {}
@@ -49,9 +49,9 @@ if __name__ == "__main__":
     K, n = 96000, 480000
     run(K, n, 64, check=63)
     for N in (1 << 18, 1 << 19, 1 << 20):
-        for N2 in (1024, 2048, 4096):
+        for N2 in (2048, 4096):
             run(K, n, 256, env=dict(ADSP_FFT_N=N, ADSP_FFT_N2=N2))
-    for mb in (16, 32, 48, 96, 160, 400):
+    for mb in (24, 48, 96, 200):
         run(K, n, 256, env=dict(ADSP_FFT_N=1 << 19, ADSP_SCRATCH_MB=mb))
     run(K, n, 256, dtype=np.float32, check=5)
     run(1000, 1 << 20, 256, check=3)
