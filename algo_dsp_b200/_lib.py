@@ -30,6 +30,8 @@ PROTOTYPES = {
     "adsp_ctx_sync": (C.c_int, [c_vp]),
     "adsp_ctx_launch_count": (C.c_uint64, [c_vp]),
     "adsp_ctx_stream": (c_vp, [c_vp]),
+    "adsp_ctx_kernel_timing": (None, [c_vp, C.c_int]),
+    "adsp_ctx_kernel_time": (C.c_int, [c_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]),
     "adsp_host_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(c_vp)]),
     "adsp_host_free_pinned": (None, [c_vp]),
     "adsp_device_alloc": (C.c_int, [c_vp, C.c_size_t, C.POINTER(c_vp)]),

@@ -95,6 +95,22 @@ class Context:
     def stream(self) -> int:
         return int(L.load().adsp_ctx_stream(self._h) or 0)
 
+    KERNEL_KINDS = ("cols_fwd", "rows", "cols_inv", "full", "direct", "other")
+
+    def kernel_timing(self, enable: bool):
+        L.load().adsp_ctx_kernel_timing(self._h, 1 if enable else 0)
+
+    def kernel_times(self, reset=True):
+        """{kind: (total_ms, launches)} accumulated while kernel_timing was on."""
+        out = {}
+        for i, name in enumerate(self.KERNEL_KINDS):
+            ms, n = C.c_double(), C.c_uint64()
+            _check(L.load().adsp_ctx_kernel_time(self._h, i, C.byref(ms), C.byref(n), 0))
+            out[name] = (ms.value, n.value)
+        if reset:
+            _check(L.load().adsp_ctx_kernel_time(self._h, 0, None, None, 1))
+        return out
+
     def close(self):
         if self._h:
             L.load().adsp_ctx_destroy(self._h)
@@ -105,6 +121,20 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array backed by page-locked host memory (adsp_host_alloc_pinned); keep a reference to
+    the returned array -- the memory is released when it is garbage collected."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    ptr = C.c_void_p()
+    _check(L.load().adsp_host_alloc_pinned(n * dtype.itemsize, C.byref(ptr)))
+    buf = (C.c_char * (n * dtype.itemsize)).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    import weakref
+    weakref.finalize(buf, L.load().adsp_host_free_pinned, ptr)
+    return arr
 
 
 _default_ctx: dict[int, Context] = {}
@@ -342,11 +372,13 @@ class _Plan:
             raise TypeError("output must be a contiguous numpy array of the plan's dtype")
         _check(L.load().adsp_plan_process(self._h, _p(x), x.size, _p(output), output.size))
 
-    def ProcessBatch(self, x2d):
-        """All rows of x2d (channels x n) in one call."""
-        x = np.ascontiguousarray(x2d, dtype=self._dtype)
+    def ProcessBatch(self, x2d, out=None):
+        """All rows of x2d (channels x n) in one call (host buffers; pinned ones DMA directly)."""
+        x = x2d if (isinstance(x2d, np.ndarray) and x2d.dtype == self._dtype and x2d.flags.c_contiguous) else \
+            np.ascontiguousarray(x2d, dtype=self._dtype)
         ch, n = x.shape
-        out = np.empty((ch, n + self.KernelLen() - 1), dtype=self._dtype)
+        if out is None:
+            out = np.empty((ch, n + self.KernelLen() - 1), dtype=self._dtype)
         _check(L.load().adsp_plan_process_batch(self._h, _p(x), n, ch, n, _p(out), out.shape[1]))
         return out
 

@@ -103,6 +103,7 @@ adsp_status direct_device(adsp_ctx *ctx, const T *d_a, long long n, long long a_
     if (grid <= 0) return ADSP_OK;
     if (grid > 0x7fffffffLL) { set_error("direct: grid too large"); return ADSP_ERR_INVALID_ARG; }
     static const bool exact = env_ll("ADSP_DIRECT_EXACT", 0) != 0;
+    LaunchTimer lt(ctx, ctx->main, KK_DIRECT);
     if (exact)
         direct_conv_kernel<T, false><<<(unsigned)grid, DIRECT_THREADS, 0, ctx->main>>>(d_a, n, a_stride, d_b, m, b_stride, d_out, out_stride, tiles);
     else
@@ -211,7 +212,9 @@ static adsp_status plan_run_device(adsp_plan *p, const T *d_in, long long n, lon
     return ADSP_OK;
 }
 
-// host-pointer batch: stage through device buffers owned by the context
+// host-pointer batch.  Small calls: one H2D, compute, one D2H.  Large multi-channel calls: channel
+// chunks flow through a three-stage pipeline (H2D on copy_in | kernels on main+workers | D2H on
+// copy_out) with two device slots per direction, so both PCIe directions and the SMs overlap.
 template <typename T>
 static adsp_status plan_run_host(adsp_plan *p, const T *in, long long n, long long channels, long long in_stride,
                                  T *out, long long out_stride) {
@@ -219,13 +222,46 @@ static adsp_status plan_run_host(adsp_plan *p, const T *in, long long n, long lo
     const long long out_len = n + p->K - 1;
     // device layout: dense rows padded to 32 elements so every channel starts 256-byte aligned
     const long long dis = ((n + 31) / 32) * 32, dos = ((out_len + 31) / 32) * 32;
-    ADSP_TRY(ctx->d_in.reserve((size_t)dis * channels * sizeof(T)));
-    ADSP_TRY(ctx->d_out.reserve((size_t)dos * channels * sizeof(T)));
-    ADSP_TRY(copy2d(ctx, ctx->d_in.p, (size_t)dis * sizeof(T), in, (size_t)in_stride * sizeof(T), (size_t)n * sizeof(T),
-                    (size_t)channels, cudaMemcpyHostToDevice));
-    ADSP_TRY(plan_run_device<T>(p, (const T *)ctx->d_in.p, n, channels, dis, (T *)ctx->d_out.p, dos));
-    ADSP_TRY(copy2d(ctx, out, (size_t)out_stride * sizeof(T), ctx->d_out.p, (size_t)dos * sizeof(T),
-                    (size_t)out_len * sizeof(T), (size_t)channels, cudaMemcpyDeviceToHost));
+    const size_t row_bytes = (size_t)(dis + dos) * sizeof(T);
+    const long long chunk_target = env_ll("ADSP_PIPE_CHUNK_MB", 96) << 20;
+    long long cc = (long long)(chunk_target / (long long)row_bytes);
+    if (cc < 2) cc = 2;
+    if (channels < 4 || (size_t)channels * row_bytes < (size_t)(32u << 20) || cc >= channels) {
+        ADSP_TRY(ctx->d_in.reserve((size_t)dis * channels * sizeof(T)));
+        ADSP_TRY(ctx->d_out.reserve((size_t)dos * channels * sizeof(T)));
+        ADSP_TRY(copy2d(ctx, ctx->d_in.p, (size_t)dis * sizeof(T), in, (size_t)in_stride * sizeof(T), (size_t)n * sizeof(T),
+                        (size_t)channels, cudaMemcpyHostToDevice));
+        ADSP_TRY(plan_run_device<T>(p, (const T *)ctx->d_in.p, n, channels, dis, (T *)ctx->d_out.p, dos));
+        ADSP_TRY(copy2d(ctx, out, (size_t)out_stride * sizeof(T), ctx->d_out.p, (size_t)dos * sizeof(T),
+                        (size_t)out_len * sizeof(T), (size_t)channels, cudaMemcpyDeviceToHost));
+        ADSP_CUDA(cudaStreamSynchronize(ctx->main));
+        return ADSP_OK;
+    }
+    for (int s = 0; s < 2; s++) {
+        ADSP_TRY(ctx->pipe_in[s].reserve((size_t)dis * cc * sizeof(T)));
+        ADSP_TRY(ctx->pipe_out[s].reserve((size_t)dos * cc * sizeof(T)));
+    }
+    long long idx = 0;
+    for (long long c0 = 0; c0 < channels; c0 += cc, idx++) {
+        const long long nc = std::min(cc, channels - c0);
+        const int s = (int)(idx & 1);
+        // stage 1: H2D (slot free once the compute that last used it is done)
+        if (idx >= 2) ADSP_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_comp[s], 0));
+        ADSP_CUDA(cudaMemcpy2DAsync(ctx->pipe_in[s].p, (size_t)dis * sizeof(T), in + c0 * in_stride, (size_t)in_stride * sizeof(T),
+                                    (size_t)n * sizeof(T), (size_t)nc, cudaMemcpyHostToDevice, ctx->copy_in));
+        ADSP_CUDA(cudaEventRecord(ctx->ev_in[s], ctx->copy_in));
+        // stage 2: kernels (output slot free once its previous D2H is done)
+        ADSP_CUDA(cudaStreamWaitEvent(ctx->main, ctx->ev_in[s], 0));
+        if (idx >= 2) ADSP_CUDA(cudaStreamWaitEvent(ctx->main, ctx->ev_out[s], 0));
+        ADSP_TRY(plan_run_device<T>(p, (const T *)ctx->pipe_in[s].p, n, nc, dis, (T *)ctx->pipe_out[s].p, dos));
+        ADSP_CUDA(cudaEventRecord(ctx->ev_comp[s], ctx->main));
+        // stage 3: D2H
+        ADSP_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_comp[s], 0));
+        ADSP_CUDA(cudaMemcpy2DAsync(out + c0 * out_stride, (size_t)out_stride * sizeof(T), ctx->pipe_out[s].p, (size_t)dos * sizeof(T),
+                                    (size_t)out_len * sizeof(T), (size_t)nc, cudaMemcpyDeviceToHost, ctx->copy_out));
+        ADSP_CUDA(cudaEventRecord(ctx->ev_out[s], ctx->copy_out));
+    }
+    ADSP_CUDA(cudaStreamSynchronize(ctx->copy_out));
     ADSP_CUDA(cudaStreamSynchronize(ctx->main));
     return ADSP_OK;
 }
@@ -296,6 +332,13 @@ adsp_status adsp_ctx_create(int device, adsp_ctx **out) {
         ADSP_CUDA(cudaStreamCreateWithFlags(&c->worker[i], cudaStreamNonBlocking));
         ADSP_CUDA(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
     }
+    ADSP_CUDA(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
+    ADSP_CUDA(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        ADSP_CUDA(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+        ADSP_CUDA(cudaEventCreateWithFlags(&c->ev_comp[i], cudaEventDisableTiming));
+        ADSP_CUDA(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
+    }
     *out = c;
     return ADSP_OK;
 }
@@ -307,7 +350,13 @@ void adsp_ctx_destroy(adsp_ctx *c) {
     for (auto &kv : c->tw_tables) cudaFree(kv.second);
     for (auto &kv : c->tw4_tables) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
     c->scratch.release(); c->d_in.release(); c->d_out.release(); c->d_k.release(); c->d_tmp.release(); c->d_small.release();
-    for (int i = 0; i < 2; i++) { c->h_in[i].release(); c->h_out[i].release(); }
+    for (int i = 0; i < 2; i++) {
+        c->h_in[i].release(); c->h_out[i].release(); c->pipe_in[i].release(); c->pipe_out[i].release();
+        cudaEventDestroy(c->ev_in[i]); cudaEventDestroy(c->ev_comp[i]); cudaEventDestroy(c->ev_out[i]);
+    }
+    for (auto &t : c->timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+    for (auto e : c->event_pool) cudaEventDestroy(e);
+    cudaStreamDestroy(c->copy_in); cudaStreamDestroy(c->copy_out);
     c->h_small.release();
     for (int i = 0; i < kWorkerStreams; i++) { cudaStreamDestroy(c->worker[i]); cudaEventDestroy(c->ev_join[i]); }
     cudaEventDestroy(c->ev_fork);
@@ -323,6 +372,27 @@ adsp_status adsp_ctx_sync(adsp_ctx *c) {
 }
 
 uint64_t adsp_ctx_launch_count(adsp_ctx *c) { return c ? c->launches.load() : 0; }
+
+void adsp_ctx_kernel_timing(adsp_ctx *c, int enable) {
+    if (!c) return;
+    c->timing = enable != 0;
+}
+
+adsp_status adsp_ctx_kernel_time(adsp_ctx *c, int kind, double *total_ms, uint64_t *launches, int reset) {
+    if (!c || kind < 0 || kind >= 8) return ADSP_ERR_INVALID_ARG;
+    ADSP_CUDA(cudaSetDevice(c->device));
+    ADSP_CUDA(cudaDeviceSynchronize());
+    for (auto &t : c->timed) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, t.e0, t.e1) == cudaSuccess) { c->kind_ms[t.kind] += ms; c->kind_launches[t.kind]++; }
+        c->event_pool.push_back(t.e0); c->event_pool.push_back(t.e1);
+    }
+    c->timed.clear();
+    if (total_ms) *total_ms = c->kind_ms[kind];
+    if (launches) *launches = c->kind_launches[kind];
+    if (reset) for (int k = 0; k < 8; k++) { c->kind_ms[k] = 0; c->kind_launches[k] = 0; }
+    return ADSP_OK;
+}
 void *adsp_ctx_stream(adsp_ctx *c) { return c ? (void *)c->main : nullptr; }
 
 adsp_status adsp_host_alloc_pinned(size_t bytes, void **out) {

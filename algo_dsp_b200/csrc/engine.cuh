@@ -80,6 +80,17 @@ struct adsp_ctx {
     adsp::PinnedBuf h_in[2], h_out[2], h_small;
     std::atomic<uint64_t> launches{0};
     size_t scratch_budget = 0;  // bytes of scratch allowed in flight (fits L2)
+    // host-staged pipeline (H2D | compute | D2H overlapped over channel chunks)
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    adsp::DevBuf pipe_in[2], pipe_out[2];
+    // optional per-kernel timing (bench roofline): event pairs around every launch of a kind
+    bool timing = false;
+    struct TimedLaunch { int kind; cudaEvent_t e0, e1; };
+    std::vector<TimedLaunch> timed;
+    std::vector<cudaEvent_t> event_pool;
+    double kind_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t kind_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 namespace adsp {
@@ -114,5 +125,22 @@ adsp_status direct_device(adsp_ctx *ctx, const T *d_a, long long n, long long a_
                           long long b_stride, long long batch, T *d_out, long long out_stride);
 
 inline void count_launch(adsp_ctx *ctx, int n = 1) { ctx->launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+enum KernelKind { KK_COLS_FWD = 0, KK_ROWS = 1, KK_COLS_INV = 2, KK_FULL = 3, KK_DIRECT = 4, KK_OTHER = 5 };
+
+// RAII bracket: when ctx->timing is on, records an event pair around one launch
+struct LaunchTimer {
+    adsp_ctx *ctx; cudaStream_t st; int kind; cudaEvent_t e0 = nullptr;
+    static cudaEvent_t get(adsp_ctx *c) {
+        if (!c->event_pool.empty()) { cudaEvent_t e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
+        cudaEvent_t e = nullptr; cudaEventCreate(&e); return e;
+    }
+    LaunchTimer(adsp_ctx *c, cudaStream_t s, int k) : ctx(c), st(s), kind(k) {
+        if (ctx->timing) { e0 = get(ctx); cudaEventRecord(e0, st); }
+    }
+    ~LaunchTimer() {
+        if (e0) { cudaEvent_t e1 = get(ctx); cudaEventRecord(e1, st); ctx->timed.push_back({kind, e0, e1}); }
+    }
+};
 
 }  // namespace adsp

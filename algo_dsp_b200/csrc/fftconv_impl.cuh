@@ -126,6 +126,7 @@ static adsp_status launch_full_t(adsp_ctx *ctx, cudaStream_t st, const ConvGeom 
     static AttrOnce once;
     if (once.need(ctx->device)) ADSP_TRY(set_smem(fftconv_full<T, L, SPEC>, smem));
     const long long grid = (npairs + ROWS - 1) / ROWS;
+    LaunchTimer lt(ctx, st, KK_FULL);
     fftconv_full<T, L, SPEC><<<(unsigned)grid, 256, smem, st>>>(g, x, y, H, spec, scale, tw, npairs);
     count_launch(ctx);
     ADSP_CUDA(cudaGetLastError());
@@ -153,6 +154,7 @@ static adsp_status launch_rows_t(adsp_ctx *ctx, cudaStream_t st, cpx<T> *scratch
     static AttrOnce once;
     if (once.need(ctx->device)) ADSP_TRY(set_smem(fftconv_rows<T, L, SPEC>, smem));
     dim3 grid((unsigned)(N1 / ROWS > 0 ? N1 / ROWS : 1), (unsigned)pairs);
+    LaunchTimer lt(ctx, st, KK_ROWS);
     fftconv_rows<T, L, SPEC><<<grid, 256, smem, st>>>(scratch, H, spec, scale, N1, tw);
     count_launch(ctx);
     ADSP_CUDA(cudaGetLastError());
@@ -184,6 +186,7 @@ static adsp_status launch_cols_t(adsp_ctx *ctx, cudaStream_t st, bool inverse, c
         ADSP_TRY(set_smem(fftconv_cols_inv<T, N1>, smem));
     }
     dim3 grid((unsigned)(N2 / CS::TC), (unsigned)pairs);
+    LaunchTimer lt(ctx, st, inverse ? KK_COLS_INV : KK_COLS_FWD);
     if (!inverse)
         fftconv_cols_fwd<T, N1><<<grid, CS::THREADS, smem, st>>>(g, x, scratch, N2, lgN, tw, hi, lo, pair0);
     else

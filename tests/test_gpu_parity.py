@@ -1,0 +1,267 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs,
+against the committed golden fixtures, and -- at BASELINE.json's full sizes -- through
+size-independent properties.  Tolerances are the north star's: fp64 <= 1e-12 relative L2,
+fp32 <= 1e-5 relative L2."""
+import os
+
+import numpy as np
+import pytest
+
+from algo_dsp_b200 import siggen as G
+
+pytestmark = pytest.mark.gpu
+
+TOL64 = 1e-12
+TOL32 = 1e-5
+FIX = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_fixtures.npz"))
+
+
+def rel(y, ref):
+    return G.rel_l2(y, ref)
+
+
+# ---------------------------------------------------------------- golden fixtures
+@pytest.mark.parametrize("name", ["ols_k300_n5000", "ols_k4097_n20000", "ols_k1_n100", "ols_k900_n100"])
+def test_fixture_overlap_save(conv, name):
+    h, x, y = FIX[name + "_h"], FIX[name + "_x"], FIX[name + "_y"]
+    assert rel(conv.NewOverlapSave(h, 0).Process(x), y) <= TOL64
+    assert rel(conv.NewOverlapAdd(h, 0).Process(x), y) <= TOL64
+    assert rel(conv.OverlapSaveConvolve(x, h), y) <= TOL64
+
+
+def test_fixture_direct_correlate_partitioned(conv):
+    assert rel(conv.Convolve(FIX["direct_k64_x"], FIX["direct_k64_h"]), FIX["direct_k64_y"]) <= TOL64
+    c = conv.Correlate(FIX["corr_a"], FIX["corr_b"])
+    assert rel(c, FIX["corr_y"]) <= TOL64
+    idx, val = conv.FindPeak(c)
+    assert idx == int(FIX["corr_peak"][0]) and abs(val - FIX["corr_peak"][1]) <= 1e-9 * abs(val)
+    p = conv.NewPartitionedConvolution(FIX["part_h"], 6, 13)
+    out = np.zeros(len(FIX["part_x"]))
+    p.ProcessBlock(FIX["part_x"], out)
+    assert rel(out, FIX["part_y"]) <= TOL64
+    y32 = conv.NewOverlapSave(FIX["ols32_h"], 0, dtype=np.float32).Process(FIX["ols32_x"])
+    assert y32.dtype == np.float32 and rel(y32, FIX["ols32_y"]) <= TOL32
+
+
+# ---------------------------------------------------------------- oracle on seeded inputs
+OLS_SHAPES = [(1, 1), (1, 777), (2, 3), (3, 1000), (64, 4096), (65, 1000), (100, 99), (257, 5000), (1000, 30000), (1025, 10000),
+              (2049, 100000), (5000, 50000), (9000, 9000), (20000, 100000), (33000, 10), (50000, 300000), (131073, 300000)]
+
+
+@pytest.mark.parametrize("K,n", OLS_SHAPES)
+def test_overlap_save_and_add_vs_oracle(conv, oracle, K, n):
+    h, x = G.decaying_ir(K, seed=7), G.white(n, seed=K + n)
+    ref = oracle.overlap_save(h, 0, x)
+    ols = conv.NewOverlapSave(h, 0)
+    assert (ols.FFTSize(), ols.StepSize()) == oracle.ols_sizes(K, 0)       # getters report the reference's values
+    y = ols.Process(x)
+    assert len(y) == n + K - 1 and rel(y, ref) <= TOL64
+    ola = conv.NewOverlapAdd(h, 0)
+    assert (ola.BlockSize(), ola.FFTSize()) == oracle.ola_sizes(K, 0)
+    assert rel(ola.Process(x), oracle.overlap_add(h, 0, x)) <= TOL64
+    # Process is stateless across calls (overlap_save.go:136-138): a second call gives the same answer
+    assert np.array_equal(ols.Process(x), y)
+
+
+def test_config1_ols_96k_taps(conv, oracle):
+    """BASELINE config 1: 10 s white noise @48 kHz, 96 000-tap decaying IR, mono f64."""
+    h, x = G.decaying_ir(96000), G.white(480000, seed=1)
+    ols = conv.NewOverlapSave(h, 0)
+    assert (ols.FFTSize(), ols.StepSize(), ols.KernelLen()) == (262144, 166145, 96000)
+    y = ols.Process(x)
+    assert len(y) == 575999
+    assert rel(y, oracle.overlap_save(h, 0, x)) <= TOL64
+    y32 = conv.NewOverlapSave(h, 0, dtype=np.float32).Process(x)
+    assert rel(y32, oracle.overlap_save(h, 0, x)) <= TOL32
+
+
+def test_user_fft_sizes_and_errors(conv, oracle):
+    h, x = G.decaying_ir(300), G.white(5000, seed=3)
+    for f in (1024, 4096, 256):            # 256 < 2K is silently raised (overlap_save.go:71-73)
+        c = conv.NewOverlapSave(h, f)
+        assert (c.FFTSize(), c.StepSize()) == oracle.ols_sizes(300, f)
+        assert rel(c.Process(x), oracle.overlap_save(h, f, x)) <= TOL64
+    for b in (32, 100, 4096):              # OLA block size need not be a power of two
+        c = conv.NewOverlapAdd(h, b)
+        assert (c.BlockSize(), c.FFTSize()) == oracle.ola_sizes(300, b)
+        assert rel(c.Process(x), oracle.overlap_add(h, b, x)) <= TOL64
+    with pytest.raises(conv.ConvError) as ei:
+        conv.NewOverlapSave(h, 1000)
+    assert conv.errors_is(ei.value, conv.ErrInvalidBlockSize)
+    with pytest.raises(conv.ConvError) as ei:
+        conv.NewOverlapSave([], 0)
+    assert conv.errors_is(ei.value, conv.ErrEmptyKernel)
+    with pytest.raises(conv.ConvError) as ei:
+        conv.NewOverlapSave(h, 0).Process([])
+    assert conv.errors_is(ei.value, conv.ErrEmptyInput)
+    with pytest.raises(conv.ConvError) as ei:
+        conv.NewOverlapSave(h, 0).ProcessTo(np.zeros(5), x)
+    assert conv.errors_is(ei.value, conv.ErrLengthMismatch)
+
+
+@pytest.mark.parametrize("n,m", [(10, 1), (1000, 3), (4096, 16), (5000, 15), (100000, 64), (64, 100000), (70, 65), (3, 3)])
+def test_convolve_auto_select_vs_oracle(conv, oracle, n, m):
+    """Convolve: swap so the longer operand is the signal, direct iff the shorter has <= 64 taps."""
+    a, b = G.white(n, seed=n), G.white(m, seed=m + 1)
+    ref = oracle.convolve(a, b)
+    assert rel(conv.Convolve(a, b), ref) <= TOL64
+    assert rel(conv.Direct(a, b), oracle.direct(a, b)) <= TOL64
+    for mode in (conv.ModeFull, conv.ModeSame, conv.ModeValid):
+        got, want = conv.ConvolveMode(a, b, mode), oracle.convolve_mode(a, b, mode)
+        assert len(got) == len(want) and rel(got, want) <= TOL64
+
+
+def test_direct_long_kernel_and_f32(conv, oracle):
+    a, b = G.white(3000, seed=1), G.white(700, seed=2)
+    assert rel(conv.Direct(a, b), oracle.direct(a, b)) <= TOL64          # Direct is legal for any kernel length
+    a32, b32 = a.astype(np.float32), G.test_kernel(64).astype(np.float32)
+    assert rel(conv.Direct32(a32, b32), oracle.direct(a32, b32, np.float32)) <= TOL32
+    assert rel(conv.Convolve32(a32, b.astype(np.float32)), oracle.convolve(a, b)) <= TOL32
+
+
+def test_direct_batch_config2_shape(conv, oracle):
+    """Config 2 shape (channels x samples, 64-tap Hann-windowed sinc), reduced channel count."""
+    ch, n = 8, 1 << 16
+    x = np.stack([G.white(n, seed=1 + c) for c in range(ch)])
+    k = G.test_kernel(64)
+    y = conv.DirectBatch(x, k)
+    assert y.shape == (ch, n + 63)
+    for c in (0, ch - 1):
+        assert rel(y[c], oracle.direct(x[c], k)) <= TOL64
+    # per-channel kernels
+    ks = np.stack([k * (c + 1) for c in range(ch)])
+    y2 = conv.DirectBatch(x, ks)
+    assert rel(y2[3], oracle.direct(x[3], ks[3])) <= TOL64
+
+
+@pytest.mark.parametrize("n,m", [(11, 5), (3000, 700), (700, 3000), (100000, 50), (65536, 65536)])
+def test_correlation_family_vs_oracle(conv, oracle, n, m):
+    a, b = G.white(n, seed=n + 5), G.white(m, seed=m + 6)
+    ref = oracle.correlate(a, b)
+    got = conv.Correlate(a, b)
+    assert len(got) == n + m - 1 and rel(got, ref) <= TOL64
+    assert rel(conv.CorrelateFFT(a, b), oracle.correlate_fft(a, b)) <= TOL64
+    assert rel(conv.CorrelateNormalized(a, b), oracle.correlate_normalized(a, b)) <= TOL64
+    assert conv.FindPeak(got)[0] == oracle.find_peak(ref)[0]
+    if n * m <= 3_000_000:
+        assert rel(conv.CorrelateDirect(a, b), oracle.correlate_direct(a, b)) <= TOL64
+    for mode in (conv.ModeSame, conv.ModeValid):
+        assert rel(conv.CorrelateMode(a, b, mode), oracle.correlate_mode(a, b, mode)) <= TOL64
+    assert rel(conv.AutoCorrelateNormalized(a), oracle.auto_correlate_normalized(a)) <= TOL64
+
+
+def test_find_peak_rules(conv):
+    assert conv.FindPeak([]) == (-1, 0.0)                       # correlate.go:201-203
+    assert conv.FindPeak([3, 7, 7, 1]) == (1, 7.0)              # first maximum wins (strict >)
+    assert conv.FindPeak([-5, -2, -9]) == (1, -2.0)             # signed, not absolute
+    x = np.zeros(1 << 20)
+    x[[12345, 999999]] = 2.5
+    assert conv.FindPeak(x) == (12345, 2.5)
+    assert conv.FindPeak([1.0]) == (0, 1.0)
+
+
+def test_correlate_batch_peak_lag_config4_shape(conv, oracle):
+    """Config 4 shape, reduced: sweep/response pairs, delay recovered exactly from the peak lag."""
+    n, pairs = 1 << 16, 4
+    sweep = G.log_sweep(n)
+    a = np.zeros((pairs, n))
+    delays = [0, 17, 1000, 4095]
+    for p, d in enumerate(delays):
+        a[p, d:] = sweep[: n - d]
+        a[p] += G.white(n, seed=1000 + p, amp=0.01)
+    b = np.tile(sweep, (pairs, 1))
+    out, pi, pv = conv.CorrelateBatch(a, b)
+    for p, d in enumerate(delays):
+        assert conv.LagFromIndex(int(pi[p]), n) == d
+    assert rel(out[2], oracle.correlate(a[2], b[2])) <= TOL64
+    _, pi2, _ = conv.CorrelateBatch(a, b, want_output=False)
+    assert np.array_equal(pi, pi2)
+
+
+# ---------------------------------------------------------------- partitioned / streaming semantics
+@pytest.mark.parametrize("K,n,mn,mx,chunk", [(64, 512, 4, 10, 0), (1024, 4096, 6, 13, 0), (8192, 16384, 6, 13, 1000),
+                                              (3000, 9000, 7, 13, 128), (96000, 200000, 7, 13, 48000)])
+def test_partitioned_vs_oracle(conv, oracle, K, n, mn, mx, chunk):
+    """ProcessBlock (partitioned.go:348-396): conv delayed by 2^minOrder, arbitrary call sizes."""
+    h, x = G.exp_kernel(K, 0.9999 if K > 10000 else 0.99), G.white(n, seed=K)
+    ref = oracle.Partitioned(h, mn, mx).process_block(x)
+    p = conv.NewPartitionedConvolution(h, mn, mx)
+    assert p.Latency() == 1 << mn and p.KernelLen() == K
+    if chunk == 0:
+        out = np.zeros(n)
+        p.ProcessBlock(x, out)
+    else:
+        parts = []
+        for i in range(0, n, chunk):
+            o = np.zeros(len(x[i:i + chunk]))
+            p.ProcessBlock(x[i:i + chunk], o)
+            parts.append(o)
+        out = np.concatenate(parts)
+    assert rel(out, ref) <= TOL64
+    p.Reset()
+    out2 = np.zeros(n)
+    p.ProcessBlock(x, out2)
+    assert rel(out2, ref) <= TOL64
+
+
+def test_partitioned_f32(conv, oracle):
+    h, x = G.exp_kernel(2000).astype(np.float32), G.white(8000, seed=9).astype(np.float32)
+    ref = oracle.Partitioned(h.astype(np.float64), 6, 13).process_block(x.astype(np.float64))
+    p = conv.NewPartitionedConvolution32(h, 6, 13)
+    out = np.zeros(len(x), np.float32)
+    p.ProcessBlock(x, out)
+    assert rel(out, ref) <= TOL32
+
+
+# ---------------------------------------------------------------- full-size properties (BASELINE sizes)
+def test_full_size_batch_properties(conv, oracle):
+    """Bench workload shape (96k taps, many channels): spot-check channels against the oracle and
+    check linearity / DC-gain / impulse identities on the whole batch."""
+    K, n, ch = 96000, 480000, 16
+    h = G.decaying_ir(K)
+    x = np.stack([G.white(n, seed=1 + c) for c in range(ch)])
+    ols = conv.NewOverlapSave(h, 0)
+    y = ols.ProcessBatch(x)
+    assert y.shape == (ch, n + K - 1)
+    for c in (0, 7, ch - 1):
+        assert rel(y[c], oracle.overlap_save(h, 0, x[c])) <= TOL64
+    # DC gain: sum(y) = sum(x) * sum(h)
+    assert np.allclose(y.sum(axis=1), x.sum(axis=1) * h.sum(), rtol=1e-9, atol=1e-6)
+    # linearity across channels: conv(2*x0 - 3*x1) == 2*y0 - 3*y1
+    z = ols.Process(2 * x[0] - 3 * x[1])
+    assert rel(z, 2 * y[0] - 3 * y[1]) <= 1e-12
+    # impulse at t0 returns the IR shifted by t0
+    d = np.zeros(n)
+    d[12345] = 1.0
+    yi = ols.Process(d)
+    assert rel(yi[12345:12345 + K], h) <= 1e-12 and np.max(np.abs(yi[:12345])) <= 1e-13
+
+
+def test_long_kernel_partitions_config5_shape(conv, oracle):
+    """Kernel longer than half the largest transform -> summed IR partitions (config 5 shape, reduced)."""
+    K, n = 600000, 700000
+    h, x = G.decaying_ir(K), G.white(n, seed=5)
+    c = conv.NewOverlapSave(h, 0)
+    assert c.internal_geometry()["partitions"] >= 2
+    assert rel(c.Process(x), oracle.overlap_save(h, 0, x)) <= TOL64
+
+
+def test_time_block_sharding_with_halo(conv, oracle):
+    """Config 5 decomposition: a long signal cut into time shards with a K-1 halo reproduces the
+    unsharded result exactly where shards abut."""
+    K, n, shards = 5000, 400000, 4
+    h, x = G.decaying_ir(K), G.white(n, seed=11)
+    full = conv.NewOverlapSave(h, 0).Process(x)
+    S = -(-n // shards)
+    c = conv.NewOverlapSave(h, 0)
+    out = np.zeros(n + K - 1)
+    for s in range(shards):
+        lo, hi = s * S, min((s + 1) * S, n)
+        seg = x[max(0, lo - (K - 1)):hi]
+        ys = c.Process(seg)
+        skip = lo - max(0, lo - (K - 1))
+        last = s == shards - 1
+        take = (hi - lo) + (K - 1 if last else 0)
+        out[lo:lo + take] = ys[skip:skip + take]
+    assert rel(out, full) <= 1e-13
+    assert rel(out, oracle.overlap_save(h, 0, x)) <= TOL64
