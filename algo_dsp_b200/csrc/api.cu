@@ -58,21 +58,10 @@ long long env_ll(const char *name, long long dflt) {
 // Internal transform size for K taps.  The API only fixes results, so the GPU is free to use a
 // larger transform than the reference's nextPow2(2K): a longer block wastes less of each
 // transform on the K-1 discarded samples.
-FftChoice choose_fft(long long K) {
+// geometry for a given transform length N and (partition) kernel length Kp
+FftChoice make_choice(long long Kp, long long N) {
     FftChoice c;
-    const long long NMAX = env_ll("ADSP_MAX_FFT", 1LL << 20);
-    long long Kp = K;
-    if (K - 1 > NMAX / 2) {
-        c.parts = (int)((K + NMAX / 2 - 1) / (NMAX / 2));
-        Kp = (K + c.parts - 1) / c.parts;
-    }
     c.part_len = Kp;
-    long long N = next_pow2_ll(8 * Kp);
-    const long long forced = env_ll("ADSP_FFT_N", 0);
-    if (forced > 0) N = forced;
-    if (N < 256) N = 256;
-    if (N > NMAX) N = NMAX;
-    while (N < 2 * Kp && N < (1LL << 22)) N *= 2;
     c.N = N;
     int lg = 0;
     while ((1LL << lg) < N) lg++;
@@ -92,6 +81,59 @@ FftChoice choose_fft(long long K) {
     c.D = D;
     c.S = N - D;
     return c;
+}
+
+FftChoice choose_fft(long long K) {
+    const long long NMAX = env_ll("ADSP_MAX_FFT", 1LL << 20);
+    long long Kp = K;
+    int parts = 1;
+    if (K - 1 > NMAX / 2) {
+        parts = (int)((K + NMAX / 2 - 1) / (NMAX / 2));
+        Kp = (K + parts - 1) / parts;
+    }
+    long long N = next_pow2_ll(8 * Kp);
+    const long long forced = env_ll("ADSP_FFT_N", 0);
+    if (forced > 0) N = forced;
+    if (N < 256) N = 256;
+    if (N > NMAX) N = NMAX;
+    while (N < 2 * Kp && N < (1LL << 22)) N *= 2;
+    FftChoice c = make_choice(Kp, N);
+    c.parts = parts;
+    return c;
+}
+
+// Cover `out_len` output samples with overlap-save blocks of mixed transform lengths: full blocks of
+// the largest length, then the cheapest one or two smaller transforms for the remainder (a 96k-tap
+// IR on a 480k-sample signal needs 2^19 + 2^18 points per channel instead of 2^20).
+struct Segment { long long N; long long off; long long len; };
+static std::vector<Segment> plan_segments(long long out_len, long long K, const FftChoice &big) {
+    std::vector<Segment> segs;
+    const long long full = out_len / big.S;
+    long long rem = out_len - full * big.S;
+    if (full > 0) segs.push_back({big.N, 0, full * big.S});
+    if (rem <= 0) return segs;
+    if (env_ll("ADSP_FFT_N", 0) > 0 || env_ll("ADSP_NO_MIXED", 0) > 0) { segs.push_back({big.N, full * big.S, rem}); return segs; }
+    long long nmin = next_pow2_ll(2 * K);
+    if (nmin < 256) nmin = 256;
+    auto cost = [](long long N) { int lg = 0; while ((1LL << lg) < N) lg++; return (double)N * (lg + 4); };
+    double best = cost(big.N);
+    long long ba = big.N, bb = 0;
+    for (long long Na = big.N; Na >= nmin; Na >>= 1) {
+        const long long Sa = make_choice(K, Na).S;
+        if (Sa <= 0) break;
+        if (Sa >= rem) { if (cost(Na) < best) { best = cost(Na); ba = Na; bb = 0; } continue; }
+        for (long long Nb = Na; Nb >= nmin; Nb >>= 1) {
+            const long long Sb = make_choice(K, Nb).S;
+            if (Sb <= 0 || Sa + Sb < rem) break;
+            if (cost(Na) + cost(Nb) < best) { best = cost(Na) + cost(Nb); ba = Na; bb = Nb; }
+        }
+    }
+    const long long off = full * big.S;
+    const long long Sa = make_choice(K, ba).S;
+    const long long la = std::min(rem, Sa);
+    segs.push_back({ba, off, la});
+    if (bb > 0 && rem > la) segs.push_back({bb, off + la, rem - la});
+    return segs;
 }
 
 template <typename T>
@@ -168,8 +210,11 @@ struct adsp_plan {
     long long K = 0;
     long long ref_fft = 0, ref_step = 0, ref_block = 0;  // what the Go getters report
     FftChoice ch;
-    std::vector<FftConv<double>> fc64;
+    std::vector<FftConv<double>> fc64;   // one per IR partition at the main transform length
     std::vector<FftConv<float>> fc32;
+    DevBuf d_kernel;                     // the IR stays on the device so other transform lengths can be built lazily
+    std::map<long long, FftConv<double>> extra64;   // engines for remainder blocks, keyed by N
+    std::map<long long, FftConv<float>> extra32;
     // partitioned (streaming) state
     int latency = 0, min_order = 0, max_order = 0;
     std::vector<PartStage> stages;
@@ -182,18 +227,21 @@ struct adsp_plan {
 template <typename T> static std::vector<FftConv<T>> &plan_fc(adsp_plan *p);
 template <> std::vector<FftConv<double>> &plan_fc<double>(adsp_plan *p) { return p->fc64; }
 template <> std::vector<FftConv<float>> &plan_fc<float>(adsp_plan *p) { return p->fc32; }
+template <typename T> static std::map<long long, FftConv<T>> &plan_extra(adsp_plan *p);
+template <> std::map<long long, FftConv<double>> &plan_extra<double>(adsp_plan *p) { return p->extra64; }
+template <> std::map<long long, FftConv<float>> &plan_extra<float>(adsp_plan *p) { return p->extra32; }
 
 template <typename T> static adsp_status plan_build(adsp_plan *p, const T *host_kernel) {
     adsp_ctx *ctx = p->ctx;
-    ADSP_TRY(ctx->d_k.reserve((size_t)p->K * sizeof(T)));
-    ADSP_CUDA(cudaMemcpyAsync(ctx->d_k.p, host_kernel, (size_t)p->K * sizeof(T), cudaMemcpyHostToDevice, ctx->main));
+    ADSP_TRY(p->d_kernel.reserve((size_t)p->K * sizeof(T)));
+    ADSP_CUDA(cudaMemcpyAsync(p->d_kernel.p, host_kernel, (size_t)p->K * sizeof(T), cudaMemcpyHostToDevice, ctx->main));
     p->ch = choose_fft(p->K);
     auto &v = plan_fc<T>(p);
     v.resize((size_t)p->ch.parts);
     for (int i = 0; i < p->ch.parts; i++) {
         const long long k0 = (long long)i * p->ch.part_len;
         const long long kp = std::min<long long>(p->ch.part_len, p->K - k0);
-        ADSP_TRY(v[(size_t)i].init(ctx, (const T *)ctx->d_k.p + k0, kp, p->ch));
+        ADSP_TRY(v[(size_t)i].init(ctx, (const T *)p->d_kernel.p + k0, kp, p->ch));
     }
     return ADSP_OK;
 }
@@ -203,7 +251,23 @@ static adsp_status plan_run_device(adsp_plan *p, const T *d_in, long long n, lon
                                    T *d_out, long long out_stride) {
     auto &v = plan_fc<T>(p);
     const long long out_len = n + p->K - 1;
-    if (v.size() == 1) return v[0].run(d_in, n, channels, in_stride, d_out, out_stride, out_len, 0, 0, false);
+    if (v.size() == 1) {
+        for (const Segment &sg : plan_segments(out_len, p->K, p->ch)) {
+            FftConv<T> *fc = &v[0];
+            if (sg.N != p->ch.N) {
+                auto &ex = plan_extra<T>(p);
+                auto it = ex.find(sg.N);
+                if (it == ex.end()) {
+                    FftConv<T> f;
+                    ADSP_TRY(f.init(p->ctx, (const T *)p->d_kernel.p, p->K, make_choice(p->K, sg.N)));
+                    it = ex.emplace(sg.N, f).first;
+                }
+                fc = &it->second;
+            }
+            ADSP_TRY(fc->run(d_in, n, channels, in_stride, d_out, out_stride, sg.len, sg.off, sg.off, false));
+        }
+        return ADSP_OK;
+    }
     ADSP_CUDA(cudaMemset2DAsync(d_out, (size_t)out_stride * sizeof(T), 0, (size_t)out_len * sizeof(T), (size_t)channels, p->ctx->main));
     for (size_t i = 0; i < v.size(); i++) {
         const long long k0 = (long long)i * p->ch.part_len;
@@ -728,6 +792,9 @@ void adsp_plan_destroy(adsp_plan *p) {
     cudaStreamSynchronize(p->ctx->main);
     for (auto &f : p->fc64) f.destroy();
     for (auto &f : p->fc32) f.destroy();
+    for (auto &kv : p->extra64) kv.second.destroy();
+    for (auto &kv : p->extra32) kv.second.destroy();
+    p->d_kernel.release();
     p->hist[0].release(); p->hist[1].release(); p->blk_in.release(); p->blk_out.release();
     delete p;
 }

@@ -60,6 +60,7 @@ struct FftChoice {
 };
 
 FftChoice choose_fft(long long K);
+FftChoice make_choice(long long Kp, long long N);
 long long env_ll(const char *name, long long dflt);
 
 }  // namespace adsp
