@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libalgodsp_cuda.so")
+LIB_PATH = os.environ.get("ADSP_LIB_PATH") or os.path.join(HERE, "libalgodsp_cuda.so")   # override: experimental build variants
 
 c_i64 = C.c_int64
 c_vp = C.c_void_p

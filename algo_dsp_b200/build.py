@@ -40,9 +40,9 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def _compile(src: str, verbose: bool) -> str:
-    obj = os.path.join(BUILD, src.replace(".cu", ".o"))
-    cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+def _compile(src: str, verbose: bool, defines=(), tag: str = "") -> str:
+    obj = os.path.join(BUILD, src.replace(".cu", tag + ".o"))
+    cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -54,19 +54,25 @@ def _compile(src: str, verbose: bool) -> str:
     return obj
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, defines=(), out: str | None = None) -> str:
+    """defines/out build an experimental variant (e.g. defines=["ADSP_COLS_CTA_THREADS=128"],
+    out="libvariant.so") that tools/ can select with ADSP_LIB_PATH; the default build takes neither."""
     os.makedirs(BUILD, exist_ok=True)
     deps = _deps()
-    if not force and not _stale(LIB, deps):
-        return LIB
+    lib = os.path.join(HERE, out) if out else LIB
+    if not force and not _stale(lib, deps):
+        return lib
+    tag = ("_" + os.path.splitext(out)[0]) if out else ""
     with cf.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
-        objs = list(ex.map(lambda s: _compile(s, verbose), SOURCES))
-    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+        objs = list(ex.map(lambda s: _compile(s, verbose, defines, tag), SOURCES))
+    cmd = [_nvcc(), "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=defs, out=outs[0] if outs else None))

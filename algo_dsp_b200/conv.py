@@ -95,7 +95,7 @@ class Context:
     def stream(self) -> int:
         return int(L.load().adsp_ctx_stream(self._h) or 0)
 
-    KERNEL_KINDS = ("cols_fwd", "rows", "cols_inv", "full", "direct", "other")
+    KERNEL_KINDS = ("cols_fwd", "rows", "cols_inv", "full", "direct", "other", "fused")
 
     def kernel_timing(self, enable: bool):
         L.load().adsp_ctx_kernel_timing(self._h, 1 if enable else 0)

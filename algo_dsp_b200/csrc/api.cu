@@ -413,7 +413,7 @@ void adsp_ctx_destroy(adsp_ctx *c) {
     cudaDeviceSynchronize();
     for (auto &kv : c->tw_tables) cudaFree(kv.second);
     for (auto &kv : c->tw4_tables) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
-    c->scratch.release(); c->d_in.release(); c->d_out.release(); c->d_k.release(); c->d_tmp.release(); c->d_small.release();
+    c->scratch.release(); c->d_in.release(); c->d_out.release(); c->d_k.release(); c->d_tmp.release(); c->d_small.release(); c->d_counters.release();
     for (int i = 0; i < 2; i++) {
         c->h_in[i].release(); c->h_out[i].release(); c->pipe_in[i].release(); c->pipe_out[i].release();
         cudaEventDestroy(c->ev_in[i]); cudaEventDestroy(c->ev_comp[i]); cudaEventDestroy(c->ev_out[i]);

@@ -59,23 +59,34 @@ __device__ __forceinline__ BlockIO<T> block_io(const ConvGeom &g, const T *x, T 
 
 template <typename T> __device__ __forceinline__ T ld_stream(const T *p) { return __ldcs(p); }
 
+// CTA shapes (compile-time knobs; tools/ builds variants with -D to A/B them on the GPU).
+// A row CTA owns 16 points per thread: L/16 threads per row, rows_cta_threads(L)/(L/16) rows per CTA.
+#ifndef ADSP_ROWS_SMALL_CTA
+#define ADSP_ROWS_SMALL_CTA 0
+#endif
+#ifndef ADSP_COLS_CTA_THREADS
+#define ADSP_COLS_CTA_THREADS 256
+#endif
+constexpr int rows_cta_threads(int L) { return (ADSP_ROWS_SMALL_CTA && L <= 2048) ? 128 : 256; }
+constexpr int rows_min_ctas(int L) { return 512 / rows_cta_threads(L); }
+
 // ------------------------------------------------------------------------------------------
 // Single-kernel path, N = L <= 4096.  256 threads; 4096/L block-pairs per CTA.
 // SPECTRUM mode: forward transform of x only, scaled, written to `spec` (used once per plan to
 // build the cached IR spectrum, replacing overlap_save.go:96-101).
 template <typename T, int L, bool SPECTRUM>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(rows_cta_threads(L), rows_min_ctas(L))
 fftconv_full(ConvGeom g, const T *__restrict__ x, T *__restrict__ y,
              const cpx<T> *__restrict__ H, cpx<T> *__restrict__ spec, T scale,
              const cpx<T> *__restrict__ tw, long long npairs) {
     using C = cpx<T>;
     using Sh = FftShape<L>;
     constexpr int TPF = Sh::TPF;
-    constexpr int ROWS = 256 / TPF;
+    constexpr int ROWS = rows_cta_threads(L) / TPF;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C *buf = reinterpret_cast<C *>(smem_raw);
     C *stw = buf + ROWS * L;
-    load_tw_smem<T, L>(stw, tw, threadIdx.x, 256);  // visible after the first __syncthreads in cta_fft
+    load_tw_smem<T, L>(stw, tw, threadIdx.x, rows_cta_threads(L));  // visible after the first __syncthreads in cta_fft
 
     const int row = threadIdx.x / TPF;
     const int j = threadIdx.x % TPF;
@@ -156,32 +167,29 @@ template <typename C> __device__ __forceinline__ void geometric16(C base, C rho,
 
 template <int N1> struct ColShape {
     static constexpr int TPF = N1 / 16;                         // threads per column transform
-    static constexpr int TC = (N1 <= 256) ? (256 / TPF) : ((N1 == 512) ? 16 : 8);  // columns per tile
+    static constexpr int TC = (N1 <= 256) ? (ADSP_COLS_CTA_THREADS / TPF) : ((N1 == 512) ? 16 : 8);  // columns per tile
     static constexpr int THREADS = TPF * TC;
     static constexpr int SMEM_ELEMS = N1 * TC;
-    static constexpr int MIN_CTAS = (THREADS <= 256) ? 2 : 1;
+    static constexpr int MIN_CTAS = (THREADS <= 128) ? 4 : ((THREADS <= 256) ? 2 : 1);
 };
 
-// Forward column pass.  grid = (N2/TC, pairs in this group).  Writes A[k1][n2] * W_N^(k1*n2)
-// to scratch (row-major N1 x N2 per pair).
+// ------------------------------------------------------------------------------------------
+// Tile bodies (device functions) shared by the stand-alone kernels and the persistent fused kernel.
+// Scratch is read with ld.global.cg (L2 only): in the fused kernel another CTA produced it, and L1
+// could hold stale lines from an earlier use of the same scratch slot.
+
+// Forward column tile: N1-point transforms down TC columns of the N1 x N2 view of block pair `pair`,
+// times the four-step twiddle W_N^(k1*n2), written to scratch (row-major N1 x N2).
 template <typename T, int N1>
-__global__ void __launch_bounds__(ColShape<N1>::THREADS, ColShape<N1>::MIN_CTAS)
-fftconv_cols_fwd(ConvGeom g, const T *__restrict__ x, cpx<T> *__restrict__ scratch, int N2, int lgN,
-                 const cpx<T> *__restrict__ tw, const cpx<T> *__restrict__ tw_hi,
-                 const cpx<T> *__restrict__ tw_lo, long long pair0) {
+__device__ __forceinline__ void cols_fwd_tile(const ConvGeom &g, const T *__restrict__ x, cpx<T> *__restrict__ scratch_pair,
+                                              int N2, int lgN, const cpx<T> *stw, const cpx<T> *__restrict__ tw_hi,
+                                              const cpx<T> *__restrict__ tw_lo, long long pair, int tile, cpx<T> *buf) {
     using C = cpx<T>;
     using CS = ColShape<N1>;
     constexpr int TPF = CS::TPF, TC = CS::TC;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    C *buf = reinterpret_cast<C *>(smem_raw);
-
-    C *stw = buf + ((FftShape<N1>::P > 0) ? CS::SMEM_ELEMS : 0);
-    load_tw_smem<T, N1>(stw, tw, threadIdx.x, CS::THREADS);
-
     const int c = threadIdx.x % TC;
     const int j = threadIdx.x / TC;
-    const int n2 = blockIdx.x * TC + c;
-    const long long pair = pair0 + blockIdx.y;
+    const int n2 = tile * TC + c;
     ColAddr<TC> addr{c};
 
     // four-step twiddle seeds, fetched first so their latency hides behind the data loads
@@ -201,94 +209,69 @@ fftconv_cols_fwd(ConvGeom g, const T *__restrict__ x, cpx<T> *__restrict__ scrat
     }
     cta_fft<T, N1, false>(e, buf, addr, stw, j);
 
-    // four-step twiddle: k1 = j + r*TPF  ->  W_N^(n2*j) * (W_N^(n2*TPF))^r
+    // k1 = j + r*TPF  ->  W_N^(n2*j) * (W_N^(n2*TPF))^r
     C gtw[16];
     geometric16(tw_base, tw_rho, gtw);
-    C *dst = scratch + (size_t)blockIdx.y * ((size_t)N1 * N2) + n2;
+    C *dst = scratch_pair + n2;
 #pragma unroll
-    for (int r = 0; r < 16; r++) dst[(size_t)(j + r * TPF) * N2] = cmul(e[r], gtw[r]);
+    for (int r = 0; r < 16; r++) __stcg(&dst[(size_t)(j + r * TPF) * N2], cmul(e[r], gtw[r]));
 }
 
-// Row pass, in place on scratch: N2-point FFT, multiply by the cached IR spectrum (already
-// permuted to the four-step order and scaled by 1/N), N2-point inverse FFT.
-// grid = (N1 / ROWS, pairs in this group); 256 threads; ROWS = 4096/L rows per CTA.
-// SPECTRUM mode: forward only, scaled, written to `spec` (IR spectrum construction).
-template <typename T, int L, bool SPECTRUM>
-__global__ void __launch_bounds__(256, 2)
-fftconv_rows(cpx<T> *__restrict__ scratch, const cpx<T> *__restrict__ H, cpx<T> *__restrict__ spec, T scale,
-             int N1, const cpx<T> *__restrict__ tw) {
+// Row tile, in place on scratch: ROWS rows; N2-point FFT, multiply by the cached IR spectrum
+// (four-step order, pre-scaled by 1/N, prefetched by cp.async), N2-point inverse FFT.
+template <typename T, int L>
+__device__ __forceinline__ void rows_tile(cpx<T> *__restrict__ scratch_pair, const cpx<T> *__restrict__ H, int rowtile,
+                                          cpx<T> *buf, const cpx<T> *stw) {
     using C = cpx<T>;
     using Sh = FftShape<L>;
     constexpr int TPF = Sh::TPF;
-    constexpr int ROWS = 256 / TPF;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    C *buf = reinterpret_cast<C *>(smem_raw);
-    C *stw = buf + ROWS * L;
-    load_tw_smem<T, L>(stw, tw, threadIdx.x, 256);
-
+    constexpr int ROWS = rows_cta_threads(L) / TPF;
     const int row = threadIdx.x / TPF;
     const int j = threadIdx.x % TPF;
-    const size_t k1 = (size_t)blockIdx.x * ROWS + row;
+    const size_t k1 = (size_t)rowtile * ROWS + row;
     RowAddr<T, Sh::R0> addr{row * L};
-    C *p = scratch + (size_t)blockIdx.y * ((size_t)N1 * L) + k1 * L + j;
     const size_t hoff = k1 * L + j;
+    C *p = scratch_pair + hoff;
 
     C e[16];
 #pragma unroll
-    for (int q = 0; q < 16; q++) e[q] = p[q * TPF];
+    for (int q = 0; q < 16; q++) e[q] = __ldcg(&p[q * TPF]);
     auto prefetch_h = [&](C *b) {
-        if (!SPECTRUM) {
 #pragma unroll
-            for (int q = 0; q < 16; q++) cp_async_elem(&b[addr.at(j + q * TPF, Sh::P - 1)], &H[hoff + q * TPF]);
-        }
+        for (int q = 0; q < 16; q++) cp_async_elem(&b[addr.at(j + q * TPF, Sh::P - 1)], &H[hoff + q * TPF]);
     };
     cta_fft<T, L, false>(e, buf, addr, stw, j, prefetch_h);
-    if (SPECTRUM) {
-#pragma unroll
-        for (int q = 0; q < 16; q++) {
-            C v; v.x = e[q].x * scale; v.y = e[q].y * scale;
-            spec[(size_t)blockIdx.y * ((size_t)N1 * L) + hoff + q * TPF] = v;
-        }
-        return;
-    }
     cp_async_wait_all();
 #pragma unroll
     for (int q = 0; q < 16; q++) e[q] = cmul(e[q], buf[addr.at(j + q * TPF, Sh::P - 1)]);
     cta_fft<T, L, true>(e, buf, addr, stw, j);
 #pragma unroll
-    for (int q = 0; q < 16; q++) p[q * TPF] = e[q];
+    for (int q = 0; q < 16; q++) __stcg(&p[q * TPF], e[q]);
 }
 
-// Inverse column pass: conj four-step twiddle, N1-point inverse, keep positions >= D, split
-// re/im to the two real output blocks.
+// Inverse column tile: conj four-step twiddle, N1-point inverse, keep positions >= D, split re/im to
+// the two real output blocks.
 template <typename T, int N1>
-__global__ void __launch_bounds__(ColShape<N1>::THREADS, ColShape<N1>::MIN_CTAS)
-fftconv_cols_inv(ConvGeom g, const cpx<T> *__restrict__ scratch, const T *__restrict__ x, T *__restrict__ y,
-                 int N2, int lgN, const cpx<T> *__restrict__ tw, const cpx<T> *__restrict__ tw_hi,
-                 const cpx<T> *__restrict__ tw_lo, long long pair0) {
+__device__ __forceinline__ void cols_inv_tile(const ConvGeom &g, const cpx<T> *__restrict__ scratch_pair, const T *x,
+                                              T *__restrict__ y, int N2, int lgN, const cpx<T> *stw,
+                                              const cpx<T> *__restrict__ tw_hi, const cpx<T> *__restrict__ tw_lo,
+                                              long long pair, int tile, cpx<T> *buf) {
     using C = cpx<T>;
     using CS = ColShape<N1>;
     constexpr int TPF = CS::TPF, TC = CS::TC;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    C *buf = reinterpret_cast<C *>(smem_raw);
-
-    C *stw = buf + ((FftShape<N1>::P > 0) ? CS::SMEM_ELEMS : 0);
-    load_tw_smem<T, N1>(stw, tw, threadIdx.x, CS::THREADS);
-
     const int c = threadIdx.x % TC;
     const int j = threadIdx.x / TC;
-    const int n2 = blockIdx.x * TC + c;
-    const long long pair = pair0 + blockIdx.y;
+    const int n2 = tile * TC + c;
     ColAddr<TC> addr{c};
 
     const unsigned maskN = (1u << lgN) - 1u;
     C gtw[16];
     geometric16(twiddle_n<T>(tw_hi, tw_lo, ((unsigned)n2 * (unsigned)j) & maskN),
                 twiddle_n<T>(tw_hi, tw_lo, ((unsigned)n2 * (unsigned)TPF) & maskN), gtw);
-    const C *src = scratch + (size_t)blockIdx.y * ((size_t)N1 * N2) + n2;
+    const C *src = scratch_pair + n2;
     C e[16];
 #pragma unroll
-    for (int q = 0; q < 16; q++) e[q] = cmul_tw<true>(src[(size_t)(j + q * TPF) * N2], gtw[q]);
+    for (int q = 0; q < 16; q++) e[q] = cmul_tw<true>(__ldcg(&src[(size_t)(j + q * TPF) * N2]), gtw[q]);
     cta_fft<T, N1, true>(e, buf, addr, stw, j);
 
     const BlockIO<T> a = block_io<T>(g, x, y, 2 * pair);
@@ -307,5 +290,212 @@ fftconv_cols_inv(ConvGeom g, const cpx<T> *__restrict__ scratch, const T *__rest
         }
     }
 }
+
+// ------------------------------------------------------------------------------------------
+// Stand-alone kernels (three launches per group of pairs).  grid = (tiles, pairs in this group).
+template <typename T, int N1>
+__global__ void __launch_bounds__(ColShape<N1>::THREADS, ColShape<N1>::MIN_CTAS)
+fftconv_cols_fwd(ConvGeom g, const T *__restrict__ x, cpx<T> *__restrict__ scratch, int N2, int lgN,
+                 const cpx<T> *__restrict__ tw, const cpx<T> *__restrict__ tw_hi,
+                 const cpx<T> *__restrict__ tw_lo, long long pair0) {
+    using C = cpx<T>;
+    using CS = ColShape<N1>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C *buf = reinterpret_cast<C *>(smem_raw);
+    C *stw = buf + ((FftShape<N1>::P > 0) ? CS::SMEM_ELEMS : 0);
+    load_tw_smem<T, N1>(stw, tw, threadIdx.x, CS::THREADS);
+    cols_fwd_tile<T, N1>(g, x, scratch + (size_t)blockIdx.y * ((size_t)N1 * N2), N2, lgN, stw, tw_hi, tw_lo,
+                         pair0 + blockIdx.y, blockIdx.x, buf);
+}
+
+// SPECTRUM mode: forward only, scaled, written to `spec` (IR spectrum construction, once per plan).
+template <typename T, int L, bool SPECTRUM>
+__global__ void __launch_bounds__(rows_cta_threads(L), rows_min_ctas(L))
+fftconv_rows(cpx<T> *__restrict__ scratch, const cpx<T> *__restrict__ H, cpx<T> *__restrict__ spec, T scale,
+             int N1, const cpx<T> *__restrict__ tw) {
+    using C = cpx<T>;
+    using Sh = FftShape<L>;
+    constexpr int TPF = Sh::TPF;
+    constexpr int ROWS = rows_cta_threads(L) / TPF;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C *buf = reinterpret_cast<C *>(smem_raw);
+    C *stw = buf + ROWS * L;
+    load_tw_smem<T, L>(stw, tw, threadIdx.x, rows_cta_threads(L));
+    C *pairbase = scratch + (size_t)blockIdx.y * ((size_t)N1 * L);
+    if (!SPECTRUM) {
+        rows_tile<T, L>(pairbase, H, blockIdx.x, buf, stw);
+        return;
+    }
+    const int row = threadIdx.x / TPF;
+    const int j = threadIdx.x % TPF;
+    const size_t k1 = (size_t)blockIdx.x * ROWS + row;
+    RowAddr<T, Sh::R0> addr{row * L};
+    const size_t hoff = k1 * L + j;
+    C e[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++) e[q] = pairbase[hoff + q * TPF];
+    cta_fft<T, L, false>(e, buf, addr, stw, j);
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        C v; v.x = e[q].x * scale; v.y = e[q].y * scale;
+        spec[(size_t)blockIdx.y * ((size_t)N1 * L) + hoff + q * TPF] = v;
+    }
+}
+
+template <typename T, int N1>
+__global__ void __launch_bounds__(ColShape<N1>::THREADS, ColShape<N1>::MIN_CTAS)
+fftconv_cols_inv(ConvGeom g, const cpx<T> *__restrict__ scratch, const T *__restrict__ x, T *__restrict__ y,
+                 int N2, int lgN, const cpx<T> *__restrict__ tw, const cpx<T> *__restrict__ tw_hi,
+                 const cpx<T> *__restrict__ tw_lo, long long pair0) {
+    using C = cpx<T>;
+    using CS = ColShape<N1>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C *buf = reinterpret_cast<C *>(smem_raw);
+    C *stw = buf + ((FftShape<N1>::P > 0) ? CS::SMEM_ELEMS : 0);
+    load_tw_smem<T, N1>(stw, tw, threadIdx.x, CS::THREADS);
+    cols_inv_tile<T, N1>(g, scratch + (size_t)blockIdx.y * ((size_t)N1 * N2), x, y, N2, lgN, stw, tw_hi, tw_lo,
+                         pair0 + blockIdx.y, blockIdx.x, buf);
+}
+
+// ------------------------------------------------------------------------------------------
+// Persistent fused kernel: ONE launch runs all three phases of every block pair as a dataflow over
+// tiles.  CTAs (2 per SM) draw tickets from a global counter; ticket t maps to a task through a
+// host-built periodic order table in which, per "round", the forward-column tiles of pair m, the row
+// tiles of pairs m-2/m-1 (offset 1.5 rounds) and the inverse-column tiles of pair m-3 are interleaved,
+// so memory-latency-bound column tiles and FP64-bound row tiles share every SM, every dependency has
+// >= half a round of slack (more than the in-flight ticket window), and intermediates live in
+// `nslots` scratch slots that stay L2 resident.  A task only ever waits on smaller tickets, so the
+// scheme cannot deadlock whatever the residency.
+struct FusedParams {
+    ConvGeom g;
+    long long npairs;
+    int N2, lgN, nslots;
+    int tiles_c, tiles_r, round_len;   // column tiles, row tiles and tasks per round
+    int flags;                         // bit0: dry run (scheduling only), bit1: static ticket assignment
+    long long total_tickets;
+};
+
+enum { TASK_CF = 0, TASK_R = 1, TASK_CI = 2 };
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// stats (optional, may be null): [type] = spin iterations, [4 + type] = tasks that had to wait
+__device__ __forceinline__ void wait_count(const unsigned *p, unsigned need, unsigned *stats, int type) {
+    if (threadIdx.x == 0) {
+        unsigned spins = 0;
+        while (ld_acquire_u32(p) < need) { __nanosleep(64); spins++; }
+        if (spins && stats) { atomicAdd(&stats[type], spins); atomicAdd(&stats[4 + type], 1u); }
+    }
+    __syncthreads();
+}
+
+#if (ADSP_COLS_CTA_THREADS == 256 && !ADSP_ROWS_SMALL_CTA)
+// order[s] = type | idx << 2 | pair_delta << 20
+template <typename T, int N1, int L>
+__global__ void __launch_bounds__(256, 2)
+fftconv_fused(FusedParams prm, const T *__restrict__ x, T *__restrict__ y, cpx<T> *__restrict__ scratch,
+              const cpx<T> *__restrict__ H, const cpx<T> *__restrict__ tw_rows, const cpx<T> *__restrict__ tw_cols,
+              const cpx<T> *__restrict__ tw_hi, const cpx<T> *__restrict__ tw_lo, const unsigned *__restrict__ order,
+              unsigned *counters /* [0] ticket, then done_cf[npairs], done_r[npairs], done_ci[npairs] */) {
+    using C = cpx<T>;
+    using CS = ColShape<N1>;
+    static_assert(CS::THREADS == 256 && rows_cta_threads(L) == 256, "fused kernel needs 256-thread tiles");
+    constexpr int ROWS = 256 / FftShape<L>::TPF;
+    constexpr int BUF_ELEMS = (ROWS * L > CS::SMEM_ELEMS) ? ROWS * L : CS::SMEM_ELEMS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C *buf = reinterpret_cast<C *>(smem_raw);
+    C *stw_r = buf + BUF_ELEMS;
+    C *stw_c = stw_r + FftShape<L>::TW_ENTRIES;
+    __shared__ long long s_ticket;
+    load_tw_smem<T, L>(stw_r, tw_rows, threadIdx.x, 256);
+    load_tw_smem<T, N1>(stw_c, tw_cols, threadIdx.x, 256);
+
+    unsigned *done_cf = counters + 1;
+    unsigned *done_r = done_cf + prm.npairs;
+    unsigned *done_ci = done_r + prm.npairs;
+    unsigned *stats = done_ci + prm.npairs;   // 8 words
+    const size_t pair_elems = (size_t)N1 * L;
+
+    const bool dry = (prm.flags & 1) != 0;          // scheduling only (overhead measurement)
+    const bool static_tickets = (prm.flags & 2) != 0;
+    long long t = static_tickets ? (long long)blockIdx.x : -1;
+    unsigned dep_prefetched = 0;   // thread 0: value of the next task's dependency counter, loaded a task ahead
+    bool have_prefetch = false;
+    for (;;) {
+        __syncthreads();  // previous task finished everywhere (smem + s_ticket reusable)
+        if (!static_tickets) {
+            if (threadIdx.x == 0) s_ticket = (long long)atomicAdd(&counters[0], 1u);
+            __syncthreads();
+            t = s_ticket;
+        }
+        if (t >= prm.total_tickets) break;
+        const long long round = t / prm.round_len;
+        const unsigned ent = __ldg(&order[(int)(t - round * prm.round_len)]);
+        const int type = ent & 3u;
+        const int idx = (ent >> 2) & 0x3ffffu;
+        const long long pair = round - (long long)(ent >> 20);
+        // static mode: look one task ahead and start loading its dependency counter now
+        const unsigned *dep_next = nullptr;
+        unsigned need_next = 0;
+        if (static_tickets) {
+            const long long tn = t + gridDim.x;
+            if (tn < prm.total_tickets) {
+                const long long rn = tn / prm.round_len;
+                const unsigned en = __ldg(&order[(int)(tn - rn * prm.round_len)]);
+                const int ty = en & 3u;
+                const long long pn = rn - (long long)(en >> 20);
+                if (pn >= 0 && pn < prm.npairs) {
+                    if (ty == TASK_CF) { if (pn >= prm.nslots) { dep_next = &done_ci[pn - prm.nslots]; need_next = prm.tiles_c; } }
+                    else if (ty == TASK_R) { dep_next = &done_cf[pn]; need_next = prm.tiles_c; }
+                    else { dep_next = &done_r[pn]; need_next = prm.tiles_r; }
+                }
+            }
+        }
+        const bool valid = pair >= 0 && pair < prm.npairs;
+        if (valid) {
+            C *slot = scratch + (size_t)(pair % prm.nslots) * pair_elems;
+            const unsigned *dep = nullptr;
+            unsigned need = 0;
+            if (type == TASK_CF) { if (pair >= prm.nslots) { dep = &done_ci[pair - prm.nslots]; need = prm.tiles_c; } }
+            else if (type == TASK_R) { dep = &done_cf[pair]; need = prm.tiles_c; }
+            else { dep = &done_r[pair]; need = prm.tiles_r; }
+            if (dep) {
+                if (static_tickets && have_prefetch) {
+                    // thread 0 already holds a (possibly stale) value; only poll if it was not yet complete
+                    if (threadIdx.x == 0 && dep_prefetched < need) {
+                        unsigned spins = 0;
+                        while (ld_acquire_u32(dep) < need) { __nanosleep(64); spins++; }
+                        atomicAdd(&stats[type], spins + 1); atomicAdd(&stats[4 + type], 1u);
+                    }
+                    __syncthreads();
+                } else {
+                    wait_count(dep, need, stats, type);
+                }
+            }
+            unsigned pf = 0;
+            if (dep_next && threadIdx.x == 0) pf = ld_acquire_u32(dep_next);   // consumed after the task body
+            if (!dry) {
+                if (type == TASK_CF) cols_fwd_tile<T, N1>(prm.g, x, slot, prm.N2, prm.lgN, stw_c, tw_hi, tw_lo, pair, idx, buf);
+                else if (type == TASK_R) rows_tile<T, L>(slot, H, idx, buf, stw_r);
+                else cols_inv_tile<T, N1>(prm.g, slot, x, y, prm.N2, prm.lgN, stw_c, tw_hi, tw_lo, pair, idx, buf);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                atomicAdd(type == TASK_CF ? &done_cf[pair] : (type == TASK_R ? &done_r[pair] : &done_ci[pair]), 1u);
+                dep_prefetched = pf;
+            }
+            have_prefetch = (dep_next != nullptr);
+        } else {
+            have_prefetch = false;
+        }
+        if (static_tickets) t += gridDim.x;
+    }
+}
+
+#endif
 
 }  // namespace adsp

@@ -77,7 +77,7 @@ struct adsp_ctx {
     std::map<std::pair<int, int>, void *> tw_tables;                     // (L, prec) -> device table
     std::map<std::pair<int, int>, std::pair<void *, void *>> tw4_tables;  // (lgN, prec) -> (hi, lo)
     adsp::DevBuf scratch;              // four-step intermediates (L2 resident by construction)
-    adsp::DevBuf d_in, d_out, d_k, d_tmp, d_small;
+    adsp::DevBuf d_in, d_out, d_k, d_tmp, d_small, d_counters;
     adsp::PinnedBuf h_in[2], h_out[2], h_small;
     std::atomic<uint64_t> launches{0};
     size_t scratch_budget = 0;  // bytes of scratch allowed in flight (fits L2)
@@ -96,8 +96,15 @@ struct adsp_ctx {
 
 namespace adsp {
 
+// per-engine cache of the fused kernel's task-order table
+struct FusedCache {
+    unsigned *d_order = nullptr;
+    int round_len = 0, tiles_c = 0, tiles_r = 0, nslots = 0, extra_rounds = 0, resident = 0;
+};
+
 // Device-resident FFT convolver for one (partition of an) impulse response.
 template <typename T> struct FftConv {
+    FusedCache fused;
     adsp_ctx *ctx = nullptr;
     long long K = 0;  // taps of this partition
     FftChoice ch;
@@ -127,7 +134,7 @@ adsp_status direct_device(adsp_ctx *ctx, const T *d_a, long long n, long long a_
 
 inline void count_launch(adsp_ctx *ctx, int n = 1) { ctx->launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
-enum KernelKind { KK_COLS_FWD = 0, KK_ROWS = 1, KK_COLS_INV = 2, KK_FULL = 3, KK_DIRECT = 4, KK_OTHER = 5 };
+enum KernelKind { KK_COLS_FWD = 0, KK_ROWS = 1, KK_COLS_INV = 2, KK_FULL = 3, KK_DIRECT = 4, KK_OTHER = 5, KK_FUSED = 6 };
 
 // RAII bracket: when ctx->timing is on, records an event pair around one launch
 struct LaunchTimer {

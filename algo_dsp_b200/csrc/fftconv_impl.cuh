@@ -2,6 +2,7 @@
 // Included by fftconv_f64.cu / fftconv_f32.cu with ADSP_REAL defined (one TU per precision so
 // the template-heavy kernels compile in parallel).
 #pragma once
+#include <algorithm>
 #include <cmath>
 
 #include "engine.cuh"
@@ -121,13 +122,14 @@ struct AttrOnce {
 template <typename T, int L, bool SPEC>
 static adsp_status launch_full_t(adsp_ctx *ctx, cudaStream_t st, const ConvGeom &g, const T *x, T *y, const cpx<T> *H,
                                  cpx<T> *spec, T scale, const cpx<T> *tw, long long npairs) {
-    constexpr int ROWS = 256 / FftShape<L>::TPF;
+    constexpr int THREADS = rows_cta_threads(L);
+    constexpr int ROWS = THREADS / FftShape<L>::TPF;
     const size_t smem = ((size_t)ROWS * L + FftShape<L>::TW_ENTRIES) * sizeof(cpx<T>);
     static AttrOnce once;
     if (once.need(ctx->device)) ADSP_TRY(set_smem(fftconv_full<T, L, SPEC>, smem));
     const long long grid = (npairs + ROWS - 1) / ROWS;
     LaunchTimer lt(ctx, st, KK_FULL);
-    fftconv_full<T, L, SPEC><<<(unsigned)grid, 256, smem, st>>>(g, x, y, H, spec, scale, tw, npairs);
+    fftconv_full<T, L, SPEC><<<(unsigned)grid, THREADS, smem, st>>>(g, x, y, H, spec, scale, tw, npairs);
     count_launch(ctx);
     ADSP_CUDA(cudaGetLastError());
     return ADSP_OK;
@@ -149,13 +151,14 @@ static adsp_status launch_full(adsp_ctx *ctx, cudaStream_t st, int L, const Conv
 template <typename T, int L, bool SPEC>
 static adsp_status launch_rows_t(adsp_ctx *ctx, cudaStream_t st, cpx<T> *scratch, const cpx<T> *H, cpx<T> *spec,
                                  T scale, int N1, const cpx<T> *tw, int pairs) {
-    constexpr int ROWS = 256 / FftShape<L>::TPF;
+    constexpr int THREADS = rows_cta_threads(L);
+    constexpr int ROWS = THREADS / FftShape<L>::TPF;
     const size_t smem = ((size_t)ROWS * L + FftShape<L>::TW_ENTRIES) * sizeof(cpx<T>);
     static AttrOnce once;
     if (once.need(ctx->device)) ADSP_TRY(set_smem(fftconv_rows<T, L, SPEC>, smem));
     dim3 grid((unsigned)(N1 / ROWS > 0 ? N1 / ROWS : 1), (unsigned)pairs);
     LaunchTimer lt(ctx, st, KK_ROWS);
-    fftconv_rows<T, L, SPEC><<<grid, 256, smem, st>>>(scratch, H, spec, scale, N1, tw);
+    fftconv_rows<T, L, SPEC><<<grid, THREADS, smem, st>>>(scratch, H, spec, scale, N1, tw);
     count_launch(ctx);
     ADSP_CUDA(cudaGetLastError());
     return ADSP_OK;
@@ -212,6 +215,117 @@ static adsp_status launch_cols(adsp_ctx *ctx, cudaStream_t st, int N1, bool inve
     }
 }
 
+// ------------------------------------------------------------------ persistent fused kernel
+#define ADSP_FUSED_AVAILABLE (ADSP_COLS_CTA_THREADS == 256 && !ADSP_ROWS_SMALL_CTA)
+struct FusedPlan {
+    std::vector<unsigned> order;
+    int round_len = 0, tiles_c = 0, tiles_r = 0, nslots = 0, extra_rounds = 0;
+};
+
+// Periodic task order: forward-column tiles at offset 0, row tiles at offset `lag` rounds, inverse
+// column tiles at 2*lag; `lag` exceeds the in-flight ticket window so no task ever finds its
+// producers unfinished in steady state.
+static FusedPlan make_fused_plan(int tiles_c, int tiles_r, int resident_ctas) {
+    FusedPlan fp;
+    fp.tiles_c = tiles_c; fp.tiles_r = tiles_r;
+    fp.round_len = 2 * tiles_c + tiles_r;
+    const double window = (double)resident_ctas / fp.round_len;
+    // producers of a pair span one full round, so consumers must trail by a round plus the window
+    double lag = 1.0 + window * 1.3;
+    lag = std::ceil(lag * 2.0) / 2.0;            // multiples of half a round
+    const double forced = (double)env_ll("ADSP_FUSED_LAG_X2", 0) / 2.0;
+    if (forced > 0) lag = forced;
+    fp.nslots = (int)std::ceil(3.0 * lag + 1.0);
+    fp.extra_rounds = (int)std::ceil(2.0 * lag) + 1;
+    struct Ent { double key; unsigned val; };
+    std::vector<Ent> ents;
+    auto add = [&](int type, int count, double off) {
+        for (int i = 0; i < count; i++) {
+            const double u = (i + 0.5) / count + off;
+            const double fl = std::floor(u);
+            ents.push_back({u - fl + 1e-9 * type, (unsigned)type | ((unsigned)i << 2) | ((unsigned)fl << 20)});
+        }
+    };
+    add(TASK_CF, tiles_c, 0.0);
+    add(TASK_R, tiles_r, lag);
+    add(TASK_CI, tiles_c, 2.0 * lag);
+    std::stable_sort(ents.begin(), ents.end(), [](const Ent &a, const Ent &b) { return a.key < b.key; });
+    for (auto &e : ents) fp.order.push_back(e.val);
+    return fp;
+}
+
+#if ADSP_FUSED_AVAILABLE
+template <typename T, int N1, int L>
+static adsp_status launch_fused_t(adsp_ctx *ctx, const ConvGeom &g, long long npairs, int lgN, const T *x, T *y,
+                                  const cpx<T> *H, const cpx<T> *tw_rows, const cpx<T> *tw_cols, const cpx<T> *tw_hi,
+                                  const cpx<T> *tw_lo, FusedCache &fc) {
+    using CS = ColShape<N1>;
+    constexpr int ROWS = 256 / FftShape<L>::TPF;
+    constexpr int BUF_ELEMS = (ROWS * L > CS::SMEM_ELEMS) ? ROWS * L : CS::SMEM_ELEMS;
+    const size_t smem = ((size_t)BUF_ELEMS + FftShape<L>::TW_ENTRIES + FftShape<N1>::TW_ENTRIES) * sizeof(cpx<T>);
+    static AttrOnce once;
+    if (once.need(ctx->device)) ADSP_TRY(set_smem(fftconv_fused<T, N1, L>, smem));
+    int per_sm = 0;
+    ADSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fftconv_fused<T, N1, L>, 256, smem));
+    if (per_sm < 1) { set_error("fused kernel does not fit on an SM"); return ADSP_ERR_CUDA; }
+    const int resident = per_sm * ctx->sm_count;
+    if (fc.d_order == nullptr || fc.resident != resident) {
+        FusedPlan fp = make_fused_plan(L / CS::TC, N1 / ROWS, resident);
+        if (fc.d_order) cudaFree(fc.d_order);
+        ADSP_CUDA(cudaMalloc((void **)&fc.d_order, fp.order.size() * sizeof(unsigned)));
+        ADSP_CUDA(cudaMemcpyAsync(fc.d_order, fp.order.data(), fp.order.size() * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->main));
+        ADSP_CUDA(cudaStreamSynchronize(ctx->main));
+        fc.round_len = fp.round_len; fc.tiles_c = fp.tiles_c; fc.tiles_r = fp.tiles_r; fc.nslots = fp.nslots;
+        fc.extra_rounds = fp.extra_rounds; fc.resident = resident;
+    }
+    const size_t pair_bytes = (size_t)N1 * L * sizeof(cpx<T>);
+    const int nslots = (int)std::min<long long>(fc.nslots, npairs);
+    ADSP_TRY(ctx->scratch.reserve((size_t)nslots * pair_bytes));
+    const size_t ncount = 1 + 3 * (size_t)npairs + 8;
+    ADSP_TRY(ctx->d_counters.reserve(ncount * sizeof(unsigned)));
+    ADSP_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, ncount * sizeof(unsigned), ctx->main));
+    FusedParams prm;
+    prm.g = g; prm.npairs = npairs; prm.N2 = L; prm.lgN = lgN; prm.nslots = nslots;
+    prm.tiles_c = fc.tiles_c; prm.tiles_r = fc.tiles_r; prm.round_len = fc.round_len;
+    prm.total_tickets = (npairs + fc.extra_rounds) * (long long)fc.round_len;
+    prm.flags = (int)env_ll("ADSP_FUSED_FLAGS", 0);
+    const long long grid = std::min<long long>(resident, prm.total_tickets);
+    {
+        LaunchTimer lt(ctx, ctx->main, KK_FUSED);
+        fftconv_fused<T, N1, L><<<(unsigned)grid, 256, smem, ctx->main>>>(prm, x, y, (cpx<T> *)ctx->scratch.p, H, tw_rows, tw_cols,
+                                                                       tw_hi, tw_lo, fc.d_order, (unsigned *)ctx->d_counters.p);
+    }
+    count_launch(ctx);
+    ADSP_CUDA(cudaGetLastError());
+    if (env_ll("ADSP_FUSED_STATS", 0)) {
+        unsigned st[8];
+        ADSP_CUDA(cudaMemcpyAsync(st, (unsigned *)ctx->d_counters.p + 1 + 3 * npairs, sizeof st, cudaMemcpyDeviceToHost, ctx->main));
+        ADSP_CUDA(cudaStreamSynchronize(ctx->main));
+        fprintf(stderr, "[fused N1=%d N2=%d pairs=%lld round=%d slots=%d extra=%d grid=%lld] spins cf/r/ci = %u/%u/%u  waited tasks = %u/%u/%u\n",
+                N1, L, npairs, fc.round_len, nslots, fc.extra_rounds, grid, st[0], st[1], st[2], st[4], st[5], st[6]);
+    }
+    return ADSP_OK;
+}
+
+#endif
+
+// returns ADSP_OK and sets *done when the (N1, N2) combination has a fused instantiation
+template <typename T>
+static adsp_status launch_fused(adsp_ctx *ctx, int N1, int N2, const ConvGeom &g, long long npairs, int lgN, const T *x, T *y,
+                                const cpx<T> *H, const cpx<T> *tw_rows, const cpx<T> *tw_cols, const cpx<T> *tw_hi,
+                                const cpx<T> *tw_lo, FusedCache &fc, bool *done) {
+    *done = true;
+#if ADSP_FUSED_AVAILABLE
+#define ADSP_FUSED_CASE(n1, n2) \
+    if (N1 == n1 && N2 == n2) return launch_fused_t<T, n1, n2>(ctx, g, npairs, lgN, x, y, H, tw_rows, tw_cols, tw_hi, tw_lo, fc);
+    ADSP_FUSED_CASE(16, 512) ADSP_FUSED_CASE(16, 1024) ADSP_FUSED_CASE(16, 2048) ADSP_FUSED_CASE(16, 4096)
+    ADSP_FUSED_CASE(32, 4096) ADSP_FUSED_CASE(64, 4096) ADSP_FUSED_CASE(128, 4096) ADSP_FUSED_CASE(256, 4096)
+#undef ADSP_FUSED_CASE
+#endif
+    *done = false;
+    return ADSP_OK;
+}
+
 // ------------------------------------------------------------------ FftConv
 template <typename T>
 adsp_status FftConv<T>::init(adsp_ctx *c, const T *d_kernel, long long K_, const FftChoice &choice) {
@@ -245,6 +359,8 @@ adsp_status FftConv<T>::init(adsp_ctx *c, const T *d_kernel, long long K_, const
 template <typename T> void FftConv<T>::destroy() {
     if (H) cudaFree(H);
     H = nullptr;
+    if (fused.d_order) cudaFree(fused.d_order);
+    fused.d_order = nullptr;
 }
 
 template <typename T>
@@ -263,7 +379,14 @@ adsp_status FftConv<T>::run(const T *d_x, long long n, long long channels, long 
     if (ch.N1 == 1)
         return launch_full<T, false>(ctx, ctx->main, ch.N2, g, d_x, d_y, H, (cpx<T> *)nullptr, (T)0, tw_rows, npairs);
 
-    // four-step: groups of pairs sized so that the intermediates of all in-flight groups stay in L2
+    // four-step, persistent fused kernel (one launch for the whole batch) when the batch is large enough
+    // (opt-in, ADSP_FUSED=1: measured slower than the three-kernel path)
+    if (ADSP_FUSED_AVAILABLE && npairs >= env_ll("ADSP_FUSED_MIN_PAIRS", 12) && env_ll("ADSP_FUSED", 0) != 0 && env_ll("ADSP_NO_FUSED", 0) == 0) {
+        bool done = false;
+        ADSP_TRY(launch_fused<T>(ctx, ch.N1, ch.N2, g, npairs, ch.lgN, d_x, d_y, H, tw_rows, tw_cols, tw_hi, tw_lo, fused, &done));
+        if (done) return ADSP_OK;
+    }
+    // four-step, three kernels per group of pairs sized so that the intermediates of all in-flight groups stay in L2
     const size_t per_pair = (size_t)ch.N * sizeof(cpx<T>);
     size_t budget = ctx->scratch_budget;
     const long long mb = env_ll("ADSP_SCRATCH_MB", 0);  // tuning override

@@ -67,7 +67,7 @@ ADSP_API adsp_status adsp_ctx_sync(adsp_ctx *ctx);
 ADSP_API uint64_t adsp_ctx_launch_count(adsp_ctx *ctx);
 /* Per-kernel device timing for the bench roofline: when enabled, every launch is bracketed by a
  * CUDA event pair on its own stream.  kind: 0 cols_fwd, 1 rows, 2 cols_inv, 3 single-kernel FFT
- * conv, 4 direct, 5 other.  adsp_ctx_kernel_time synchronises, returns the accumulated device
+ * conv, 4 direct, 5 other, 6 persistent fused four-step kernel.  adsp_ctx_kernel_time synchronises, returns the accumulated device
  * time and launch count of `kind`, and clears the accumulators when reset != 0. */
 ADSP_API void adsp_ctx_kernel_timing(adsp_ctx *ctx, int enable);
 ADSP_API adsp_status adsp_ctx_kernel_time(adsp_ctx *ctx, int kind, double *total_ms, uint64_t *launches, int reset);
