@@ -68,7 +68,9 @@ FftChoice make_choice(long long Kp, long long N) {
     c.lgN = lg;
     if (N <= 4096) { c.N1 = 1; c.N2 = (int)N; }
     else {
-        long long n2 = env_ll("ADSP_FFT_N2", 4096);
+        // rows of 2048 points run as 128-thread CTAs (4 per SM); 2^20-point transforms keep 4096-point
+        // rows so that the column transforms stay at N1 = 256
+        long long n2 = env_ll("ADSP_FFT_N2", N >= (1LL << 20) ? 4096 : 2048);
         if (n2 > N / 16) n2 = N / 16;
         if (n2 < 256) n2 = 256;
         while (N / n2 > 1024) n2 *= 2;
@@ -140,11 +142,11 @@ template <typename T>
 adsp_status direct_device(adsp_ctx *ctx, const T *d_a, long long n, long long a_stride, const T *d_b, long long m,
                           long long b_stride, long long batch, T *d_out, long long out_stride) {
     const long long out_len = n + m - 1;
+    static const bool exact = env_ll("ADSP_DIRECT_EXACT", 0) != 0;
     const long long tiles = (out_len + DIRECT_TILE - 1) / DIRECT_TILE;
     const long long grid = tiles * batch;
     if (grid <= 0) return ADSP_OK;
     if (grid > 0x7fffffffLL) { set_error("direct: grid too large"); return ADSP_ERR_INVALID_ARG; }
-    static const bool exact = env_ll("ADSP_DIRECT_EXACT", 0) != 0;
     LaunchTimer lt(ctx, ctx->main, KK_DIRECT);
     if (exact)
         direct_conv_kernel<T, false><<<(unsigned)grid, DIRECT_THREADS, 0, ctx->main>>>(d_a, n, a_stride, d_b, m, b_stride, d_out, out_stride, tiles);

@@ -61,12 +61,18 @@ template <typename T> __device__ __forceinline__ T ld_stream(const T *p) { retur
 
 // CTA shapes (compile-time knobs; tools/ builds variants with -D to A/B them on the GPU).
 // A row CTA owns 16 points per thread: L/16 threads per row, rows_cta_threads(L)/(L/16) rows per CTA.
+// ADSP_EXPERIMENTAL=1 additionally compiles the ping-pong and persistent fused kernels (both measured
+// slower than the default path on B200); they need 256-thread tiles.
+#ifndef ADSP_EXPERIMENTAL
+#define ADSP_EXPERIMENTAL 0
+#endif
 #ifndef ADSP_ROWS_SMALL_CTA
-#define ADSP_ROWS_SMALL_CTA 0
+#define ADSP_ROWS_SMALL_CTA (ADSP_EXPERIMENTAL ? 0 : 1)
 #endif
 #ifndef ADSP_COLS_CTA_THREADS
-#define ADSP_COLS_CTA_THREADS 256
+#define ADSP_COLS_CTA_THREADS (ADSP_EXPERIMENTAL ? 256 : 128)
 #endif
+#define ADSP_WIDE_TILES (ADSP_EXPERIMENTAL && ADSP_COLS_CTA_THREADS == 256 && !ADSP_ROWS_SMALL_CTA)
 constexpr int rows_cta_threads(int L) { return (ADSP_ROWS_SMALL_CTA && L <= 2048) ? 128 : 256; }
 constexpr int rows_min_ctas(int L) { return 512 / rows_cta_threads(L); }
 
@@ -111,7 +117,8 @@ fftconv_full(ConvGeom g, const T *__restrict__ x, T *__restrict__ y,
             for (int q = 0; q < 16; q++) cp_async_elem(&b[addr.at(j + q * TPF, Sh::P - 1)], &H[j + q * TPF]);
         }
     };
-    cta_fft<T, L, false>(e, buf, addr, stw, j, prefetch_h);
+    CtaGate gate;
+    cta_fft<T, L, false>(e, buf, addr, stw, j, gate, prefetch_h);
     if (SPECTRUM) {
         if (pair < npairs) {
 #pragma unroll
@@ -125,7 +132,7 @@ fftconv_full(ConvGeom g, const T *__restrict__ x, T *__restrict__ y,
     cp_async_wait_all();
 #pragma unroll
     for (int q = 0; q < 16; q++) e[q] = cmul(e[q], buf[addr.at(j + q * TPF, Sh::P - 1)]);
-    cta_fft<T, L, true>(e, buf, addr, stw, j);
+    cta_fft<T, L, true>(e, buf, addr, stw, j, gate);
 #pragma unroll
     for (int q = 0; q < 16; q++) {
         const long long o = (long long)(j + q * TPF) - g.D;
@@ -174,21 +181,24 @@ template <int N1> struct ColShape {
 };
 
 // ------------------------------------------------------------------------------------------
-// Tile bodies (device functions) shared by the stand-alone kernels and the persistent fused kernel.
-// Scratch is read with ld.global.cg (L2 only): in the fused kernel another CTA produced it, and L1
-// could hold stale lines from an earlier use of the same scratch slot.
+// Tile bodies (device functions) shared by the stand-alone kernels, the ping-pong kernels and the
+// persistent fused kernel.  `tid` is the thread's index inside its 256-thread tile group, `gate` the
+// barrier/phase policy (fft_core.cuh), `active` false for padding tiles (they run the same barrier
+// sequence on zeros and store nothing).  Scratch is read with ld.global.cg (L2 only): another CTA
+// produced it and L1 could hold stale lines from an earlier use of the same scratch slot.
 
 // Forward column tile: N1-point transforms down TC columns of the N1 x N2 view of block pair `pair`,
 // times the four-step twiddle W_N^(k1*n2), written to scratch (row-major N1 x N2).
-template <typename T, int N1>
+template <typename T, int N1, typename Gate>
 __device__ __forceinline__ void cols_fwd_tile(const ConvGeom &g, const T *__restrict__ x, cpx<T> *__restrict__ scratch_pair,
                                               int N2, int lgN, const cpx<T> *stw, const cpx<T> *__restrict__ tw_hi,
-                                              const cpx<T> *__restrict__ tw_lo, long long pair, int tile, cpx<T> *buf) {
+                                              const cpx<T> *__restrict__ tw_lo, long long pair, int tile, cpx<T> *buf,
+                                              int tid, Gate &gate, bool active) {
     using C = cpx<T>;
     using CS = ColShape<N1>;
     constexpr int TPF = CS::TPF, TC = CS::TC;
-    const int c = threadIdx.x % TC;
-    const int j = threadIdx.x / TC;
+    const int c = tid % TC;
+    const int j = tid / TC;
     const int n2 = tile * TC + c;
     ColAddr<TC> addr{c};
 
@@ -197,8 +207,8 @@ __device__ __forceinline__ void cols_fwd_tile(const ConvGeom &g, const T *__rest
     const C tw_base = twiddle_n<T>(tw_hi, tw_lo, ((unsigned)n2 * (unsigned)j) & maskN);
     const C tw_rho = twiddle_n<T>(tw_hi, tw_lo, ((unsigned)n2 * (unsigned)TPF) & maskN);
 
-    const BlockIO<T> a = block_io<T>(g, x, (T *)nullptr, 2 * pair);
-    const BlockIO<T> b = block_io<T>(g, x, (T *)nullptr, 2 * pair + 1);
+    const BlockIO<T> a = block_io<T>(g, x, (T *)nullptr, active ? 2 * pair : g.total_blocks);
+    const BlockIO<T> b = block_io<T>(g, x, (T *)nullptr, active ? 2 * pair + 1 : g.total_blocks);
 
     C e[16];
 #pragma unroll
@@ -207,75 +217,102 @@ __device__ __forceinline__ void cols_fwd_tile(const ConvGeom &g, const T *__rest
         e[q].x = (i >= a.lo && i < a.hi) ? ld_stream(a.in + i) : (T)0;
         e[q].y = (i >= b.lo && i < b.hi) ? ld_stream(b.in + i) : (T)0;
     }
-    cta_fft<T, N1, false>(e, buf, addr, stw, j);
+    cta_fft<T, N1, false, false, true>(e, buf, addr, stw, j, gate);   // leaves the last D phase open
 
     // k1 = j + r*TPF  ->  W_N^(n2*j) * (W_N^(n2*TPF))^r
     C gtw[16];
     geometric16(tw_base, tw_rho, gtw);
-    C *dst = scratch_pair + n2;
 #pragma unroll
-    for (int r = 0; r < 16; r++) __stcg(&dst[(size_t)(j + r * TPF) * N2], cmul(e[r], gtw[r]));
+    for (int r = 0; r < 16; r++) e[r] = cmul(e[r], gtw[r]);
+    gate.d_end();
+    if (active) {
+        C *dst = scratch_pair + n2;
+#pragma unroll
+        for (int r = 0; r < 16; r++) __stcg(&dst[(size_t)(j + r * TPF) * N2], e[r]);
+    }
 }
 
 // Row tile, in place on scratch: ROWS rows; N2-point FFT, multiply by the cached IR spectrum
 // (four-step order, pre-scaled by 1/N, prefetched by cp.async), N2-point inverse FFT.
-template <typename T, int L>
+template <typename T, int L, typename Gate>
 __device__ __forceinline__ void rows_tile(cpx<T> *__restrict__ scratch_pair, const cpx<T> *__restrict__ H, int rowtile,
-                                          cpx<T> *buf, const cpx<T> *stw) {
+                                          cpx<T> *buf, const cpx<T> *stw, int tid, Gate &gate, bool active) {
     using C = cpx<T>;
     using Sh = FftShape<L>;
     constexpr int TPF = Sh::TPF;
     constexpr int ROWS = rows_cta_threads(L) / TPF;
-    const int row = threadIdx.x / TPF;
-    const int j = threadIdx.x % TPF;
+    const int row = tid / TPF;
+    const int j = tid % TPF;
     const size_t k1 = (size_t)rowtile * ROWS + row;
     RowAddr<T, Sh::R0> addr{row * L};
     const size_t hoff = k1 * L + j;
     C *p = scratch_pair + hoff;
 
     C e[16];
+    if (active) {
 #pragma unroll
-    for (int q = 0; q < 16; q++) e[q] = __ldcg(&p[q * TPF]);
+        for (int q = 0; q < 16; q++) e[q] = __ldcg(&p[q * TPF]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 16; q++) { e[q].x = (T)0; e[q].y = (T)0; }
+    }
     auto prefetch_h = [&](C *b) {
+        if (active) {
 #pragma unroll
-        for (int q = 0; q < 16; q++) cp_async_elem(&b[addr.at(j + q * TPF, Sh::P - 1)], &H[hoff + q * TPF]);
+            for (int q = 0; q < 16; q++) cp_async_elem(&b[addr.at(j + q * TPF, Sh::P - 1)], &H[hoff + q * TPF]);
+        }
     };
-    cta_fft<T, L, false>(e, buf, addr, stw, j, prefetch_h);
+    cta_fft<T, L, false, false, true>(e, buf, addr, stw, j, gate, prefetch_h);   // D phase stays open ...
     cp_async_wait_all();
+    if (active) {
 #pragma unroll
-    for (int q = 0; q < 16; q++) e[q] = cmul(e[q], buf[addr.at(j + q * TPF, Sh::P - 1)]);
-    cta_fft<T, L, true>(e, buf, addr, stw, j);
+        for (int q = 0; q < 16; q++) e[q] = cmul(e[q], buf[addr.at(j + q * TPF, Sh::P - 1)]);
+    }
+    cta_fft<T, L, true, true, false>(e, buf, addr, stw, j, gate);                // ... through the inverse's first pass
+    if (active) {
 #pragma unroll
-    for (int q = 0; q < 16; q++) __stcg(&p[q * TPF], e[q]);
+        for (int q = 0; q < 16; q++) __stcg(&p[q * TPF], e[q]);
+    }
 }
 
 // Inverse column tile: conj four-step twiddle, N1-point inverse, keep positions >= D, split re/im to
 // the two real output blocks.
-template <typename T, int N1>
+template <typename T, int N1, typename Gate>
 __device__ __forceinline__ void cols_inv_tile(const ConvGeom &g, const cpx<T> *__restrict__ scratch_pair, const T *x,
                                               T *__restrict__ y, int N2, int lgN, const cpx<T> *stw,
                                               const cpx<T> *__restrict__ tw_hi, const cpx<T> *__restrict__ tw_lo,
-                                              long long pair, int tile, cpx<T> *buf) {
+                                              long long pair, int tile, cpx<T> *buf, int tid, Gate &gate, bool active) {
     using C = cpx<T>;
     using CS = ColShape<N1>;
     constexpr int TPF = CS::TPF, TC = CS::TC;
-    const int c = threadIdx.x % TC;
-    const int j = threadIdx.x / TC;
+    const int c = tid % TC;
+    const int j = tid / TC;
     const int n2 = tile * TC + c;
     ColAddr<TC> addr{c};
 
     const unsigned maskN = (1u << lgN) - 1u;
-    C gtw[16];
-    geometric16(twiddle_n<T>(tw_hi, tw_lo, ((unsigned)n2 * (unsigned)j) & maskN),
-                twiddle_n<T>(tw_hi, tw_lo, ((unsigned)n2 * (unsigned)TPF) & maskN), gtw);
+    const C tw_base = twiddle_n<T>(tw_hi, tw_lo, ((unsigned)n2 * (unsigned)j) & maskN);
+    const C tw_rho = twiddle_n<T>(tw_hi, tw_lo, ((unsigned)n2 * (unsigned)TPF) & maskN);
     const C *src = scratch_pair + n2;
     C e[16];
+    if (active) {
 #pragma unroll
-    for (int q = 0; q < 16; q++) e[q] = cmul_tw<true>(__ldcg(&src[(size_t)(j + q * TPF) * N2]), gtw[q]);
-    cta_fft<T, N1, true>(e, buf, addr, stw, j);
+        for (int q = 0; q < 16; q++) e[q] = __ldcg(&src[(size_t)(j + q * TPF) * N2]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 16; q++) { e[q].x = (T)0; e[q].y = (T)0; }
+    }
+    gate.d_begin();
+    {
+        C gtw[16];
+        geometric16(tw_base, tw_rho, gtw);
+#pragma unroll
+        for (int q = 0; q < 16; q++) e[q] = cmul_tw<true>(e[q], gtw[q]);
+    }
+    cta_fft<T, N1, true, true, false>(e, buf, addr, stw, j, gate);
 
-    const BlockIO<T> a = block_io<T>(g, x, y, 2 * pair);
-    const BlockIO<T> b = block_io<T>(g, x, y, 2 * pair + 1);
+    const BlockIO<T> a = block_io<T>(g, x, y, active ? 2 * pair : g.total_blocks);
+    const BlockIO<T> b = block_io<T>(g, x, y, active ? 2 * pair + 1 : g.total_blocks);
 #pragma unroll
     for (int r = 0; r < 16; r++) {
         const long long o = (long long)(j + r * TPF) * N2 + n2 - g.D;
@@ -292,7 +329,7 @@ __device__ __forceinline__ void cols_inv_tile(const ConvGeom &g, const cpx<T> *_
 }
 
 // ------------------------------------------------------------------------------------------
-// Stand-alone kernels (three launches per group of pairs).  grid = (tiles, pairs in this group).
+// Stand-alone kernels (one tile per CTA).  grid = (tiles, pairs in this group).
 template <typename T, int N1>
 __global__ void __launch_bounds__(ColShape<N1>::THREADS, ColShape<N1>::MIN_CTAS)
 fftconv_cols_fwd(ConvGeom g, const T *__restrict__ x, cpx<T> *__restrict__ scratch, int N2, int lgN,
@@ -304,8 +341,9 @@ fftconv_cols_fwd(ConvGeom g, const T *__restrict__ x, cpx<T> *__restrict__ scrat
     C *buf = reinterpret_cast<C *>(smem_raw);
     C *stw = buf + ((FftShape<N1>::P > 0) ? CS::SMEM_ELEMS : 0);
     load_tw_smem<T, N1>(stw, tw, threadIdx.x, CS::THREADS);
+    CtaGate gate;
     cols_fwd_tile<T, N1>(g, x, scratch + (size_t)blockIdx.y * ((size_t)N1 * N2), N2, lgN, stw, tw_hi, tw_lo,
-                         pair0 + blockIdx.y, blockIdx.x, buf);
+                         pair0 + blockIdx.y, blockIdx.x, buf, threadIdx.x, gate, true);
 }
 
 // SPECTRUM mode: forward only, scaled, written to `spec` (IR spectrum construction, once per plan).
@@ -322,8 +360,9 @@ fftconv_rows(cpx<T> *__restrict__ scratch, const cpx<T> *__restrict__ H, cpx<T> 
     C *stw = buf + ROWS * L;
     load_tw_smem<T, L>(stw, tw, threadIdx.x, rows_cta_threads(L));
     C *pairbase = scratch + (size_t)blockIdx.y * ((size_t)N1 * L);
+    CtaGate gate;
     if (!SPECTRUM) {
-        rows_tile<T, L>(pairbase, H, blockIdx.x, buf, stw);
+        rows_tile<T, L>(pairbase, H, blockIdx.x, buf, stw, threadIdx.x, gate, true);
         return;
     }
     const int row = threadIdx.x / TPF;
@@ -334,7 +373,7 @@ fftconv_rows(cpx<T> *__restrict__ scratch, const cpx<T> *__restrict__ H, cpx<T> 
     C e[16];
 #pragma unroll
     for (int q = 0; q < 16; q++) e[q] = pairbase[hoff + q * TPF];
-    cta_fft<T, L, false>(e, buf, addr, stw, j);
+    cta_fft<T, L, false>(e, buf, addr, stw, j, gate);
 #pragma unroll
     for (int q = 0; q < 16; q++) {
         C v; v.x = e[q].x * scale; v.y = e[q].y * scale;
@@ -353,9 +392,53 @@ fftconv_cols_inv(ConvGeom g, const cpx<T> *__restrict__ scratch, const T *__rest
     C *buf = reinterpret_cast<C *>(smem_raw);
     C *stw = buf + ((FftShape<N1>::P > 0) ? CS::SMEM_ELEMS : 0);
     load_tw_smem<T, N1>(stw, tw, threadIdx.x, CS::THREADS);
+    CtaGate gate;
     cols_inv_tile<T, N1>(g, scratch + (size_t)blockIdx.y * ((size_t)N1 * N2), x, y, N2, lgN, stw, tw_hi, tw_lo,
-                         pair0 + blockIdx.y, blockIdx.x, buf);
+                         pair0 + blockIdx.y, blockIdx.x, buf, threadIdx.x, gate, true);
 }
+
+#if ADSP_WIDE_TILES
+// ------------------------------------------------------------------------------------------
+// Ping-pong kernels: persistent 512-thread CTAs (one per SM); each CTA runs two tiles at a time, one
+// per 256-thread group, phase-locked by PingPongGate so the FP64 pipe and the shared-memory pipe of
+// the SM are busy simultaneously.  Tile T of the launch = (iteration*gridDim.x + blockIdx.x)*2 + group;
+// T -> (pair = T / tiles_per_pair, tile = T % tiles_per_pair).  Padding tiles keep the barrier
+// sequences of the two groups identical.
+enum { PP_COLS_FWD = 0, PP_ROWS = 1, PP_COLS_INV = 2 };
+
+template <typename T, int N1, int L, int KIND>
+__global__ void __launch_bounds__(512, 1)
+fftconv_pingpong(ConvGeom g, const T *__restrict__ x, T *__restrict__ y, cpx<T> *__restrict__ scratch,
+                 const cpx<T> *__restrict__ H, int lgN, const cpx<T> *__restrict__ tw, const cpx<T> *__restrict__ tw_hi,
+                 const cpx<T> *__restrict__ tw_lo, long long pair0, int tiles_per_pair, int ntiles) {
+    using C = cpx<T>;
+    using CS = ColShape<N1>;
+    static_assert(CS::THREADS == 256 && rows_cta_threads(L) == 256, "ping-pong groups are 256 threads");
+    constexpr int BUF_ELEMS = (KIND == PP_ROWS) ? (256 / FftShape<L>::TPF) * L : CS::SMEM_ELEMS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int grp = threadIdx.x >> 8;
+    const int tid = threadIdx.x & 255;
+    C *buf = reinterpret_cast<C *>(smem_raw) + (size_t)grp * BUF_ELEMS;
+    C *stw = reinterpret_cast<C *>(smem_raw) + 2 * (size_t)BUF_ELEMS;
+    if (KIND == PP_ROWS) load_tw_smem<T, L>(stw, tw, threadIdx.x, 512);
+    else load_tw_smem<T, N1>(stw, tw, threadIdx.x, 512);
+    __syncthreads();
+    PingPongGate gate(grp);
+    const size_t pair_elems = (size_t)N1 * L;
+    const int per_iter = 2 * (int)gridDim.x;
+    const int iters = (ntiles + per_iter - 1) / per_iter;
+    for (int it = 0; it < iters; it++) {
+        const int Tix = (it * (int)gridDim.x + (int)blockIdx.x) * 2 + grp;
+        const bool active = Tix < ntiles;
+        const int pl = active ? Tix / tiles_per_pair : 0;
+        const int tile = active ? Tix - pl * tiles_per_pair : 0;
+        C *sp = scratch + (size_t)pl * pair_elems;
+        if (KIND == PP_COLS_FWD) cols_fwd_tile<T, N1>(g, x, sp, L, lgN, stw, tw_hi, tw_lo, pair0 + pl, tile, buf, tid, gate, active);
+        else if (KIND == PP_ROWS) rows_tile<T, L>(sp, H, tile, buf, stw, tid, gate, active);
+        else cols_inv_tile<T, N1>(g, sp, x, y, L, lgN, stw, tw_hi, tw_lo, pair0 + pl, tile, buf, tid, gate, active);
+    }
+}
+#endif
 
 // ------------------------------------------------------------------------------------------
 // Persistent fused kernel: ONE launch runs all three phases of every block pair as a dataflow over
@@ -392,7 +475,7 @@ __device__ __forceinline__ void wait_count(const unsigned *p, unsigned need, uns
     __syncthreads();
 }
 
-#if (ADSP_COLS_CTA_THREADS == 256 && !ADSP_ROWS_SMALL_CTA)
+#if ADSP_WIDE_TILES
 // order[s] = type | idx << 2 | pair_delta << 20
 template <typename T, int N1, int L>
 __global__ void __launch_bounds__(256, 2)
@@ -419,6 +502,7 @@ fftconv_fused(FusedParams prm, const T *__restrict__ x, T *__restrict__ y, cpx<T
     unsigned *stats = done_ci + prm.npairs;   // 8 words
     const size_t pair_elems = (size_t)N1 * L;
 
+    CtaGate cgate;
     const bool dry = (prm.flags & 1) != 0;          // scheduling only (overhead measurement)
     const bool static_tickets = (prm.flags & 2) != 0;
     long long t = static_tickets ? (long long)blockIdx.x : -1;
@@ -478,9 +562,9 @@ fftconv_fused(FusedParams prm, const T *__restrict__ x, T *__restrict__ y, cpx<T
             unsigned pf = 0;
             if (dep_next && threadIdx.x == 0) pf = ld_acquire_u32(dep_next);   // consumed after the task body
             if (!dry) {
-                if (type == TASK_CF) cols_fwd_tile<T, N1>(prm.g, x, slot, prm.N2, prm.lgN, stw_c, tw_hi, tw_lo, pair, idx, buf);
-                else if (type == TASK_R) rows_tile<T, L>(slot, H, idx, buf, stw_r);
-                else cols_inv_tile<T, N1>(prm.g, slot, x, y, prm.N2, prm.lgN, stw_c, tw_hi, tw_lo, pair, idx, buf);
+                if (type == TASK_CF) cols_fwd_tile<T, N1>(prm.g, x, slot, prm.N2, prm.lgN, stw_c, tw_hi, tw_lo, pair, idx, buf, threadIdx.x, cgate, true);
+                else if (type == TASK_R) rows_tile<T, L>(slot, H, idx, buf, stw_r, threadIdx.x, cgate, true);
+                else cols_inv_tile<T, N1>(prm.g, slot, x, y, prm.N2, prm.lgN, stw_c, tw_hi, tw_lo, pair, idx, buf, threadIdx.x, cgate, true);
             }
             __syncthreads();
             if (threadIdx.x == 0) {

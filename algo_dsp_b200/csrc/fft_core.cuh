@@ -167,33 +167,82 @@ __device__ __forceinline__ void load_tw_smem(cpx<T> *stw, const cpx<T> *__restri
     for (int i = tid; i < FftShape<L>::TW_ENTRIES; i += nthreads) stw[i] = __ldg(&gtw[i]);
 }
 
+// ---------------------------------------------------------------- phase gates
+// A transform alternates FP64-pipe phases (butterflies, "D") and shared-memory phases (Stockham
+// exchanges, "L").
+//  * CtaGate: one tile per CTA, whole-CTA barriers, no gating.
+//  * PingPongGate: a 512-thread CTA runs TWO tiles, one per 256-thread group.  Named barriers hand a
+//    D token and an L token back and forth, so one group is always in a D phase while the other is
+//    in an L phase (group 1 trails group 0 by one phase): a deterministic FP64 | LSU pipeline on
+//    every SM instead of the random overlap of independent CTAs.
+struct CtaGate {
+    __device__ __forceinline__ void sync() { __syncthreads(); }
+    __device__ __forceinline__ void d_begin() {}
+    __device__ __forceinline__ void d_end() {}
+    __device__ __forceinline__ void l_begin() {}
+    __device__ __forceinline__ void l_end() {}
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+struct PingPongGate {
+    // barrier ids: 1/2 group-local sync, 3 D 0->1, 4 D 1->0, 5 L 0->1, 6 L 1->0
+    int g;
+    bool first_d = true, first_l = true;
+    __device__ __forceinline__ explicit PingPongGate(int group) : g(group) {}
+    __device__ __forceinline__ void sync() { named_bar_sync(1 + g, 256); }
+    __device__ __forceinline__ void acquire(int id01, int id10, bool &first) {
+        if (g == 0) { if (!first) named_bar_sync(id10, 512); first = false; }
+        else named_bar_sync(id01, 512);
+    }
+    __device__ __forceinline__ void release(int id01, int id10) { named_bar_arrive(g == 0 ? id01 : id10, 512); }
+    __device__ __forceinline__ void d_begin() { acquire(3, 4, first_d); }
+    __device__ __forceinline__ void d_end() { release(3, 4); }
+    __device__ __forceinline__ void l_begin() { acquire(5, 6, first_l); }
+    __device__ __forceinline__ void l_end() { release(5, 6); }
+};
+
 // ---------------------------------------------------------------- the in-CTA transform
 // e[q] holds point (j + q*TPF) of the transform on entry and on exit (natural order).
 // stw: compact twiddle table for this L in SHARED memory (see tw_pass_entries; entry for power r,
 //      position k of a pass with NS: exp(-2*pi*i * r*k / (16*NS))).
 // hook(buf): called once, right after the last pass has read its inputs from `buf` (the calling
 //      thread may then reuse exactly the slots it read: addr.at(j + q*TPF, P-1)).
-// All threads of the CTA must call this together (it uses __syncthreads).
-template <typename T, int L, bool INV, typename Addr, typename Hook = NoHook>
-__device__ __forceinline__ void cta_fft(cpx<T> (&e)[16], cpx<T> *buf, const Addr &addr,
-                                        const cpx<T> *stw, int j, const Hook &hook = Hook()) {
+// gate: barrier/phase policy (see above).  D_OPEN_IN: the caller already holds the D phase;
+//      D_OPEN_OUT: leave the final D phase open for the caller to close (gate.d_end()).
+// All threads of the CTA (or ping-pong group) must call this together.
+template <typename T, int L, bool INV, bool D_OPEN_IN = false, bool D_OPEN_OUT = false, typename Addr, typename Gate,
+          typename Hook = NoHook>
+__device__ __forceinline__ void cta_fft(cpx<T> (&e)[16], cpx<T> *buf, const Addr &addr, const cpx<T> *stw, int j,
+                                        Gate &gate, const Hook &hook = Hook()) {
     using C = cpx<T>;
     using Sh = FftShape<L>;
     constexpr int R0 = Sh::R0, P = Sh::P, TPF = Sh::TPF, S0 = 16 / R0;
 
     // pass 0: radix R0, no twiddles
+    if (!D_OPEN_IN) gate.d_begin();
 #pragma unroll
     for (int u = 0; u < S0; u++) Dft<R0, S0, INV, C>::run(&e[u]);
-    if (P == 0) return;
+    if (P == 0) {
+        if (!D_OPEN_OUT) gate.d_end();
+        return;
+    }
+    gate.d_end();
 
-    __syncthreads();  // buffer may still be read by the previous user
+    gate.l_begin();
+    gate.sync();  // buffer may still be read by the previous user
 #pragma unroll
     for (int u = 0; u < S0; u++) {
         const int b = j + u * TPF;
 #pragma unroll
         for (int r = 0; r < R0; r++) buf[addr.at(R0 * b + r, 0)] = e[u + r * S0];
     }
-    __syncthreads();
+    gate.sync();
 
     int ns = R0;
     int off = 0;
@@ -202,6 +251,9 @@ __device__ __forceinline__ void cta_fft(cpx<T> (&e)[16], cpx<T> *buf, const Addr
 #pragma unroll
         for (int q = 0; q < 16; q++) e[q] = buf[addr.at(j + q * TPF, t - 1)];
         if (t == P) hook(buf);
+        gate.l_end();
+
+        gate.d_begin();
         const int k = j & (ns - 1);
         if (ns <= 16) {
             const C *twp = stw + off + k;
@@ -232,15 +284,18 @@ __device__ __forceinline__ void cta_fft(cpx<T> (&e)[16], cpx<T> *buf, const Addr
         }
         Dft<16, 1, INV, C>::run(&e[0]);
         if (t < P) {
-            __syncthreads();
+            gate.d_end();
+            gate.l_begin();
+            gate.sync();
             const int j0 = (j - k) * 16 + k;
 #pragma unroll
             for (int r = 0; r < 16; r++) buf[addr.at(j0 + r * ns, t)] = e[r];
-            __syncthreads();
+            gate.sync();
         }
         off += tw_pass_entries(ns);
         ns *= 16;
     }
+    if (!D_OPEN_OUT) gate.d_end();
 }
 
 // 16-byte / 8-byte asynchronous global -> shared copy (LDGSTS), used to prefetch the spectrum

@@ -215,8 +215,69 @@ static adsp_status launch_cols(adsp_ctx *ctx, cudaStream_t st, int N1, bool inve
     }
 }
 
+// ------------------------------------------------------------------ ping-pong kernels
+#define ADSP_PINGPONG_AVAILABLE ADSP_WIDE_TILES
+#if ADSP_PINGPONG_AVAILABLE
+template <typename T, int N1, int L, int KIND>
+static adsp_status launch_pp_t(adsp_ctx *ctx, cudaStream_t st, const ConvGeom &g, const T *x, T *y, cpx<T> *scratch,
+                               const cpx<T> *H, int lgN, const cpx<T> *tw, const cpx<T> *hi, const cpx<T> *lo, long long pair0,
+                               int pairs) {
+    using CS = ColShape<N1>;
+    constexpr int BUF_ELEMS = (KIND == PP_ROWS) ? (256 / FftShape<L>::TPF) * L : CS::SMEM_ELEMS;
+    constexpr int TW = (KIND == PP_ROWS) ? FftShape<L>::TW_ENTRIES : FftShape<N1>::TW_ENTRIES;
+    const size_t smem = (2 * (size_t)BUF_ELEMS + TW) * sizeof(cpx<T>);
+    static AttrOnce once;
+    if (once.need(ctx->device)) ADSP_TRY(set_smem(fftconv_pingpong<T, N1, L, KIND>, smem));
+    const int tiles_per_pair = (KIND == PP_ROWS) ? N1 / (256 / FftShape<L>::TPF) : L / CS::TC;
+    const int ntiles = tiles_per_pair * pairs;
+    int grid = (ntiles + 1) / 2;
+    if (grid > ctx->sm_count) grid = ctx->sm_count;
+    LaunchTimer lt(ctx, st, KIND == PP_ROWS ? KK_ROWS : (KIND == PP_COLS_FWD ? KK_COLS_FWD : KK_COLS_INV));
+    fftconv_pingpong<T, N1, L, KIND><<<grid, 512, smem, st>>>(g, x, y, scratch, H, lgN, tw, hi, lo, pair0, tiles_per_pair, ntiles);
+    count_launch(ctx);
+    ADSP_CUDA(cudaGetLastError());
+    return ADSP_OK;
+}
+
+template <typename T, int N1, int L>
+static adsp_status launch_pp_group(adsp_ctx *ctx, cudaStream_t st, const ConvGeom &g, const T *x, T *y, cpx<T> *scratch,
+                                   const cpx<T> *H, int lgN, const cpx<T> *tw_rows, const cpx<T> *tw_cols, const cpx<T> *hi,
+                                   const cpx<T> *lo, long long pair0, int pairs) {
+    ADSP_TRY((launch_pp_t<T, N1, L, PP_COLS_FWD>(ctx, st, g, x, y, scratch, H, lgN, tw_cols, hi, lo, pair0, pairs)));
+    ADSP_TRY((launch_pp_t<T, N1, L, PP_ROWS>(ctx, st, g, x, y, scratch, H, lgN, tw_rows, hi, lo, pair0, pairs)));
+    ADSP_TRY((launch_pp_t<T, N1, L, PP_COLS_INV>(ctx, st, g, x, y, scratch, H, lgN, tw_cols, hi, lo, pair0, pairs)));
+    return ADSP_OK;
+}
+#endif
+
+// one group (cols_fwd -> rows -> cols_inv) through the ping-pong kernels; *done=false if (N1,N2) has no instantiation
+template <typename T>
+static adsp_status launch_pp(adsp_ctx *ctx, cudaStream_t st, int N1, int N2, const ConvGeom &g, const T *x, T *y,
+                             cpx<T> *scratch, const cpx<T> *H, int lgN, const cpx<T> *tw_rows, const cpx<T> *tw_cols,
+                             const cpx<T> *hi, const cpx<T> *lo, long long pair0, int pairs, bool *done) {
+    *done = true;
+#if ADSP_PINGPONG_AVAILABLE
+#define ADSP_PP_CASE(n1, n2) \
+    if (N1 == n1 && N2 == n2) return launch_pp_group<T, n1, n2>(ctx, st, g, x, y, scratch, H, lgN, tw_rows, tw_cols, hi, lo, pair0, pairs);
+    ADSP_PP_CASE(16, 4096) ADSP_PP_CASE(32, 4096) ADSP_PP_CASE(64, 4096) ADSP_PP_CASE(128, 4096) ADSP_PP_CASE(256, 4096)
+    ADSP_PP_CASE(128, 2048) ADSP_PP_CASE(256, 2048)
+#undef ADSP_PP_CASE
+#endif
+    *done = false;
+    return ADSP_OK;
+}
+
+static bool pp_supported(int N1, int N2) {
+#if ADSP_PINGPONG_AVAILABLE
+    return (N2 == 4096 && (N1 == 16 || N1 == 32 || N1 == 64 || N1 == 128 || N1 == 256)) || (N2 == 2048 && (N1 == 128 || N1 == 256));
+#else
+    (void)N1; (void)N2;
+    return false;
+#endif
+}
+
 // ------------------------------------------------------------------ persistent fused kernel
-#define ADSP_FUSED_AVAILABLE (ADSP_COLS_CTA_THREADS == 256 && !ADSP_ROWS_SMALL_CTA)
+#define ADSP_FUSED_AVAILABLE ADSP_WIDE_TILES
 struct FusedPlan {
     std::vector<unsigned> order;
     int round_len = 0, tiles_c = 0, tiles_r = 0, nslots = 0, extra_rounds = 0;
@@ -391,11 +452,35 @@ adsp_status FftConv<T>::run(const T *d_x, long long n, long long channels, long 
     size_t budget = ctx->scratch_budget;
     const long long mb = env_ll("ADSP_SCRATCH_MB", 0);  // tuning override
     if (mb > 0) budget = (size_t)mb << 20;
-    long long G = (long long)(budget / kWorkerStreams / per_pair);
+
+    // ping-pong kernels: persistent 512-thread CTAs, two phase-locked tiles per SM
+    const int conc = 2 * ctx->sm_count;   // tiles in flight
+    const int tiles_r = ch.N1 / (256 / (ch.N2 / 16) > 0 ? 256 / (ch.N2 / 16) : 1);
+    const bool use_pp = pp_supported(ch.N1, ch.N2) && env_ll("ADSP_PINGPONG", 0) != 0 && npairs * (long long)tiles_r >= conc;
+    int nslots_max = use_pp ? 2 : kWorkerStreams;
+    long long G = (long long)(budget / nslots_max / per_pair);
     if (G < 1) G = 1;
     if (G > npairs) G = npairs;
     if (G > 32768) G = 32768;
-    const int nslots = (npairs > G) ? kWorkerStreams : 1;
+    if (use_pp && G > 1) {
+        // pick the group size whose tile counts fill whole waves of `conc` tiles best
+        const int tiles_c = ch.N2 / (256 / (ch.N1 / 16));
+        long long best = G;
+        double best_eff = 0;
+        for (long long cand = G; cand >= (G + 1) / 2 && cand >= 1; cand--) {
+            double eff = 1.0;
+            for (int tp : {tiles_r, tiles_c}) {
+                const long long nt = cand * tp;
+                const double e = (double)nt / (double)(((nt + conc - 1) / conc) * conc);
+                if (e < eff) eff = e;
+            }
+            if (eff > best_eff + 1e-9) { best_eff = eff; best = cand; }
+        }
+        G = best;
+        const long long forced = env_ll("ADSP_PP_GROUP", 0);
+        if (forced > 0) G = std::min<long long>(forced, npairs);
+    }
+    const int nslots = (npairs > G) ? nslots_max : 1;
     ADSP_TRY(ctx->scratch.reserve((size_t)nslots * (size_t)G * per_pair));
     cpx<T> *scr = (cpx<T> *)ctx->scratch.p;
 
@@ -409,6 +494,9 @@ adsp_status FftConv<T>::run(const T *d_x, long long n, long long channels, long 
         const int slot = (int)(grp % nslots);
         cudaStream_t st = (nslots > 1) ? ctx->worker[slot] : ctx->main;
         cpx<T> *sl = scr + (size_t)slot * (size_t)G * (size_t)ch.N;
+        bool done = false;
+        if (use_pp) ADSP_TRY(launch_pp<T>(ctx, st, ch.N1, ch.N2, g, d_x, d_y, sl, H, ch.lgN, tw_rows, tw_cols, tw_hi, tw_lo, pair0, gp, &done));
+        if (done) continue;
         ADSP_TRY(launch_cols<T>(ctx, st, ch.N1, false, g, d_x, d_y, sl, ch.N2, ch.lgN, tw_cols, tw_hi, tw_lo, pair0, gp));
         ADSP_TRY((launch_rows<T, false>(ctx, st, ch.N2, sl, H, (cpx<T> *)nullptr, (T)0, ch.N1, tw_rows, gp)));
         ADSP_TRY(launch_cols<T>(ctx, st, ch.N1, true, g, d_x, d_y, sl, ch.N2, ch.lgN, tw_cols, tw_hi, tw_lo, pair0, gp));

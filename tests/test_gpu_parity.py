@@ -237,35 +237,29 @@ def test_full_size_batch_properties(conv, oracle):
     assert rel(yi[12345:12345 + K], h) <= 1e-12 and np.max(np.abs(yi[:12345])) <= 1e-13
 
 
-def test_fused_persistent_kernel_matches_three_kernel_path(conv, oracle, monkeypatch):
-    """Large batches run the persistent fused four-step kernel; it must agree bit for bit with the
-    three-kernel path (same arithmetic, different scheduling) and with the oracle."""
+def test_large_batch_groups_and_streams(conv, oracle, monkeypatch):
+    """Large batches are cut into L2-sized groups of block pairs rotated over worker streams; the
+    grouping must not change the results (also: odd block counts, fp32, host-chunked pipeline)."""
     K, n, ch = 20000, 150000, 48
-    monkeypatch.setenv("ADSP_PIPE_CHUNK_MB", "4096")   # one chunk: the whole batch in a single engine call
     h = G.decaying_ir(K)
     x = np.stack([G.white(n, seed=50 + c) for c in range(ch)])
     ols = conv.NewOverlapSave(h, 0)
-    ctx = conv.default_context()
-    ctx.kernel_timing(True)
-    ctx.kernel_times(reset=True)
-    y_fused = ols.ProcessBatch(x)
-    kt = ctx.kernel_times(reset=True)
-    assert kt["fused"][1] >= 1 and kt["rows"][1] == 0
-    monkeypatch.setenv("ADSP_NO_FUSED", "1")
-    y_three = ols.ProcessBatch(x)
-    kt = ctx.kernel_times(reset=True)
-    ctx.kernel_timing(False)
-    assert kt["fused"][1] == 0 and kt["rows"][1] >= 1
-    assert np.array_equal(y_fused, y_three)
+    monkeypatch.setenv("ADSP_PIPE_CHUNK_MB", "4096")   # one chunk: the whole batch in a single engine call
+    y_one = ols.ProcessBatch(x)
+    monkeypatch.setenv("ADSP_SCRATCH_MB", "8")         # tiny scratch budget -> many small groups
+    y_small = ols.ProcessBatch(x)
+    monkeypatch.delenv("ADSP_SCRATCH_MB")
+    monkeypatch.setenv("ADSP_PIPE_CHUNK_MB", "16")     # host pipeline in many chunks
+    y_chunks = ols.ProcessBatch(x)
+    # two real blocks share one complex transform, so a block's rounding depends (at the 1e-16 level)
+    # on its partner: regrouping is not bit-identical, only far inside the tolerance
+    assert rel(y_small, y_one) <= 1e-14 and rel(y_chunks, y_one) <= 1e-14
     for c in (0, 17, ch - 1):
-        assert rel(y_fused[c], oracle.overlap_save(h, 0, x[c])) <= TOL64
-    # odd number of blocks (last pair half empty) and the fp32 mode
-    monkeypatch.delenv("ADSP_NO_FUSED")
-    x2 = x[:33]
-    y2 = conv.NewOverlapSave(h, 0).ProcessBatch(x2)
-    assert np.array_equal(y2, y_fused[:33])
-    y32 = conv.NewOverlapSave(h, 0, dtype=np.float32).ProcessBatch(x2.astype(np.float32))
-    assert rel(y32[5], oracle.overlap_save(h, 0, x2[5])) <= TOL32
+        assert rel(y_one[c], oracle.overlap_save(h, 0, x[c])) <= TOL64
+    y2 = conv.NewOverlapSave(h, 0).ProcessBatch(x[:33])
+    assert rel(y2, y_one[:33]) <= 1e-14
+    y32 = conv.NewOverlapSave(h, 0, dtype=np.float32).ProcessBatch(x[:33].astype(np.float32))
+    assert rel(y32[5], oracle.overlap_save(h, 0, x[5])) <= TOL32
 
 
 def test_long_kernel_partitions_config5_shape(conv, oracle):
