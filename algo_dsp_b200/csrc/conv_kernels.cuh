@@ -59,6 +59,16 @@ __device__ __forceinline__ BlockIO<T> block_io(const ConvGeom &g, const T *x, T 
 
 template <typename T> __device__ __forceinline__ T ld_stream(const T *p) { return __ldcs(p); }
 
+// Timing-attribution switches (development only, results are WRONG when non-zero): skip a memory
+// phase of a tile to see what hiding it would be worth.  bit0 rows load, bit1 rows store, bit2 rows
+// H prefetch+multiply, bit3 cols_fwd load, bit4 cols_fwd store, bit5 cols_inv load, bit6 cols_inv store.
+#ifdef ADSP_PHASE_DEBUG
+static __device__ int g_phase_skip = 0;
+#define ADSP_SKIP(bit) ((g_phase_skip >> (bit)) & 1)
+#else
+#define ADSP_SKIP(bit) 0
+#endif
+
 // CTA shapes (compile-time knobs; tools/ builds variants with -D to A/B them on the GPU).
 // A row CTA owns 16 points per thread: L/16 threads per row, rows_cta_threads(L)/(L/16) rows per CTA.
 // ADSP_EXPERIMENTAL=1 additionally compiles the ping-pong and persistent fused kernels (both measured
@@ -214,8 +224,8 @@ __device__ __forceinline__ void cols_fwd_tile(const ConvGeom &g, const T *__rest
 #pragma unroll
     for (int q = 0; q < 16; q++) {
         const long long i = (long long)(j + q * TPF) * N2 + n2;
-        e[q].x = (i >= a.lo && i < a.hi) ? ld_stream(a.in + i) : (T)0;
-        e[q].y = (i >= b.lo && i < b.hi) ? ld_stream(b.in + i) : (T)0;
+        e[q].x = (i >= a.lo && i < a.hi && !ADSP_SKIP(3)) ? ld_stream(a.in + i) : (T)0;
+        e[q].y = (i >= b.lo && i < b.hi && !ADSP_SKIP(3)) ? ld_stream(b.in + i) : (T)0;
     }
     cta_fft<T, N1, false, false, true>(e, buf, addr, stw, j, gate);   // leaves the last D phase open
 
@@ -225,7 +235,7 @@ __device__ __forceinline__ void cols_fwd_tile(const ConvGeom &g, const T *__rest
 #pragma unroll
     for (int r = 0; r < 16; r++) e[r] = cmul(e[r], gtw[r]);
     gate.d_end();
-    if (active) {
+    if (active && !ADSP_SKIP(4)) {
         C *dst = scratch_pair + n2;
 #pragma unroll
         for (int r = 0; r < 16; r++) __stcg(&dst[(size_t)(j + r * TPF) * N2], e[r]);
@@ -249,7 +259,7 @@ __device__ __forceinline__ void rows_tile(cpx<T> *__restrict__ scratch_pair, con
     C *p = scratch_pair + hoff;
 
     C e[16];
-    if (active) {
+    if (active && !ADSP_SKIP(0)) {
 #pragma unroll
         for (int q = 0; q < 16; q++) e[q] = __ldcg(&p[q * TPF]);
     } else {
@@ -257,19 +267,19 @@ __device__ __forceinline__ void rows_tile(cpx<T> *__restrict__ scratch_pair, con
         for (int q = 0; q < 16; q++) { e[q].x = (T)0; e[q].y = (T)0; }
     }
     auto prefetch_h = [&](C *b) {
-        if (active) {
+        if (active && !ADSP_SKIP(2)) {
 #pragma unroll
             for (int q = 0; q < 16; q++) cp_async_elem(&b[addr.at(j + q * TPF, Sh::P - 1)], &H[hoff + q * TPF]);
         }
     };
     cta_fft<T, L, false, false, true>(e, buf, addr, stw, j, gate, prefetch_h);   // D phase stays open ...
     cp_async_wait_all();
-    if (active) {
+    if (active && !ADSP_SKIP(2)) {
 #pragma unroll
         for (int q = 0; q < 16; q++) e[q] = cmul(e[q], buf[addr.at(j + q * TPF, Sh::P - 1)]);
     }
     cta_fft<T, L, true, true, false>(e, buf, addr, stw, j, gate);                // ... through the inverse's first pass
-    if (active) {
+    if (active && !ADSP_SKIP(1)) {
 #pragma unroll
         for (int q = 0; q < 16; q++) __stcg(&p[q * TPF], e[q]);
     }
@@ -295,7 +305,7 @@ __device__ __forceinline__ void cols_inv_tile(const ConvGeom &g, const cpx<T> *_
     const C tw_rho = twiddle_n<T>(tw_hi, tw_lo, ((unsigned)n2 * (unsigned)TPF) & maskN);
     const C *src = scratch_pair + n2;
     C e[16];
-    if (active) {
+    if (active && !ADSP_SKIP(5)) {
 #pragma unroll
         for (int q = 0; q < 16; q++) e[q] = __ldcg(&src[(size_t)(j + q * TPF) * N2]);
     } else {
@@ -316,7 +326,7 @@ __device__ __forceinline__ void cols_inv_tile(const ConvGeom &g, const cpx<T> *_
 #pragma unroll
     for (int r = 0; r < 16; r++) {
         const long long o = (long long)(j + r * TPF) * N2 + n2 - g.D;
-        if (o >= 0) {
+        if (o >= 0 && !ADSP_SKIP(6)) {
             if (g.accumulate) {
                 if (o < a.cnt) a.out[o] += e[r].x;
                 if (o < b.cnt) b.out[o] += e[r].y;

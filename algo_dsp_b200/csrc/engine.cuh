@@ -32,7 +32,7 @@ adsp_status cuda_fail(cudaError_t e, const char *what, const char *file, int lin
         if (s__ != ADSP_OK) return s__;      \
     } while (0)
 
-constexpr int kWorkerStreams = 3;
+constexpr int kWorkerStreams = 8;   // created per context; ADSP_STREAMS (default 3) of them are used per call
 
 struct DevBuf {
     void *p = nullptr;
@@ -70,9 +70,9 @@ struct adsp_ctx {
     int sm_count = 0;
     size_t l2_bytes = 0;
     cudaStream_t main = nullptr;
-    cudaStream_t worker[adsp::kWorkerStreams] = {nullptr, nullptr, nullptr};
+    cudaStream_t worker[adsp::kWorkerStreams] = {};
     cudaEvent_t ev_fork = nullptr;
-    cudaEvent_t ev_join[adsp::kWorkerStreams] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_join[adsp::kWorkerStreams] = {};
     std::mutex mu;  // serialises calls that use the context's staging / scratch buffers
     std::map<std::pair<int, int>, void *> tw_tables;                     // (L, prec) -> device table
     std::map<std::pair<int, int>, std::pair<void *, void *>> tw4_tables;  // (lgN, prec) -> (hi, lo)

@@ -428,6 +428,9 @@ template <typename T>
 adsp_status FftConv<T>::run(const T *d_x, long long n, long long channels, long long in_stride, T *d_y,
                             long long out_stride, long long out_len, long long in_shift, long long out_shift,
                             bool accumulate) {
+#ifdef ADSP_PHASE_DEBUG
+    { const int f = (int)env_ll("ADSP_PHASE_SKIP", 0); cudaMemcpyToSymbol(g_phase_skip, &f, sizeof f); }
+#endif
     ConvGeom g{};
     g.n = n; g.out_len = out_len; g.in_stride = in_stride; g.out_stride = out_stride;
     g.S = ch.S; g.D = ch.D;
@@ -457,7 +460,10 @@ adsp_status FftConv<T>::run(const T *d_x, long long n, long long channels, long 
     const int conc = 2 * ctx->sm_count;   // tiles in flight
     const int tiles_r = ch.N1 / (256 / (ch.N2 / 16) > 0 ? 256 / (ch.N2 / 16) : 1);
     const bool use_pp = pp_supported(ch.N1, ch.N2) && env_ll("ADSP_PINGPONG", 0) != 0 && npairs * (long long)tiles_r >= conc;
-    int nslots_max = use_pp ? 2 : kWorkerStreams;
+    int nstreams = (int)env_ll("ADSP_STREAMS", 3);
+    if (nstreams < 1) nstreams = 1;
+    if (nstreams > kWorkerStreams) nstreams = kWorkerStreams;
+    int nslots_max = use_pp ? 2 : nstreams;
     long long G = (long long)(budget / nslots_max / per_pair);
     if (G < 1) G = 1;
     if (G > npairs) G = npairs;
