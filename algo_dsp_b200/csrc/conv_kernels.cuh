@@ -59,15 +59,7 @@ __device__ __forceinline__ BlockIO<T> block_io(const ConvGeom &g, const T *x, T 
 
 template <typename T> __device__ __forceinline__ T ld_stream(const T *p) { return __ldcs(p); }
 
-// Timing-attribution switches (development only, results are WRONG when non-zero): skip a memory
-// phase of a tile to see what hiding it would be worth.  bit0 rows load, bit1 rows store, bit2 rows
-// H prefetch+multiply, bit3 cols_fwd load, bit4 cols_fwd store, bit5 cols_inv load, bit6 cols_inv store.
-#ifdef ADSP_PHASE_DEBUG
-static __device__ int g_phase_skip = 0;
-#define ADSP_SKIP(bit) ((g_phase_skip >> (bit)) & 1)
-#else
-#define ADSP_SKIP(bit) 0
-#endif
+
 
 // CTA shapes (compile-time knobs; tools/ builds variants with -D to A/B them on the GPU).
 // A row CTA owns 16 points per thread: L/16 threads per row, rows_cta_threads(L)/(L/16) rows per CTA.
@@ -83,8 +75,11 @@ static __device__ int g_phase_skip = 0;
 #define ADSP_COLS_CTA_THREADS (ADSP_EXPERIMENTAL ? 256 : 128)
 #endif
 #define ADSP_WIDE_TILES (ADSP_EXPERIMENTAL && ADSP_COLS_CTA_THREADS == 256 && !ADSP_ROWS_SMALL_CTA)
+#ifndef ADSP_MIN_CTAS_128
+#define ADSP_MIN_CTAS_128 4      // resident 128-thread CTAs per SM the register allocator must allow (4 -> 128 regs, 5 -> 102)
+#endif
 constexpr int rows_cta_threads(int L) { return (ADSP_ROWS_SMALL_CTA && L <= 2048) ? 128 : 256; }
-constexpr int rows_min_ctas(int L) { return 512 / rows_cta_threads(L); }
+constexpr int rows_min_ctas(int L) { return rows_cta_threads(L) == 128 ? ADSP_MIN_CTAS_128 : 2; }
 
 // ------------------------------------------------------------------------------------------
 // Single-kernel path, N = L <= 4096.  256 threads; 4096/L block-pairs per CTA.
@@ -166,6 +161,23 @@ __device__ __forceinline__ cpx<T> twiddle_n(const cpx<T> *__restrict__ tw_hi, co
     return cmul(__ldg(&tw_hi[m >> 10]), __ldg(&tw_lo[m & 1023u]));
 }
 
+// e[r] *= base * rho^r (forward) or its conjugate (INV), r = 0..15, forming the factors on the fly so
+// that only base/rho/rho^2/rho^4 stay live (the 16-entry table variant below costs 64 registers).
+template <bool INV, typename C> __device__ __forceinline__ void apply_geometric16(C (&e)[16], C base, C rho) {
+    const C rho2 = cmul(rho, rho);
+    const C rho4 = cmul(rho2, rho2);
+    C ga = base;
+#pragma unroll
+    for (int a = 0; a < 16; a += 4) {
+        if (a) ga = cmul(ga, rho4);
+        e[a] = cmul_tw<INV>(e[a], ga);
+        e[a + 1] = cmul_tw<INV>(e[a + 1], cmul(ga, rho));
+        const C g2 = cmul(ga, rho2);
+        e[a + 2] = cmul_tw<INV>(e[a + 2], g2);
+        e[a + 3] = cmul_tw<INV>(e[a + 3], cmul(g2, rho));
+    }
+}
+
 // g_r = base * rho^r, r = 0..15, short dependency chains (depth <= 6 products).
 template <typename C> __device__ __forceinline__ void geometric16(C base, C rho, C (&g)[16]) {
     const C rho2 = cmul(rho, rho);
@@ -187,7 +199,7 @@ template <int N1> struct ColShape {
     static constexpr int TC = (N1 <= 256) ? (ADSP_COLS_CTA_THREADS / TPF) : ((N1 == 512) ? 16 : 8);  // columns per tile
     static constexpr int THREADS = TPF * TC;
     static constexpr int SMEM_ELEMS = N1 * TC;
-    static constexpr int MIN_CTAS = (THREADS <= 128) ? 4 : ((THREADS <= 256) ? 2 : 1);
+    static constexpr int MIN_CTAS = (THREADS <= 128) ? ADSP_MIN_CTAS_128 : ((THREADS <= 256) ? 2 : 1);
 };
 
 // ------------------------------------------------------------------------------------------
@@ -230,10 +242,7 @@ __device__ __forceinline__ void cols_fwd_tile(const ConvGeom &g, const T *__rest
     cta_fft<T, N1, false, false, true>(e, buf, addr, stw, j, gate);   // leaves the last D phase open
 
     // k1 = j + r*TPF  ->  W_N^(n2*j) * (W_N^(n2*TPF))^r
-    C gtw[16];
-    geometric16(tw_base, tw_rho, gtw);
-#pragma unroll
-    for (int r = 0; r < 16; r++) e[r] = cmul(e[r], gtw[r]);
+    apply_geometric16<false>(e, tw_base, tw_rho);
     gate.d_end();
     if (active && !ADSP_SKIP(4)) {
         C *dst = scratch_pair + n2;
@@ -313,12 +322,7 @@ __device__ __forceinline__ void cols_inv_tile(const ConvGeom &g, const cpx<T> *_
         for (int q = 0; q < 16; q++) { e[q].x = (T)0; e[q].y = (T)0; }
     }
     gate.d_begin();
-    {
-        C gtw[16];
-        geometric16(tw_base, tw_rho, gtw);
-#pragma unroll
-        for (int q = 0; q < 16; q++) e[q] = cmul_tw<true>(e[q], gtw[q]);
-    }
+    apply_geometric16<true>(e, tw_base, tw_rho);
     cta_fft<T, N1, true, true, false>(e, buf, addr, stw, j, gate);
 
     const BlockIO<T> a = block_io<T>(g, x, y, active ? 2 * pair : g.total_blocks);
@@ -432,6 +436,7 @@ fftconv_pingpong(ConvGeom g, const T *__restrict__ x, T *__restrict__ y, cpx<T> 
     C *stw = reinterpret_cast<C *>(smem_raw) + 2 * (size_t)BUF_ELEMS;
     if (KIND == PP_ROWS) load_tw_smem<T, L>(stw, tw, threadIdx.x, 512);
     else load_tw_smem<T, N1>(stw, tw, threadIdx.x, 512);
+    cp_async_wait_all();
     __syncthreads();
     PingPongGate gate(grp);
     const size_t pair_elems = (size_t)N1 * L;

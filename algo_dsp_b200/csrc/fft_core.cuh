@@ -16,6 +16,17 @@
 
 namespace adsp {
 
+// Timing-attribution switches (development only, results are WRONG when non-zero): skip a memory
+// phase of a tile to see what hiding it would be worth.  bit0 rows load, bit1 rows store, bit2 rows
+// H prefetch+multiply, bit3 cols_fwd load, bit4 cols_fwd store, bit5 cols_inv load, bit6 cols_inv store,
+// bit7 all butterfly/twiddle arithmetic, bit8 all shared-memory exchange traffic (barriers kept).
+#ifdef ADSP_PHASE_DEBUG
+static __device__ int g_phase_skip = 0;
+#define ADSP_SKIP(bit) ((g_phase_skip >> (bit)) & 1)
+#else
+#define ADSP_SKIP(bit) 0
+#endif
+
 template <typename T> struct cpx_of;
 template <> struct cpx_of<double> { using type = double2; };
 template <> struct cpx_of<float> { using type = float2; };
@@ -161,10 +172,21 @@ struct NoHook {
     template <typename C> __device__ __forceinline__ void operator()(C * /*buf*/) const {}
 };
 
-// cooperative copy of the compact twiddle table (global -> shared); caller syncs afterwards
+// 16-byte / 8-byte asynchronous global -> shared copy (LDGSTS), used to prefetch the spectrum
+template <typename C> __device__ __forceinline__ void cp_async_elem(C *smem_dst, const C *gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    if (sizeof(C) == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+
+// cooperative ASYNCHRONOUS copy of the compact twiddle table (global -> shared, cp.async: no register
+// dependency, so the tile's own global loads issue right behind it instead of waiting a full memory
+// round trip).  cta_fft waits for it (cp.async.wait_all + barrier) just before the first twiddled pass.
 template <typename T, int L>
 __device__ __forceinline__ void load_tw_smem(cpx<T> *stw, const cpx<T> *__restrict__ gtw, int tid, int nthreads) {
-    for (int i = tid; i < FftShape<L>::TW_ENTRIES; i += nthreads) stw[i] = __ldg(&gtw[i]);
+    for (int i = tid; i < FftShape<L>::TW_ENTRIES; i += nthreads) cp_async_elem(&stw[i], &gtw[i]);
 }
 
 // ---------------------------------------------------------------- phase gates
@@ -226,8 +248,10 @@ __device__ __forceinline__ void cta_fft(cpx<T> (&e)[16], cpx<T> *buf, const Addr
 
     // pass 0: radix R0, no twiddles
     if (!D_OPEN_IN) gate.d_begin();
+    if (!ADSP_SKIP(7)) {
 #pragma unroll
-    for (int u = 0; u < S0; u++) Dft<R0, S0, INV, C>::run(&e[u]);
+        for (int u = 0; u < S0; u++) Dft<R0, S0, INV, C>::run(&e[u]);
+    }
     if (P == 0) {
         if (!D_OPEN_OUT) gate.d_end();
         return;
@@ -236,26 +260,32 @@ __device__ __forceinline__ void cta_fft(cpx<T> (&e)[16], cpx<T> *buf, const Addr
 
     gate.l_begin();
     gate.sync();  // buffer may still be read by the previous user
+    if (!ADSP_SKIP(8)) {
 #pragma unroll
-    for (int u = 0; u < S0; u++) {
-        const int b = j + u * TPF;
+        for (int u = 0; u < S0; u++) {
+            const int b = j + u * TPF;
 #pragma unroll
-        for (int r = 0; r < R0; r++) buf[addr.at(R0 * b + r, 0)] = e[u + r * S0];
+            for (int r = 0; r < R0; r++) buf[addr.at(R0 * b + r, 0)] = e[u + r * S0];
+        }
     }
+    cp_async_wait_all();   // twiddle table copy (load_tw_smem) issued by this thread has landed
     gate.sync();
 
     int ns = R0;
     int off = 0;
 #pragma unroll
     for (int t = 1; t <= P; t++) {
+        if (!ADSP_SKIP(8)) {
 #pragma unroll
-        for (int q = 0; q < 16; q++) e[q] = buf[addr.at(j + q * TPF, t - 1)];
+            for (int q = 0; q < 16; q++) e[q] = buf[addr.at(j + q * TPF, t - 1)];
+        }
         if (t == P) hook(buf);
         gate.l_end();
 
         gate.d_begin();
         const int k = j & (ns - 1);
-        if (ns <= 16) {
+        if (ADSP_SKIP(7)) {
+        } else if (ns <= 16) {
             const C *twp = stw + off + k;
 #pragma unroll
             for (int r = 1; r < 16; r++) e[r] = cmul_tw<INV>(e[r], twp[(r - 1) * ns]);
@@ -282,14 +312,16 @@ __device__ __forceinline__ void cta_fft(cpx<T> (&e)[16], cpx<T> *buf, const Addr
             e[14] = cmul_tw<INV>(e[14], w14);
             e[15] = cmul_tw<INV>(e[15], cmul(w14, w1));
         }
-        Dft<16, 1, INV, C>::run(&e[0]);
+        if (!ADSP_SKIP(7)) Dft<16, 1, INV, C>::run(&e[0]);
         if (t < P) {
             gate.d_end();
             gate.l_begin();
             gate.sync();
-            const int j0 = (j - k) * 16 + k;
+            if (!ADSP_SKIP(8)) {
+                const int j0 = (j - k) * 16 + k;
 #pragma unroll
-            for (int r = 0; r < 16; r++) buf[addr.at(j0 + r * ns, t)] = e[r];
+                for (int r = 0; r < 16; r++) buf[addr.at(j0 + r * ns, t)] = e[r];
+            }
             gate.sync();
         }
         off += tw_pass_entries(ns);
@@ -297,13 +329,5 @@ __device__ __forceinline__ void cta_fft(cpx<T> (&e)[16], cpx<T> *buf, const Addr
     }
     if (!D_OPEN_OUT) gate.d_end();
 }
-
-// 16-byte / 8-byte asynchronous global -> shared copy (LDGSTS), used to prefetch the spectrum
-template <typename C> __device__ __forceinline__ void cp_async_elem(C *smem_dst, const C *gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    if (sizeof(C) == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
-    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 }  // namespace adsp

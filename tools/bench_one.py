@@ -17,8 +17,11 @@ for _ in range(3): plan.process_device(x.data_ptr(), n, ch, n, y.data_ptr(), ost
 plan.sync()
 iters = 10
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+import time
 e0.record(st)
+th0 = time.perf_counter()
 for _ in range(iters): plan.process_device(x.data_ptr(), n, ch, n, y.data_ptr(), ostr)
+host_ms = (time.perf_counter() - th0) * 1e3 / iters
 e1.record(st); plan.sync(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / iters
 err = ""
@@ -26,4 +29,4 @@ if os.environ.get("BCHECK"):
     from oracle import oracle as O
     ref = O.overlap_save(h, 0, x[ch - 1].cpu().numpy().astype(np.float64))
     err = f" relL2={G.rel_l2(y[ch-1,:ol].cpu().numpy().astype(np.float64), ref):.2e}"
-print(f"{os.environ.get('LABEL',''):45s} {ms:7.3f} ms {ch*ol/ms/1e6:7.1f} Gs/s {plan.internal_geometry()}{err}", flush=True)
+print(f"{os.environ.get('LABEL',''):45s} host-enqueue {host_ms:6.3f} ms | {ms:7.3f} ms {ch*ol/ms/1e6:7.1f} Gs/s {plan.internal_geometry()}{err}", flush=True)

@@ -1,8 +1,6 @@
 #!/bin/bash
-# A/B the CTA-shape build variants on the bench workload
+# A/B build variants on the bench workload: tools/variant_sweep.sh lib1.so lib2.so ...
 cd "$(dirname "$0")/.."
-for lib in libalgodsp_cuda.so libvar_c128.so libvar_r128.so libvar_rc128.so; do
-  for n2 in 4096 2048 1024; do
-    ADSP_LIB_PATH=$PWD/algo_dsp_b200/$lib ADSP_FFT_N2=$n2 BCHECK=1 LABEL="$lib N2=$n2 mixed" python tools/bench_one.py
-  done
+for lib in "$@"; do
+  ADSP_LIB_PATH=$PWD/algo_dsp_b200/$lib BCHECK=1 LABEL="$lib" python tools/bench_one.py | cut -c1-180
 done
