@@ -224,6 +224,12 @@ struct adsp_plan {
     int hist_cur = 0;
     long long hist_len = 0;
     DevBuf blk_in, blk_out;
+    // CUDA-graph cache of whole device-resident calls (same pointers/sizes as a previous call)
+    struct GraphEntry {
+        const void *in; void *out; long long n, channels, in_stride, out_stride;
+        cudaGraphExec_t exec; uint64_t launches; int seen;
+    };
+    std::vector<GraphEntry> graphs;
 };
 
 template <typename T> static std::vector<FftConv<T>> &plan_fc(adsp_plan *p);
@@ -794,6 +800,7 @@ void adsp_plan_destroy(adsp_plan *p) {
     cudaStreamSynchronize(p->ctx->main);
     for (auto &f : p->fc64) f.destroy();
     for (auto &f : p->fc32) f.destroy();
+    for (auto &g : p->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (auto &kv : p->extra64) kv.second.destroy();
     for (auto &kv : p->extra32) kv.second.destroy();
     p->d_kernel.release();
@@ -814,15 +821,65 @@ void adsp_plan_internal_geometry(const adsp_plan *p, int64_t *fft_n, int64_t *n1
     if (parts) *parts = p->ch.parts;
 }
 
+static adsp_status plan_run_device_any(adsp_plan *p, const void *in, int64_t n, int64_t channels, int64_t in_stride,
+                                       void *out, int64_t out_stride) {
+    if (p->prec == ADSP_F64) return plan_run_device<double>(p, (const double *)in, n, channels, in_stride, (double *)out, out_stride);
+    return plan_run_device<float>(p, (const float *)in, n, channels, in_stride, (float *)out, out_stride);
+}
+
 adsp_status adsp_plan_process_device(adsp_plan *p, const void *in, int64_t n, int64_t channels, int64_t in_stride,
                                      void *out, int64_t out_stride) {
     if (!p || p->kind == PLAN_PART) return ADSP_ERR_INVALID_ARG;
     if (n <= 0) return ADSP_ERR_EMPTY_INPUT;
     if (channels <= 0) return ADSP_OK;
     if (!in || !out) return ADSP_ERR_INVALID_ARG;
-    ADSP_CUDA(cudaSetDevice(p->ctx->device));
-    if (p->prec == ADSP_F64) return plan_run_device<double>(p, (const double *)in, n, channels, in_stride, (double *)out, out_stride);
-    return plan_run_device<float>(p, (const float *)in, n, channels, in_stride, (float *)out, out_stride);
+    adsp_ctx *ctx = p->ctx;
+    ADSP_CUDA(cudaSetDevice(ctx->device));
+    // A repeated call (same buffers and sizes) replays a captured CUDA graph of the whole launch
+    // sequence (kernels on the worker streams, fork/join events): ~200 launches become one submission.
+    // First call runs eagerly (allocations, spectra, attributes), second call captures, later calls replay.
+    static const bool use_graphs = env_ll("ADSP_GRAPHS", 1) != 0;
+    if (!use_graphs || ctx->timing) return plan_run_device_any(p, in, n, channels, in_stride, out, out_stride);
+    adsp_plan::GraphEntry *ent = nullptr;
+    for (auto &g : p->graphs)
+        if (g.in == in && g.out == out && g.n == n && g.channels == channels && g.in_stride == in_stride && g.out_stride == out_stride) { ent = &g; break; }
+    if (ent && ent->exec) {
+        ADSP_CUDA(cudaGraphLaunch(ent->exec, ctx->main));
+        count_launch(ctx, (int)ent->launches);
+        return ADSP_OK;
+    }
+    if (!ent) {
+        if (p->graphs.size() >= 8) {   // small cache: drop the oldest
+            if (p->graphs.front().exec) cudaGraphExecDestroy(p->graphs.front().exec);
+            p->graphs.erase(p->graphs.begin());
+        }
+        p->graphs.push_back({in, out, n, channels, in_stride, out_stride, nullptr, 0, 1});
+        return plan_run_device_any(p, in, n, channels, in_stride, out, out_stride);
+    }
+    // second sighting: capture
+    const uint64_t l0 = ctx->launches.load();
+    cudaGraph_t graph = nullptr;
+    ADSP_CUDA(cudaStreamBeginCapture(ctx->main, cudaStreamCaptureModeThreadLocal));
+    adsp_status st = plan_run_device_any(p, in, n, channels, in_stride, out, out_stride);
+    cudaError_t ce = cudaStreamEndCapture(ctx->main, &graph);
+    if (st != ADSP_OK || ce != cudaSuccess || !graph) {
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        ent->seen = 1 << 30;   // do not try again for this shape
+        ent->exec = nullptr;
+        p->graphs.erase(p->graphs.begin() + (ent - p->graphs.data()));
+        return plan_run_device_any(p, in, n, channels, in_stride, out, out_stride);
+    }
+    cudaGraphExec_t exec = nullptr;
+    ce = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) { cudaGetLastError(); return plan_run_device_any(p, in, n, channels, in_stride, out, out_stride); }
+    ent->exec = exec;
+    ent->launches = ctx->launches.load() - l0;
+    ctx->launches.store(l0);
+    ADSP_CUDA(cudaGraphLaunch(ent->exec, ctx->main));
+    count_launch(ctx, (int)ent->launches);
+    return ADSP_OK;
 }
 
 adsp_status adsp_plan_process_batch(adsp_plan *p, const void *in, int64_t n, int64_t channels, int64_t in_stride,

@@ -45,7 +45,8 @@ template <typename T>
 __device__ __forceinline__ BlockIO<T> block_io(const ConvGeom &g, const T *x, T *y, long long bid) {
     BlockIO<T> io;
     if (bid >= g.total_blocks) { io.in = x; io.lo = 0; io.hi = 0; io.out = y; io.cnt = 0; return io; }
-    const long long ch = bid / g.nblk;
+    // total_blocks < 2^31 always (it is a grid dimension): 32-bit division is ~5x cheaper than 64-bit
+    const long long ch = (long long)((unsigned)bid / (unsigned)g.nblk);
     const long long b = bid - ch * g.nblk;
     const long long start = b * g.S - g.D + g.in_shift;
     io.in = x + ch * g.in_stride + start;
