@@ -576,7 +576,12 @@ adsp_status oneshot(adsp_ctx *ctx, OneShot op, const T *a, int64_t n, const T *b
         if (km <= 64) use_direct = true;                     // conv.go:209-211 (code wins over doc: <= 64)
     }
     if (use_direct) ADSP_TRY(direct_device<T>(ctx, sig, sn, 0, ker, km, 0, 1, dout, 0));
-    else ADSP_TRY(fft_convolve_device<T>(ctx, sig, sn, 1, 0, ker, km, dout, 0));
+    else {
+        bool done = false;
+        // long correlations: one packed transform of (a, reverse b) instead of a generic long-kernel convolution
+        if (corr && env_ll("ADSP_CORR_GENERIC", 0) == 0) ADSP_TRY(fft_correlate_pairs_device<T>(ctx, da, n, n, db, m, m, 1, dout, out_len, &done));
+        if (!done) ADSP_TRY(fft_convolve_device<T>(ctx, sig, sn, 1, 0, ker, km, dout, 0));
+    }
     if (post) {
         ADSP_TRY(ctx->d_small.reserve(64));
         T *dden = (T *)ctx->d_small.p;
@@ -714,6 +719,29 @@ template <typename T>
 adsp_status correlate_batch_dev(adsp_ctx *ctx, const T *a, int64_t n, int64_t a_stride, const T *b, int64_t m,
                                 int64_t b_stride, int64_t pairs, T *out, int64_t out_stride, long long *peak_i, T *peak_v) {
     const int64_t out_len = n + m - 1;
+    const bool want_peaks = peak_i && peak_v;
+    // long operands: one packed transform per pair + one shared inverse per two pairs
+    if (std::min(n, m) > 64 && env_ll("ADSP_CORR_GENERIC", 0) == 0) {
+        const int64_t chunk = out ? pairs : std::min<int64_t>(pairs, 16);
+        const int64_t tstride = ((out_len + 31) / 32) * 32;
+        T *tmp = nullptr;
+        if (!out) {
+            ADSP_TRY(ctx->d_tmp.reserve((size_t)chunk * (size_t)tstride * sizeof(T)));
+            tmp = (T *)ctx->d_tmp.p;
+        }
+        bool all_done = true;
+        for (int64_t c0 = 0; c0 < pairs && all_done; c0 += chunk) {
+            const int64_t np = std::min(chunk, pairs - c0);
+            T *o = out ? out + c0 * out_stride : tmp;
+            const int64_t os = out ? out_stride : tstride;
+            bool done = false;
+            ADSP_TRY(fft_correlate_pairs_device<T>(ctx, a + c0 * a_stride, n, a_stride, b + c0 * b_stride, m, b_stride, np, o, os, &done));
+            if (!done) { all_done = false; break; }
+            if (want_peaks) ADSP_TRY(peak_device<T>(ctx, o, out_len, os, np, peak_v + c0, peak_i + c0));
+        }
+        if (all_done) return ADSP_OK;
+    }
+    // generic path: Convolve(a, reverse(b)) per pair (direct for short operands, partitioned FFT beyond 2^22 points)
     ADSP_TRY(ctx->d_tmp.reserve((size_t)(m + (out ? 0 : out_len)) * sizeof(T)));
     T *dbr = (T *)ctx->d_tmp.p;
     T *tmp_out = out ? nullptr : dbr + m;
@@ -727,9 +755,9 @@ adsp_status correlate_batch_dev(adsp_ctx *ctx, const T *a, int64_t n, int64_t a_
         if (m > n) { sig = dbr; sn = m; ker = ap; km = n; }
         if (km <= 64) ADSP_TRY(direct_device<T>(ctx, sig, sn, 0, ker, km, 0, 1, op, 0));
         else ADSP_TRY(fft_convolve_device<T>(ctx, sig, sn, 1, 0, ker, km, op, 0));
-        if (peak_i && peak_v && !out) ADSP_TRY(peak_device<T>(ctx, op, out_len, out_len, 1, peak_v + p, peak_i + p));
+        if (want_peaks && !out) ADSP_TRY(peak_device<T>(ctx, op, out_len, out_len, 1, peak_v + p, peak_i + p));
     }
-    if (peak_i && peak_v && out) ADSP_TRY(peak_device<T>(ctx, out, out_len, out_stride, pairs, peak_v, peak_i));
+    if (want_peaks && out) ADSP_TRY(peak_device<T>(ctx, out, out_len, out_stride, pairs, peak_v, peak_i));
     return ADSP_OK;
 }
 }  // namespace

@@ -361,10 +361,12 @@ fftconv_cols_fwd(ConvGeom g, const T *__restrict__ x, cpx<T> *__restrict__ scrat
                          pair0 + blockIdx.y, blockIdx.x, buf, threadIdx.x, gate, true);
 }
 
-// SPECTRUM mode: forward only, scaled, written to `spec` (IR spectrum construction, once per plan).
-template <typename T, int L, bool SPECTRUM>
+// MODE 0: convolution (FFT, *H, IFFT, in place).  MODE 1: forward only, scaled, written to `spec`
+// (IR spectrum construction once per plan; correlation forward pass with spec == scratch).
+// MODE 2: inverse only, written to `spec` (correlation inverse pass, in place).
+template <typename T, int L, int MODE>
 __global__ void __launch_bounds__(rows_cta_threads(L), rows_min_ctas(L))
-fftconv_rows(cpx<T> *__restrict__ scratch, const cpx<T> *__restrict__ H, cpx<T> *__restrict__ spec, T scale,
+fftconv_rows(cpx<T> *__restrict__ scratch, const cpx<T> *__restrict__ H, cpx<T> *spec, T scale,
              int N1, const cpx<T> *__restrict__ tw) {
     using C = cpx<T>;
     using Sh = FftShape<L>;
@@ -376,7 +378,7 @@ fftconv_rows(cpx<T> *__restrict__ scratch, const cpx<T> *__restrict__ H, cpx<T> 
     load_tw_smem<T, L>(stw, tw, threadIdx.x, rows_cta_threads(L));
     C *pairbase = scratch + (size_t)blockIdx.y * ((size_t)N1 * L);
     CtaGate gate;
-    if (!SPECTRUM) {
+    if (MODE == 0) {
         rows_tile<T, L>(pairbase, H, blockIdx.x, buf, stw, threadIdx.x, gate, true);
         return;
     }
@@ -387,12 +389,14 @@ fftconv_rows(cpx<T> *__restrict__ scratch, const cpx<T> *__restrict__ H, cpx<T> 
     const size_t hoff = k1 * L + j;
     C e[16];
 #pragma unroll
-    for (int q = 0; q < 16; q++) e[q] = pairbase[hoff + q * TPF];
-    cta_fft<T, L, false>(e, buf, addr, stw, j, gate);
+    for (int q = 0; q < 16; q++) e[q] = __ldcg(&pairbase[hoff + q * TPF]);
+    if (MODE == 1) cta_fft<T, L, false>(e, buf, addr, stw, j, gate);
+    else cta_fft<T, L, true>(e, buf, addr, stw, j, gate);
+    C *dst = spec + (size_t)blockIdx.y * ((size_t)N1 * L) + hoff;
 #pragma unroll
     for (int q = 0; q < 16; q++) {
         C v; v.x = e[q].x * scale; v.y = e[q].y * scale;
-        spec[(size_t)blockIdx.y * ((size_t)N1 * L) + hoff + q * TPF] = v;
+        __stcg(&dst[q * TPF], v);
     }
 }
 
@@ -410,6 +414,83 @@ fftconv_cols_inv(ConvGeom g, const cpx<T> *__restrict__ scratch, const T *__rest
     CtaGate gate;
     cols_inv_tile<T, N1>(g, scratch + (size_t)blockIdx.y * ((size_t)N1 * N2), x, y, N2, lgN, stw, tw_hi, tw_lo,
                          pair0 + blockIdx.y, blockIdx.x, buf, threadIdx.x, gate, true);
+}
+
+// ------------------------------------------------------------------------------------------
+// Pairwise FFT correlation (correlate.go:16-28 evaluated as one transform per pair instead of a
+// generic long-kernel convolution): z = a + i*reverse(b) -> Z; for real a, b
+//     FFT(a)*FFT(rev b) = (Z[k]^2 - conj(Z[N-k])^2) / (4i),
+// and two pairs share one inverse transform (Q = P_A + i*P_B, outputs in re / im).
+// corr_cols_fwd: forward column pass of one pair; grid = (N2/TC, pairs).
+template <typename T, int N1>
+__global__ void __launch_bounds__(ColShape<N1>::THREADS, ColShape<N1>::MIN_CTAS)
+corr_cols_fwd(const T *__restrict__ a, long long n, long long a_stride, const T *__restrict__ b, long long m,
+              long long b_stride, cpx<T> *__restrict__ scratch, int N2, int lgN, const cpx<T> *__restrict__ tw,
+              const cpx<T> *__restrict__ tw_hi, const cpx<T> *__restrict__ tw_lo, long long pair0) {
+    using C = cpx<T>;
+    using CS = ColShape<N1>;
+    constexpr int TPF = CS::TPF, TC = CS::TC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C *buf = reinterpret_cast<C *>(smem_raw);
+    C *stw = buf + ((FftShape<N1>::P > 0) ? CS::SMEM_ELEMS : 0);
+    load_tw_smem<T, N1>(stw, tw, threadIdx.x, CS::THREADS);
+    const int c = threadIdx.x % TC;
+    const int j = threadIdx.x / TC;
+    const int n2 = blockIdx.x * TC + c;
+    ColAddr<TC> addr{c};
+    const unsigned maskN = (1u << lgN) - 1u;
+    const C tw_base = twiddle_n<T>(tw_hi, tw_lo, ((unsigned)n2 * (unsigned)j) & maskN);
+    const C tw_rho = twiddle_n<T>(tw_hi, tw_lo, ((unsigned)n2 * (unsigned)TPF) & maskN);
+    const long long pair = pair0 + blockIdx.y;
+    const T *ap = a + pair * a_stride;
+    const T *bp = b + pair * b_stride;
+    C e[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        const long long i = (long long)(j + q * TPF) * N2 + n2;
+        e[q].x = (i < n) ? ld_stream(ap + i) : (T)0;
+        e[q].y = (i < m) ? ld_stream(bp + (m - 1 - i)) : (T)0;   // reverse(b): correlate.go:22-25
+    }
+    CtaGate gate;
+    cta_fft<T, N1, false, false, true>(e, buf, addr, stw, j, gate);
+    apply_geometric16<false>(e, tw_base, tw_rho);
+    C *dst = scratch + (size_t)blockIdx.y * ((size_t)N1 * N2) + n2;
+#pragma unroll
+    for (int r = 0; r < 16; r++) __stcg(&dst[(size_t)(j + r * TPF) * N2], e[r]);
+}
+
+// Spectral product in four-step order, in place: ZA <- P_A + i*P_B (ZB may be null).  Element
+// (k1, k2) holds Z[k1 + N1*k2]; its mirror N-k sits at ((N1-k1)%N1, .).  One thread handles k and N-k.
+template <typename T>
+__global__ void corr_pointwise(cpx<T> *ZA, const cpx<T> *ZB, int N1, int N2, T scale) {
+    using C = cpx<T>;
+    const long long N = (long long)N1 * N2;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N) return;
+    const long long k1 = idx / N2, k2 = idx - k1 * N2;
+    const long long k = k1 + (long long)N1 * k2;
+    const long long km = (N - k) & (N - 1);
+    if (k > km) return;                       // the mirror thread does both
+    const long long m1 = km & (N1 - 1), m2 = km / N1;
+    const long long midx = m1 * N2 + m2;
+    auto prod = [&](C zk, C zm) {             // (zk^2 - conj(zm)^2) / (4i) * scale
+        C r;
+        const T ar = zk.x * zk.x - zk.y * zk.y, ai = 2 * zk.x * zk.y;      // zk^2
+        const T br = zm.x * zm.x - zm.y * zm.y, bi = -2 * zm.x * zm.y;     // conj(zm)^2 = conj(zm^2)
+        const T dr = ar - br, di = ai - bi;                                  // divide by 4i: (dr + i di)/(4i) = (di - i dr)/4
+        r.x = di * (scale * (T)0.25);
+        r.y = -dr * (scale * (T)0.25);
+        return r;
+    };
+    const C pa = prod(__ldcg(&ZA[idx]), __ldcg(&ZA[midx]));
+    C pb; pb.x = 0; pb.y = 0;
+    if (ZB) pb = prod(__ldcg(&ZB[idx]), __ldcg(&ZB[midx]));
+    // Q[k] = pa + i*pb ; Q[N-k] = conj(pa) + i*conj(pb)
+    C qk, qm;
+    qk.x = pa.x - pb.y; qk.y = pa.y + pb.x;
+    qm.x = pa.x + pb.y; qm.y = -pa.y + pb.x;
+    __stcg(&ZA[idx], qk);
+    if (midx != idx) __stcg(&ZA[midx], qm);
 }
 
 #if ADSP_WIDE_TILES

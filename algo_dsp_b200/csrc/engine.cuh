@@ -129,6 +129,10 @@ adsp_status fft_convolve_device(adsp_ctx *ctx, const T *d_x, long long n, long l
                                 const T *d_k, long long K, T *d_y, long long out_stride);
 
 template <typename T>
+adsp_status fft_correlate_pairs_device(adsp_ctx *ctx, const T *a, long long n, long long a_stride, const T *b, long long m,
+                                       long long b_stride, long long pairs, T *out, long long out_stride, bool *done);
+
+template <typename T>
 adsp_status direct_device(adsp_ctx *ctx, const T *d_a, long long n, long long a_stride, const T *d_b, long long m,
                           long long b_stride, long long batch, T *d_out, long long out_stride);
 

@@ -148,7 +148,7 @@ static adsp_status launch_full(adsp_ctx *ctx, cudaStream_t st, int L, const Conv
     }
 }
 
-template <typename T, int L, bool SPEC>
+template <typename T, int L, int SPEC>
 static adsp_status launch_rows_t(adsp_ctx *ctx, cudaStream_t st, cpx<T> *scratch, const cpx<T> *H, cpx<T> *spec,
                                  T scale, int N1, const cpx<T> *tw, int pairs) {
     constexpr int THREADS = rows_cta_threads(L);
@@ -164,7 +164,7 @@ static adsp_status launch_rows_t(adsp_ctx *ctx, cudaStream_t st, cpx<T> *scratch
     return ADSP_OK;
 }
 
-template <typename T, bool SPEC>
+template <typename T, int SPEC>
 static adsp_status launch_rows(adsp_ctx *ctx, cudaStream_t st, int L, cpx<T> *scratch, const cpx<T> *H, cpx<T> *spec,
                                T scale, int N1, const cpx<T> *tw, int pairs) {
     switch (L) {
@@ -544,6 +544,70 @@ adsp_status fft_convolve_device(adsp_ctx *ctx, const T *d_x, long long n, long l
     }
     return ADSP_OK;
 }
+
+// ------------------------------------------------------------------ pairwise FFT correlation
+template <typename T, int N1>
+static adsp_status launch_corr_cols_t(adsp_ctx *ctx, cudaStream_t st, const T *a, long long n, long long a_stride, const T *b,
+                                      long long m, long long b_stride, cpx<T> *scratch, int N2, int lgN, const cpx<T> *tw,
+                                      const cpx<T> *hi, const cpx<T> *lo, long long pair0, int pairs) {
+    using CS = ColShape<N1>;
+    const size_t smem = (FftShape<N1>::P > 0) ? ((size_t)CS::SMEM_ELEMS + FftShape<N1>::TW_ENTRIES) * sizeof(cpx<T>) : 16;
+    static AttrOnce once;
+    if (once.need(ctx->device)) ADSP_TRY(set_smem(corr_cols_fwd<T, N1>, smem));
+    dim3 grid((unsigned)(N2 / CS::TC), (unsigned)pairs);
+    LaunchTimer lt(ctx, st, KK_COLS_FWD);
+    corr_cols_fwd<T, N1><<<grid, CS::THREADS, smem, st>>>(a, n, a_stride, b, m, b_stride, scratch, N2, lgN, tw, hi, lo, pair0);
+    count_launch(ctx);
+    ADSP_CUDA(cudaGetLastError());
+    return ADSP_OK;
+}
+
+// out[p][k] = sum_i a[p][i] * b[p][i - (k - (m-1))], k < n+m-1, for `pairs` pairs (device pointers).
+// Returns *done=false when the shape is outside the transform sizes of this path.
+template <typename T>
+adsp_status fft_correlate_pairs_device(adsp_ctx *ctx, const T *a, long long n, long long a_stride, const T *b, long long m,
+                                       long long b_stride, long long pairs, T *out, long long out_stride, bool *done) {
+    *done = false;
+    const long long out_len = n + m - 1;
+    long long N = 8192;
+    while (N < out_len) N *= 2;
+    if (N > (1LL << 22) || pairs <= 0) return ADSP_OK;
+    FftChoice ch = make_choice(1, N);     // geometry only (N1, N2, lgN)
+    const cpx<T> *tw_rows, *tw_cols, *tw_hi, *tw_lo;
+    ADSP_TRY(get_tw_table<T>(ctx, ch.N2, &tw_rows));
+    ADSP_TRY(get_tw_table<T>(ctx, ch.N1, &tw_cols));
+    ADSP_TRY(get_tw4_tables<T>(ctx, ch.lgN, &tw_hi, &tw_lo));
+    const size_t per_pair = (size_t)N * sizeof(cpx<T>);
+    ADSP_TRY(ctx->scratch.reserve(2 * per_pair));
+    cpx<T> *ZA = (cpx<T> *)ctx->scratch.p, *ZB = ZA + N;
+    ConvGeom g{};                          // output side: block 2q -> pair 2q (re), block 2q+1 -> pair 2q+1 (im)
+    g.n = N; g.out_len = out_len; g.in_stride = 0; g.out_stride = out_stride; g.S = N; g.D = 0;
+    g.total_blocks = pairs; g.in_shift = 0; g.out_shift = 0; g.nblk = 1; g.accumulate = 0;
+    cudaStream_t st = ctx->main;
+    const T scale = (T)(1.0L / (long double)N);
+    for (long long p0 = 0; p0 < pairs; p0 += 2) {
+        const int np = (pairs - p0 >= 2) ? 2 : 1;
+#define ADSP_CORR_COLS(n1) case n1: ADSP_TRY((launch_corr_cols_t<T, n1>(ctx, st, a, n, a_stride, b, m, b_stride, ZA, ch.N2, ch.lgN, tw_cols, tw_hi, tw_lo, p0, np))); break;
+        switch (ch.N1) {
+            ADSP_CORR_COLS(16) ADSP_CORR_COLS(32) ADSP_CORR_COLS(64) ADSP_CORR_COLS(128) ADSP_CORR_COLS(256) ADSP_CORR_COLS(512) ADSP_CORR_COLS(1024)
+        default: set_error("correlate: unsupported transform shape"); return ADSP_ERR_INVALID_ARG;
+        }
+#undef ADSP_CORR_COLS
+        ADSP_TRY((launch_rows<T, 1>(ctx, st, ch.N2, ZA, (const cpx<T> *)nullptr, ZA, (T)1, ch.N1, tw_rows, np)));   // forward rows, in place
+        {
+            LaunchTimer lt(ctx, st, KK_OTHER);
+            corr_pointwise<T><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(ZA, np == 2 ? ZB : (const cpx<T> *)nullptr, ch.N1, ch.N2, scale);
+            count_launch(ctx);
+        }
+        ADSP_TRY((launch_rows<T, 2>(ctx, st, ch.N2, ZA, (const cpx<T> *)nullptr, ZA, (T)1, ch.N1, tw_rows, 1)));     // inverse rows of Q
+        ADSP_TRY(launch_cols<T>(ctx, st, ch.N1, true, g, (const T *)nullptr, out, ZA, ch.N2, ch.lgN, tw_cols, tw_hi, tw_lo, p0 / 2, 1));
+    }
+    ADSP_CUDA(cudaGetLastError());
+    *done = true;
+    return ADSP_OK;
+}
+template adsp_status fft_correlate_pairs_device<ADSP_REAL>(adsp_ctx *, const ADSP_REAL *, long long, long long, const ADSP_REAL *, long long,
+                                                           long long, long long, ADSP_REAL *, long long, bool *);
 
 template struct FftConv<ADSP_REAL>;
 template adsp_status get_tw_table<ADSP_REAL>(adsp_ctx *, int, const cpx<ADSP_REAL> **);
