@@ -254,13 +254,20 @@ def run_ours(args):
         achieved = samples_per_launch * ALGO_BYTES_PER_SAMPLE / (dom_avg_ms * 1e-3) / 1e9
         path_achieved = (channels * OUT_LEN * ALGO_BYTES_PER_SAMPLE) / (ms_step * 1e-3) / 1e9 / 1.0
         kshare = {k: round(v[0], 3) for k, v in ktimes.items() if v[1]}
+        traffic, traffic_note = None, None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            traffic = tr["fftconv_" + dom]["dram_bytes_per_launch"]
+            traffic_note = tr["source"]
+        except Exception:
+            pass
         roof = {
             "bound": "hbm", "kernel": "fftconv_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": peak_src,
+            "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
             "avg_launch_ms": dom_avg_ms, "launches": dom_n, "algorithmic_bytes_per_launch": samples_per_launch * ALGO_BYTES_PER_SAMPLE,
             "kernel_device_ms_over_timed_steps": kshare,
             "path_achieved": path_achieved * 1.0, "path_frac": path_achieved / peak,
-            "co_bound": "fp64 pipe (see DESIGN.md: ~80 DP instr per output sample caps the path below ~45% of HBM peak)",
+            "co_bound": "fp64 pipe and shared-memory pipe (DESIGN.md 3: ~80 DP instr and ~160 B of LSU traffic per output sample cap the path near 45% of HBM peak); ncu: fp64 pipe 39% / LSU 44% in fftconv_rows",
         }
         cpu_threads = os.cpu_count() or 1
         cpu_ch = max(2 * cpu_threads, 8)
