@@ -81,6 +81,8 @@ PROTOTYPES = {
     "adsp_partitioned_latency": (C.c_int, [c_vp]),
     "adsp_partitioned_stage_count": (C.c_int, [c_vp]),
     "adsp_partitioned_stage_info": (C.c_int, [c_vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "adsp_streaming_create": (C.c_int, [c_vp, c_vp, c_i64, c_i64, C.c_int, C.c_int, C.POINTER(c_vp)]),
+    "adsp_streaming_process_block": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64]),
 }
 
 _lib = None

@@ -480,3 +480,58 @@ def NewPartitionedConvolution(kernel, minBlockOrder, maxBlockOrder, ctx=None):
 def NewPartitionedConvolution32(kernel, minBlockOrder, maxBlockOrder, ctx=None):
     """NewPartitionedConvolution32 -- partitioned.go:340."""
     return PartitionedConvolution(kernel, minBlockOrder, maxBlockOrder, ctx, np.float32)
+
+
+class _Streaming(_Plan):
+    """StreamingOverlapAddT / StreamingOverlapSaveT -- streaming_overlap_add.go:20, streaming_overlap_save.go:20."""
+    _ols = 1
+
+    def __init__(self, kernel, blockSize, ctx=None, dtype=np.float64):
+        super().__init__()
+        self._dtype = np.dtype(dtype).type
+        self._ctx_obj = ctx or default_context()
+        k = self._np(kernel)
+        prec = L.F64 if self._dtype == np.float64 else L.F32
+        _check(L.load().adsp_streaming_create(self._ctx_obj.handle, _p(k), k.size, int(blockSize), self._ols, prec, C.byref(self._h)))
+
+    def BlockSize(self):
+        return int(L.load().adsp_plan_block_size(self._h))
+
+    def ProcessBlock(self, input):
+        """ProcessBlock(input) -> output block (both BlockSize() samples); state persists across calls."""
+        x = self._np(input)
+        out = np.empty(max(self.BlockSize(), 1), dtype=self._dtype)
+        _check(L.load().adsp_streaming_process_block(self._h, _p(x), x.size, _p(out), self.BlockSize()))
+        return out[: self.BlockSize()]
+
+    def ProcessBlockTo(self, output, input):
+        x = self._np(input)
+        if not (isinstance(output, np.ndarray) and output.dtype == self._dtype and output.flags.c_contiguous):
+            raise TypeError("output must be a contiguous numpy array of the plan's dtype")
+        _check(L.load().adsp_streaming_process_block(self._h, _p(x), x.size, _p(output), output.size))
+
+
+class StreamingOverlapSave(_Streaming):
+    _ols = 1
+
+
+class StreamingOverlapAdd(_Streaming):
+    _ols = 0
+
+
+def NewStreamingOverlapSave(kernel, blockSize, ctx=None):
+    """NewStreamingOverlapSave -- streaming_overlap_save.go:88."""
+    return StreamingOverlapSave(kernel, blockSize, ctx, np.float64)
+
+
+def NewStreamingOverlapSave32(kernel, blockSize, ctx=None):
+    return StreamingOverlapSave(kernel, blockSize, ctx, np.float32)
+
+
+def NewStreamingOverlapAdd(kernel, blockSize, ctx=None):
+    """NewStreamingOverlapAdd -- streaming_overlap_add.go:88."""
+    return StreamingOverlapAdd(kernel, blockSize, ctx, np.float64)
+
+
+def NewStreamingOverlapAdd32(kernel, blockSize, ctx=None):
+    return StreamingOverlapAdd(kernel, blockSize, ctx, np.float32)

@@ -201,7 +201,7 @@ static adsp_status copy2d(adsp_ctx *ctx, void *dst, size_t dpitch, const void *s
 using namespace adsp;
 
 // ================================================================ plans
-enum PlanKind { PLAN_OLS = 0, PLAN_OLA = 1, PLAN_PART = 2 };
+enum PlanKind { PLAN_OLS = 0, PLAN_OLA = 1, PLAN_PART = 2, PLAN_STREAM = 3 };
 
 struct PartStage { int part_size; int count; int start_pos; };
 
@@ -857,7 +857,7 @@ static adsp_status plan_run_device_any(adsp_plan *p, const void *in, int64_t n, 
 
 adsp_status adsp_plan_process_device(adsp_plan *p, const void *in, int64_t n, int64_t channels, int64_t in_stride,
                                      void *out, int64_t out_stride) {
-    if (!p || p->kind == PLAN_PART) return ADSP_ERR_INVALID_ARG;
+    if (!p || p->kind == PLAN_PART || p->kind == PLAN_STREAM) return ADSP_ERR_INVALID_ARG;
     if (n <= 0) return ADSP_ERR_EMPTY_INPUT;
     if (channels <= 0) return ADSP_OK;
     if (!in || !out) return ADSP_ERR_INVALID_ARG;
@@ -912,7 +912,7 @@ adsp_status adsp_plan_process_device(adsp_plan *p, const void *in, int64_t n, in
 
 adsp_status adsp_plan_process_batch(adsp_plan *p, const void *in, int64_t n, int64_t channels, int64_t in_stride,
                                     void *out, int64_t out_stride) {
-    if (!p || p->kind == PLAN_PART) return ADSP_ERR_INVALID_ARG;
+    if (!p || p->kind == PLAN_PART || p->kind == PLAN_STREAM) return ADSP_ERR_INVALID_ARG;
     if (n <= 0) return ADSP_ERR_EMPTY_INPUT;        // overlap_save.go:127-129
     if (channels <= 0) return ADSP_OK;
     if (!in || !out) return ADSP_ERR_INVALID_ARG;
@@ -1051,13 +1051,66 @@ adsp_status adsp_partitioned_process_block(adsp_plan *p, const void *in, int64_t
 
 void adsp_plan_reset(adsp_plan *p) {
     if (!p) return;
-    if (p->kind == PLAN_PART) {                                              // partitioned.go:399-407
+    if (p->kind == PLAN_PART || p->kind == PLAN_STREAM) {                    // partitioned.go:399-407, streaming_overlap_save.go:167-169
         cudaSetDevice(p->ctx->device);
         const size_t es = p->prec == ADSP_F64 ? 8 : 4;
         for (int i = 0; i < 2; i++) cudaMemsetAsync(p->hist[i].p, 0, (size_t)p->hist_len * es, p->ctx->main);
         cudaStreamSynchronize(p->ctx->main);
     }
     // OverlapSave/OverlapAdd keep no state across Process calls (overlap_save.go:136-138, overlap_add.go:185-187)
+}
+
+// ---------------------------------------------------------------- fixed-block streaming convolvers
+// NewStreamingOverlapAdd / NewStreamingOverlapSave (streaming_overlap_add.go:41, streaming_overlap_save.go:44):
+// ProcessBlock(input[blockSize]) -> output[blockSize], state carried across calls, no latency.  Both
+// algorithms produce the same stream (streaming_test.go:122-176), so one device engine serves both:
+// the partitioned engine with latency 0 (history = last K-1 input samples on the device).
+static adsp_status stream_create(adsp_ctx *ctx, const void *kernel, int64_t K, int64_t block_size, adsp_precision prec, adsp_plan **out) {
+    if (!out) return ADSP_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (!ctx) return ADSP_ERR_INVALID_ARG;
+    if (K <= 0 || !kernel) return ADSP_ERR_EMPTY_KERNEL;
+    if (block_size <= 0) { set_error("conv: blockSize must be positive, got " + std::to_string(block_size)); return ADSP_ERR_INVALID_ARG; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ADSP_CUDA(cudaSetDevice(ctx->device));
+    adsp_plan *p = new adsp_plan();
+    p->ctx = ctx; p->kind = PLAN_STREAM; p->prec = prec; p->K = K;
+    p->latency = 0;
+    p->ref_block = block_size;
+    p->ref_fft = adsp_next_pow2(block_size + K - 1);          // streaming_overlap_save.go:57-58
+    p->hist_len = K - 1;
+    const size_t es = prec == ADSP_F64 ? 8 : 4;
+    adsp_status st = prec == ADSP_F64 ? plan_build<double>(p, (const double *)kernel) : plan_build<float>(p, (const float *)kernel);
+    for (int i = 0; i < 2 && st == ADSP_OK; i++) {
+        st = p->hist[i].reserve((size_t)std::max<long long>(p->hist_len, 1) * es);
+        if (st == ADSP_OK && cudaMemsetAsync(p->hist[i].p, 0, (size_t)std::max<long long>(p->hist_len, 1) * es, ctx->main) != cudaSuccess) st = ADSP_ERR_CUDA;
+    }
+    if (st != ADSP_OK) { adsp_plan_destroy(p); return st; }
+    *out = p;
+    return ADSP_OK;
+}
+
+adsp_status adsp_streaming_create(adsp_ctx *ctx, const void *kernel, int64_t K, int64_t block_size, int overlap_save,
+                                  adsp_precision prec, adsp_plan **out) {
+    (void)overlap_save;   // same results either way; kept so the binding can mirror both constructors
+    return stream_create(ctx, kernel, K, block_size, prec, out);
+}
+
+adsp_status adsp_streaming_process_block(adsp_plan *p, const void *in, int64_t n, void *out, int64_t n_out) {
+    if (!p || p->kind != PLAN_STREAM) return ADSP_ERR_INVALID_ARG;
+    if (n != p->ref_block) {                                   // streaming_overlap_save.go:139-141
+        set_error("conv: buffer length mismatch: expected " + std::to_string(p->ref_block) + " samples, got " + std::to_string(n));
+        return ADSP_ERR_LENGTH_MISMATCH;
+    }
+    if (n_out != p->ref_block) {                               // streaming_overlap_save.go:156-158
+        set_error("conv: buffer length mismatch: expected " + std::to_string(p->ref_block) + " output samples, got " + std::to_string(n_out));
+        return ADSP_ERR_LENGTH_MISMATCH;
+    }
+    if (!in || !out) return ADSP_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(p->ctx->mu);
+    ADSP_CUDA(cudaSetDevice(p->ctx->device));
+    if (p->prec == ADSP_F64) return part_process<double>(p, (const double *)in, n, (double *)out);
+    return part_process<float>(p, (const float *)in, n, (float *)out);
 }
 
 int adsp_partitioned_latency(const adsp_plan *p) { return p ? p->latency : 0; }

@@ -349,7 +349,7 @@ template <typename T, int N1>
 __global__ void __launch_bounds__(ColShape<N1>::THREADS, ColShape<N1>::MIN_CTAS)
 fftconv_cols_fwd(ConvGeom g, const T *__restrict__ x, cpx<T> *__restrict__ scratch, int N2, int lgN,
                  const cpx<T> *__restrict__ tw, const cpx<T> *__restrict__ tw_hi,
-                 const cpx<T> *__restrict__ tw_lo, long long pair0) {
+                 const cpx<T> *__restrict__ tw_lo, long long pair0, int ntiles) {
     using C = cpx<T>;
     using CS = ColShape<N1>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -357,8 +357,13 @@ fftconv_cols_fwd(ConvGeom g, const T *__restrict__ x, cpx<T> *__restrict__ scrat
     C *stw = buf + ((FftShape<N1>::P > 0) ? CS::SMEM_ELEMS : 0);
     load_tw_smem<T, N1>(stw, tw, threadIdx.x, CS::THREADS);
     CtaGate gate;
-    cols_fwd_tile<T, N1>(g, x, scratch + (size_t)blockIdx.y * ((size_t)N1 * N2), N2, lgN, stw, tw_hi, tw_lo,
-                         pair0 + blockIdx.y, blockIdx.x, buf, threadIdx.x, gate, true);
+    // 1-D grid; a CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (table copy and prologue amortised)
+    const int tiles_per_pair = N2 / CS::TC;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int pl = t / tiles_per_pair, tile = t - pl * tiles_per_pair;
+        cols_fwd_tile<T, N1>(g, x, scratch + (size_t)pl * ((size_t)N1 * N2), N2, lgN, stw, tw_hi, tw_lo, pair0 + pl, tile, buf,
+                             threadIdx.x, gate, true);
+    }
 }
 
 // MODE 0: convolution (FFT, *H, IFFT, in place).  MODE 1: forward only, scaled, written to `spec`
@@ -367,7 +372,7 @@ fftconv_cols_fwd(ConvGeom g, const T *__restrict__ x, cpx<T> *__restrict__ scrat
 template <typename T, int L, int MODE>
 __global__ void __launch_bounds__(rows_cta_threads(L), rows_min_ctas(L))
 fftconv_rows(cpx<T> *__restrict__ scratch, const cpx<T> *__restrict__ H, cpx<T> *spec, T scale,
-             int N1, const cpx<T> *__restrict__ tw) {
+             int N1, const cpx<T> *__restrict__ tw, int ntiles) {
     using C = cpx<T>;
     using Sh = FftShape<L>;
     constexpr int TPF = Sh::TPF;
@@ -376,12 +381,16 @@ fftconv_rows(cpx<T> *__restrict__ scratch, const cpx<T> *__restrict__ H, cpx<T> 
     C *buf = reinterpret_cast<C *>(smem_raw);
     C *stw = buf + ROWS * L;
     load_tw_smem<T, L>(stw, tw, threadIdx.x, rows_cta_threads(L));
-    C *pairbase = scratch + (size_t)blockIdx.y * ((size_t)N1 * L);
     CtaGate gate;
-    if (MODE == 0) {
-        rows_tile<T, L>(pairbase, H, blockIdx.x, buf, stw, threadIdx.x, gate, true);
+    if (MODE == 0) {   // 1-D grid over flattened (pair, row tile); a CTA walks tiles with stride gridDim.x
+        const int tiles_per_pair = N1 / ROWS;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            const int pl = t / tiles_per_pair, tile = t - pl * tiles_per_pair;
+            rows_tile<T, L>(scratch + (size_t)pl * ((size_t)N1 * L), H, tile, buf, stw, threadIdx.x, gate, true);
+        }
         return;
     }
+    C *pairbase = scratch + (size_t)blockIdx.y * ((size_t)N1 * L);
     const int row = threadIdx.x / TPF;
     const int j = threadIdx.x % TPF;
     const size_t k1 = (size_t)blockIdx.x * ROWS + row;
@@ -404,7 +413,7 @@ template <typename T, int N1>
 __global__ void __launch_bounds__(ColShape<N1>::THREADS, ColShape<N1>::MIN_CTAS)
 fftconv_cols_inv(ConvGeom g, const cpx<T> *__restrict__ scratch, const T *__restrict__ x, T *__restrict__ y,
                  int N2, int lgN, const cpx<T> *__restrict__ tw, const cpx<T> *__restrict__ tw_hi,
-                 const cpx<T> *__restrict__ tw_lo, long long pair0) {
+                 const cpx<T> *__restrict__ tw_lo, long long pair0, int ntiles) {
     using C = cpx<T>;
     using CS = ColShape<N1>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -412,8 +421,12 @@ fftconv_cols_inv(ConvGeom g, const cpx<T> *__restrict__ scratch, const T *__rest
     C *stw = buf + ((FftShape<N1>::P > 0) ? CS::SMEM_ELEMS : 0);
     load_tw_smem<T, N1>(stw, tw, threadIdx.x, CS::THREADS);
     CtaGate gate;
-    cols_inv_tile<T, N1>(g, scratch + (size_t)blockIdx.y * ((size_t)N1 * N2), x, y, N2, lgN, stw, tw_hi, tw_lo,
-                         pair0 + blockIdx.y, blockIdx.x, buf, threadIdx.x, gate, true);
+    const int tiles_per_pair = N2 / CS::TC;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int pl = t / tiles_per_pair, tile = t - pl * tiles_per_pair;
+        cols_inv_tile<T, N1>(g, scratch + (size_t)pl * ((size_t)N1 * N2), x, y, N2, lgN, stw, tw_hi, tw_lo, pair0 + pl, tile, buf,
+                             threadIdx.x, gate, true);
+    }
 }
 
 // ------------------------------------------------------------------------------------------

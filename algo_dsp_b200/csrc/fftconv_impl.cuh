@@ -113,6 +113,17 @@ template <typename K> static adsp_status set_smem(K kern, size_t bytes) {
     if (bytes > 48 * 1024) ADSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     return ADSP_OK;
 }
+// Grid for the flattened tile loops: one CTA per tile by default (the hardware block scheduler balances
+// them); ADSP_TILES_PER_CTA = k > 1 makes CTAs walk k tiles (but never fewer CTAs than fill the machine).
+static int persistent_grid(adsp_ctx *ctx, int ntiles, int ctas_per_sm) {
+    const long long k = env_ll("ADSP_TILES_PER_CTA", 1);
+    if (k <= 1) return ntiles;
+    const long long resident = (long long)ctx->sm_count * ctas_per_sm;
+    long long grid = (ntiles + k - 1) / k;
+    if (grid < resident) grid = std::min<long long>(resident, ntiles);
+    return (int)grid;
+}
+
 // the opt-in shared-memory attribute is per (function, device): remember it per device
 struct AttrOnce {
     bool done[64] = {};
@@ -156,9 +167,15 @@ static adsp_status launch_rows_t(adsp_ctx *ctx, cudaStream_t st, cpx<T> *scratch
     const size_t smem = ((size_t)ROWS * L + FftShape<L>::TW_ENTRIES) * sizeof(cpx<T>);
     static AttrOnce once;
     if (once.need(ctx->device)) ADSP_TRY(set_smem(fftconv_rows<T, L, SPEC>, smem));
-    dim3 grid((unsigned)(N1 / ROWS > 0 ? N1 / ROWS : 1), (unsigned)pairs);
+    const int tiles_per_pair = (N1 / ROWS > 0 ? N1 / ROWS : 1);
+    dim3 grid((unsigned)tiles_per_pair, (unsigned)pairs);
+    int ntiles = 0;
+    if (SPEC == 0) {   // convolution mode: flattened 1-D grid, optionally persistent (ADSP_TILES_PER_CTA > 1)
+        ntiles = tiles_per_pair * pairs;
+        grid = dim3((unsigned)persistent_grid(ctx, ntiles, rows_min_ctas(L)), 1);
+    }
     LaunchTimer lt(ctx, st, KK_ROWS);
-    fftconv_rows<T, L, SPEC><<<grid, THREADS, smem, st>>>(scratch, H, spec, scale, N1, tw);
+    fftconv_rows<T, L, SPEC><<<grid, THREADS, smem, st>>>(scratch, H, spec, scale, N1, tw, ntiles);
     count_launch(ctx);
     ADSP_CUDA(cudaGetLastError());
     return ADSP_OK;
@@ -188,12 +205,13 @@ static adsp_status launch_cols_t(adsp_ctx *ctx, cudaStream_t st, bool inverse, c
         ADSP_TRY(set_smem(fftconv_cols_fwd<T, N1>, smem));
         ADSP_TRY(set_smem(fftconv_cols_inv<T, N1>, smem));
     }
-    dim3 grid((unsigned)(N2 / CS::TC), (unsigned)pairs);
+    const int ntiles = (N2 / CS::TC) * pairs;
+    const unsigned grid = (unsigned)persistent_grid(ctx, ntiles, CS::MIN_CTAS);
     LaunchTimer lt(ctx, st, inverse ? KK_COLS_INV : KK_COLS_FWD);
     if (!inverse)
-        fftconv_cols_fwd<T, N1><<<grid, CS::THREADS, smem, st>>>(g, x, scratch, N2, lgN, tw, hi, lo, pair0);
+        fftconv_cols_fwd<T, N1><<<grid, CS::THREADS, smem, st>>>(g, x, scratch, N2, lgN, tw, hi, lo, pair0, ntiles);
     else
-        fftconv_cols_inv<T, N1><<<grid, CS::THREADS, smem, st>>>(g, scratch, x, y, N2, lgN, tw, hi, lo, pair0);
+        fftconv_cols_inv<T, N1><<<grid, CS::THREADS, smem, st>>>(g, scratch, x, y, N2, lgN, tw, hi, lo, pair0, ntiles);
     count_launch(ctx);
     ADSP_CUDA(cudaGetLastError());
     return ADSP_OK;

@@ -171,6 +171,16 @@ ADSP_API int adsp_partitioned_latency(const adsp_plan *plan);      /* partitione
 ADSP_API int adsp_partitioned_stage_count(const adsp_plan *plan);  /* partitioned.go:420 */
 ADSP_API adsp_status adsp_partitioned_stage_info(const adsp_plan *plan, int index, int *part_size, int *block_count); /* :426 */
 
+/* ---------------------------------------------------------------- fixed-block streaming convolvers
+ * NewStreamingOverlapAdd(kernel, blockSize) streaming_overlap_add.go:41 / NewStreamingOverlapSave
+ * streaming_overlap_save.go:44 (+ the float32 twins): ProcessBlock(input[blockSize]) -> output[blockSize],
+ * state carried across calls; wrong input or output length -> ErrLengthMismatch; blockSize <= 0 ->
+ * ADSP_ERR_INVALID_ARG.  adsp_plan_block_size / adsp_plan_fft_size / adsp_plan_kernel_len /
+ * adsp_plan_reset serve as BlockSize() / FFTSize() / KernelLen() / Reset(). */
+ADSP_API adsp_status adsp_streaming_create(adsp_ctx *, const void *kernel, int64_t kernel_len, int64_t block_size,
+                                           int overlap_save, adsp_precision prec, adsp_plan **out);
+ADSP_API adsp_status adsp_streaming_process_block(adsp_plan *plan, const void *in, int64_t n, void *out, int64_t n_out);
+
 #ifdef __cplusplus
 }
 #endif
