@@ -430,6 +430,62 @@ fftconv_cols_inv(ConvGeom g, const cpx<T> *__restrict__ scratch, const T *__rest
 }
 
 // ------------------------------------------------------------------------------------------
+// Stage-merged kernel: ONE launch carries the row tiles of group t-1, the forward-column tiles of group
+// t and the inverse-column tiles of group t-2 (three different scratch slots).  The dependencies between
+// the three phases of a group are then plain stream order between consecutive launches, the number of
+// launches per call drops 3x (an empty 768-CTA kernel costs ~5 us on B200: tools/ubench/launch.cu), and
+// FP64-heavy row tiles share the SMs with the memory-heavy column tiles of the neighbouring groups --
+// scheduled by the hardware block scheduler, not by software tickets.
+struct StageArgs {
+    ConvGeom g;
+    long long pair0_r, pair0_cf, pair0_ci;   // first block pair of each group
+    int n_r, n_cf, n_ci;                     // tiles of each kind in this launch (rows first: longest tasks)
+    int N2, lgN;
+};
+
+#if (ADSP_COLS_CTA_THREADS == 128 && ADSP_ROWS_SMALL_CTA)
+template <typename T, int N1, int L>
+__global__ void __launch_bounds__(128, ADSP_MIN_CTAS_128)
+fftconv_stages(StageArgs a, const T *__restrict__ x, T *__restrict__ y, cpx<T> *scratch_r, cpx<T> *scratch_cf,
+               const cpx<T> *scratch_ci, const cpx<T> *__restrict__ H, const cpx<T> *__restrict__ tw_rows,
+               const cpx<T> *__restrict__ tw_cols, const cpx<T> *__restrict__ tw_hi, const cpx<T> *__restrict__ tw_lo) {
+    using C = cpx<T>;
+    using CS = ColShape<N1>;
+    static_assert(CS::THREADS == 128 && rows_cta_threads(L) == 128, "stage-merged kernel uses 128-thread tiles");
+    constexpr int ROWS = 128 / FftShape<L>::TPF;
+    constexpr int BUF_ELEMS = (ROWS * L > CS::SMEM_ELEMS) ? ROWS * L : CS::SMEM_ELEMS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C *buf = reinterpret_cast<C *>(smem_raw);
+    C *stw = buf + BUF_ELEMS;
+    CtaGate gate;
+    const size_t pair_elems = (size_t)N1 * L;
+    int t = blockIdx.x;
+    if (t < a.n_r) {
+        load_tw_smem<T, L>(stw, tw_rows, threadIdx.x, 128);
+        constexpr int tiles_per_pair = N1 / ROWS;
+        const int pl = t / tiles_per_pair, tile = t - pl * tiles_per_pair;
+        rows_tile<T, L>(scratch_r + (size_t)pl * pair_elems, H, tile, buf, stw, threadIdx.x, gate, true);
+        return;
+    }
+    t -= a.n_r;
+    load_tw_smem<T, N1>(stw, tw_cols, threadIdx.x, 128);
+    constexpr int tiles_per_pair = L / CS::TC;
+    if (t < a.n_cf) {
+        const int pl = t / tiles_per_pair, tile = t - pl * tiles_per_pair;
+        cols_fwd_tile<T, N1>(a.g, x, scratch_cf + (size_t)pl * pair_elems, a.N2, a.lgN, stw, tw_hi, tw_lo, a.pair0_cf + pl, tile,
+                             buf, threadIdx.x, gate, true);
+        return;
+    }
+    t -= a.n_cf;
+    {
+        const int pl = t / tiles_per_pair, tile = t - pl * tiles_per_pair;
+        cols_inv_tile<T, N1>(a.g, scratch_ci + (size_t)pl * pair_elems, x, y, a.N2, a.lgN, stw, tw_hi, tw_lo, a.pair0_ci + pl, tile,
+                             buf, threadIdx.x, gate, true);
+    }
+}
+#endif
+
+// ------------------------------------------------------------------------------------------
 // Pairwise FFT correlation (correlate.go:16-28 evaluated as one transform per pair instead of a
 // generic long-kernel convolution): z = a + i*reverse(b) -> Z; for real a, b
 //     FFT(a)*FFT(rev b) = (Z[k]^2 - conj(Z[N-k])^2) / (4i),
