@@ -16,6 +16,30 @@ constexpr int DIRECT_RO = 8;
 constexpr int DIRECT_TILE = DIRECT_THREADS * DIRECT_RO;  // outputs per CTA
 constexpr int DIRECT_MC = 64;                            // taps per staged chunk
 
+// taps of one staged chunk, highest first; `sa` is the padded signal tile, `sb` the taps
+template <typename T, bool FUSED, bool GUARD>
+__device__ __forceinline__ void direct_chunk(T (&acc)[DIRECT_RO], const T *sa, const T *sb, int base, int lim) {
+#define ADSP_SA(i) sa[(i) + ((i) >> 3)]
+    T w[DIRECT_RO];
+#pragma unroll
+    for (int r = 0; r < DIRECT_RO - 1; r++) w[r + 1] = ADSP_SA(base + r);
+#pragma unroll
+    for (int jj = DIRECT_MC - 1; jj >= 0; jj--) {
+#pragma unroll
+        for (int r = 0; r < DIRECT_RO - 1; r++) w[r] = w[r + 1];
+        w[DIRECT_RO - 1] = ADSP_SA(base + DIRECT_RO - 1 + (DIRECT_MC - 1) - jj);
+        if (GUARD && jj >= lim) continue;
+        const T bj = sb[jj];
+#pragma unroll
+        for (int r = 0; r < DIRECT_RO; r++) {
+            if (FUSED) acc[r] = fma(w[r], bj, acc[r]);
+            else if (sizeof(T) == 8) acc[r] = __dadd_rn((double)acc[r], __dmul_rn((double)w[r], (double)bj));   // two roundings, as Go on amd64
+            else acc[r] = __fadd_rn((float)acc[r], __fmul_rn((float)w[r], (float)bj));
+        }
+    }
+#undef ADSP_SA
+}
+
 template <typename T, bool FUSED>
 __global__ void __launch_bounds__(DIRECT_THREADS)
 direct_conv_kernel(const T *__restrict__ a, long long n, long long a_stride,
@@ -52,26 +76,13 @@ direct_conv_kernel(const T *__restrict__ a, long long n, long long a_stride,
         __syncthreads();
         // thread's outputs k = k0 + t*RO + r ; for tap j = j0 + jj the sample is
         // a[k - j] = sa[(k - j) - abase] = sa[t*RO + r + (MC-1) - jj]
-        T w[DIRECT_RO];
         const int base = t * DIRECT_RO;
-#pragma unroll
-        for (int r = 0; r < DIRECT_RO - 1; r++) w[r + 1] = ADSP_SA(base + r);  // jj = MC-1 window, shifted by one
-#pragma unroll
-        for (int jj = DIRECT_MC - 1; jj >= 0; jj--) {
-#pragma unroll
-            for (int r = 0; r < DIRECT_RO - 1; r++) w[r] = w[r + 1];
-            w[DIRECT_RO - 1] = ADSP_SA(base + DIRECT_RO - 1 + (DIRECT_MC - 1) - jj);
-            const T bj = sb[jj];
-#pragma unroll
-            for (int r = 0; r < DIRECT_RO; r++) {
-                if (FUSED) acc[r] = fma(w[r], bj, acc[r]);
-                else {
-                    // two roundings, as Go on amd64 (mul then add)
-                    if (sizeof(T) == 8) acc[r] = __dadd_rn((double)acc[r], __dmul_rn((double)w[r], (double)bj));
-                    else acc[r] = __fadd_rn((float)acc[r], __fmul_rn((float)w[r], (float)bj));
-                }
-            }
-        }
+        const int lim = (int)((m - j0 < DIRECT_MC) ? (m - j0) : DIRECT_MC);   // taps of this chunk that exist
+        // Full chunks run branch free; a partial chunk skips its padded taps (not "multiplies by zero"):
+        // the reference never forms those products, so a NaN/Inf sample must only reach the outputs
+        // its real taps touch.
+        if (lim == DIRECT_MC) direct_chunk<T, FUSED, false>(acc, sa, sb, base, lim);
+        else direct_chunk<T, FUSED, true>(acc, sa, sb, base, lim);
     }
     T *oc = out + ch * out_stride;
 #pragma unroll
