@@ -12,14 +12,18 @@ namespace adsp {
 // CTA = 128 threads, each thread produces RO consecutive outputs from a register window;
 // the signal tile and the tap chunk are staged in shared memory.
 constexpr int DIRECT_THREADS = 128;
-constexpr int DIRECT_RO = 8;
+#ifndef ADSP_DIRECT_RO
+#define ADSP_DIRECT_RO 8
+#endif
+constexpr int DIRECT_RO = ADSP_DIRECT_RO;
+constexpr int DIRECT_PAD_SHIFT = (DIRECT_RO == 16) ? 4 : 3;   // one pad word per RO samples: per-thread windows hit distinct banks
 constexpr int DIRECT_TILE = DIRECT_THREADS * DIRECT_RO;  // outputs per CTA
 constexpr int DIRECT_MC = 64;                            // taps per staged chunk
 
 // taps of one staged chunk, highest first; `sa` is the padded signal tile, `sb` the taps
 template <typename T, bool FUSED, bool GUARD>
 __device__ __forceinline__ void direct_chunk(T (&acc)[DIRECT_RO], const T *sa, const T *sb, int base, int lim) {
-#define ADSP_SA(i) sa[(i) + ((i) >> 3)]
+#define ADSP_SA(i) sa[(i) + ((i) >> DIRECT_PAD_SHIFT)]
     T w[DIRECT_RO];
 #pragma unroll
     for (int r = 0; r < DIRECT_RO - 1; r++) w[r + 1] = ADSP_SA(base + r);
@@ -46,9 +50,9 @@ direct_conv_kernel(const T *__restrict__ a, long long n, long long a_stride,
                    const T *__restrict__ b, long long m, long long b_stride,
                    T *__restrict__ out, long long out_stride, long long tiles_per_ch) {
     // padded by one word per 8 so that the per-thread windows (stride RO=8) hit distinct banks
-    __shared__ T sa[(DIRECT_TILE + DIRECT_MC) + ((DIRECT_TILE + DIRECT_MC) >> 3) + 1];
+    __shared__ T sa[(DIRECT_TILE + DIRECT_MC) + ((DIRECT_TILE + DIRECT_MC) >> DIRECT_PAD_SHIFT) + 1];
     __shared__ T sb[DIRECT_MC];
-#define ADSP_SA(i) sa[(i) + ((i) >> 3)]
+#define ADSP_SA(i) sa[(i) + ((i) >> DIRECT_PAD_SHIFT)]
     const long long ch = blockIdx.x / tiles_per_ch;
     const long long tile = blockIdx.x - ch * tiles_per_ch;
     const long long k0 = tile * DIRECT_TILE;
