@@ -59,6 +59,19 @@ long long env_ll(const char *name, long long dflt) {
 // larger transform than the reference's nextPow2(2K): a longer block wastes less of each
 // transform on the K-1 discarded samples.
 // geometry for a given transform length N and (partition) kernel length Kp
+static int odd_part(long long N) { while (N > 1 && (N & 1) == 0) N >>= 1; return (int)N; }
+
+// transform lengths the engine has kernels for: powers of two 256 .. 2^22, and P * 2^k with P in {3,5,7,9}
+// as (16*P) x N2 four-step transforms, N2 = 256 .. 4096 (conv_kernels_mr.cuh)
+bool fft_size_supported(long long N) {
+    if (N < 256) return false;
+    const int P = odd_part(N);
+    if (P == 1) return N <= (1LL << 22);
+    if (P != 3 && P != 5 && P != 7 && P != 9) return false;
+    const long long n2 = N / (16 * P);
+    return n2 >= 256 && n2 <= 4096;
+}
+
 FftChoice make_choice(long long Kp, long long N) {
     FftChoice c;
     c.part_len = Kp;
@@ -66,7 +79,9 @@ FftChoice make_choice(long long Kp, long long N) {
     int lg = 0;
     while ((1LL << lg) < N) lg++;
     c.lgN = lg;
-    if (N <= 4096) { c.N1 = 1; c.N2 = (int)N; }
+    c.P = odd_part(N);
+    if (c.P > 1) { c.N1 = 16 * c.P; c.N2 = (int)(N / c.N1); c.lgN = 0; }
+    else if (N <= 4096) { c.N1 = 1; c.N2 = (int)N; }
     else {
         // rows of 2048 points run as 128-thread CTAs (4 per SM); 2^20-point transforms keep 4096-point
         // rows so that the column transforms stay at N1 = 256
@@ -104,37 +119,73 @@ FftChoice choose_fft(long long K) {
     return c;
 }
 
-// Cover `out_len` output samples with overlap-save blocks of mixed transform lengths: full blocks of
-// the largest length, then the cheapest one or two smaller transforms for the remainder (a 96k-tap
-// IR on a 480k-sample signal needs 2^19 + 2^18 points per channel instead of 2^20).
-struct Segment { long long N; long long off; long long len; };
+struct Segment { long long N; long long off; long long len; bool no_discard; };
+
+// relative cost of one transform of length N (points x passes; the mixed-radix column kernels idle some lanes)
+static double fft_cost(long long N) {
+    int lg = 0;
+    while ((1LL << lg) < N) lg++;
+    return (double)N * (lg + 4) * (odd_part(N) > 1 ? 1.1 : 1.0);
+}
+
+// Cover `out_len` output samples of a K-tap convolution.  Two shapes compete on cost:
+//  (A) overlap-save: full blocks of the plan's largest transform, then the cheapest one or two smaller
+//      transforms for the remainder (a 96k-tap IR on a 480k-sample signal: 2^19 + 2^18 instead of 2^20);
+//  (B) when the whole result fits one transform: a single zero-padded block, nothing discarded
+//      (the same signal: 9 * 2^16 = 589 824 points).
 static std::vector<Segment> plan_segments(long long out_len, long long K, const FftChoice &big) {
     std::vector<Segment> segs;
     const long long full = out_len / big.S;
-    long long rem = out_len - full * big.S;
-    if (full > 0) segs.push_back({big.N, 0, full * big.S});
-    if (rem <= 0) return segs;
-    if (env_ll("ADSP_FFT_N", 0) > 0 || env_ll("ADSP_NO_MIXED", 0) > 0) { segs.push_back({big.N, full * big.S, rem}); return segs; }
-    long long nmin = next_pow2_ll(2 * K);
-    if (nmin < 256) nmin = 256;
-    auto cost = [](long long N) { int lg = 0; while ((1LL << lg) < N) lg++; return (double)N * (lg + 4); };
-    double best = cost(big.N);
-    long long ba = big.N, bb = 0;
-    for (long long Na = big.N; Na >= nmin; Na >>= 1) {
-        const long long Sa = make_choice(K, Na).S;
-        if (Sa <= 0) break;
-        if (Sa >= rem) { if (cost(Na) < best) { best = cost(Na); ba = Na; bb = 0; } continue; }
-        for (long long Nb = Na; Nb >= nmin; Nb >>= 1) {
-            const long long Sb = make_choice(K, Nb).S;
-            if (Sb <= 0 || Sa + Sb < rem) break;
-            if (cost(Na) + cost(Nb) < best) { best = cost(Na) + cost(Nb); ba = Na; bb = Nb; }
-        }
+    const long long rem = out_len - full * big.S;
+    const bool mixed = env_ll("ADSP_FFT_N", 0) <= 0 && env_ll("ADSP_NO_MIXED", 0) <= 0;
+    if (!mixed) {
+        if (full > 0) segs.push_back({big.N, 0, full * big.S, false});
+        if (rem > 0) segs.push_back({big.N, full * big.S, rem, false});
+        return segs;
     }
-    const long long off = full * big.S;
-    const long long Sa = make_choice(K, ba).S;
-    const long long la = std::min(rem, Sa);
-    segs.push_back({ba, off, la});
-    if (bb > 0 && rem > la) segs.push_back({bb, off + la, rem - la});
+    const bool odd_ok = env_ll("ADSP_NO_ODD", 0) <= 0;
+    std::vector<long long> cand;   // candidate lengths <= big.N, ascending
+    for (long long b = 256; b <= big.N; b <<= 1) {
+        cand.push_back(b);
+        if (odd_ok)
+            for (long long N : {b / 8 * 9, b / 4 * 5, b / 2 * 3, b / 4 * 7})
+                if (N < big.N && fft_size_supported(N)) cand.push_back(N);
+    }
+    std::sort(cand.begin(), cand.end());
+    // (A) remainder cover
+    double cost_a = (double)full * fft_cost(big.N);
+    long long ba = 0, bb = 0;
+    if (rem > 0) {
+        const long long nmin = std::max<long long>(2 * K, 256);
+        double best = fft_cost(big.N);
+        ba = big.N;
+        for (size_t ia = cand.size(); ia-- > 0;) {
+            const long long Na = cand[ia];
+            if (Na < nmin) break;
+            const long long Sa = make_choice(K, Na).S;
+            if (Sa >= rem) { if (fft_cost(Na) < best) { best = fft_cost(Na); ba = Na; bb = 0; } continue; }
+            for (size_t ib = ia + 1; ib-- > 0;) {
+                const long long Nb = cand[ib];
+                if (Nb < nmin) break;
+                if (Sa + make_choice(K, Nb).S < rem) break;
+                if (fft_cost(Na) + fft_cost(Nb) < best) { best = fft_cost(Na) + fft_cost(Nb); ba = Na; bb = Nb; }
+            }
+        }
+        cost_a += best;
+    }
+    // (B) single zero-padded block
+    for (long long N : cand)
+        if (N >= out_len) {
+            if (fft_cost(N) <= cost_a) { segs.push_back({N, 0, out_len, true}); return segs; }
+            break;
+        }
+    if (full > 0) segs.push_back({big.N, 0, full * big.S, false});
+    if (rem > 0) {
+        const long long off = full * big.S;
+        const long long la = std::min(rem, make_choice(K, ba).S);
+        segs.push_back({ba, off, la, false});
+        if (bb > 0 && rem > la) segs.push_back({bb, off + la, rem - la, false});
+    }
     return segs;
 }
 
@@ -272,6 +323,7 @@ static adsp_status plan_run_device(adsp_plan *p, const T *d_in, long long n, lon
                 }
                 fc = &it->second;
             }
+            fc->no_discard = sg.no_discard;
             ADSP_TRY(fc->run(d_in, n, channels, in_stride, d_out, out_stride, sg.len, sg.off, sg.off, false));
         }
         return ADSP_OK;

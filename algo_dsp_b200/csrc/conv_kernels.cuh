@@ -361,7 +361,7 @@ fftconv_cols_fwd(ConvGeom g, const T *__restrict__ x, cpx<T> *__restrict__ scrat
     const int tiles_per_pair = N2 / CS::TC;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int pl = t / tiles_per_pair, tile = t - pl * tiles_per_pair;
-        cols_fwd_tile<T, N1>(g, x, scratch + (size_t)pl * ((size_t)N1 * N2), N2, lgN, stw, tw_hi, tw_lo, pair0 + pl, tile, buf,
+        cols_fwd_tile<T, N1>(g, x, scratch + (size_t)ADSP_ALIAS(pl) * ((size_t)N1 * N2), N2, lgN, stw, tw_hi, tw_lo, pair0 + pl, tile, buf,
                              threadIdx.x, gate, true);
     }
 }
@@ -386,7 +386,7 @@ fftconv_rows(cpx<T> *__restrict__ scratch, const cpx<T> *__restrict__ H, cpx<T> 
         const int tiles_per_pair = N1 / ROWS;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
             const int pl = t / tiles_per_pair, tile = t - pl * tiles_per_pair;
-            rows_tile<T, L>(scratch + (size_t)pl * ((size_t)N1 * L), H, tile, buf, stw, threadIdx.x, gate, true);
+            rows_tile<T, L>(scratch + (size_t)ADSP_ALIAS(pl) * ((size_t)N1 * L), H, tile, buf, stw, threadIdx.x, gate, true);
         }
         return;
     }
@@ -424,7 +424,7 @@ fftconv_cols_inv(ConvGeom g, const cpx<T> *__restrict__ scratch, const T *__rest
     const int tiles_per_pair = N2 / CS::TC;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int pl = t / tiles_per_pair, tile = t - pl * tiles_per_pair;
-        cols_inv_tile<T, N1>(g, scratch + (size_t)pl * ((size_t)N1 * N2), x, y, N2, lgN, stw, tw_hi, tw_lo, pair0 + pl, tile, buf,
+        cols_inv_tile<T, N1>(g, scratch + (size_t)ADSP_ALIAS(pl) * ((size_t)N1 * N2), x, y, N2, lgN, stw, tw_hi, tw_lo, pair0 + pl, tile, buf,
                              threadIdx.x, gate, true);
     }
 }

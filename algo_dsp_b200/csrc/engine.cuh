@@ -14,7 +14,8 @@
 #include <vector>
 
 #include "../../include/algodsp_cuda.h"
-#include "conv_kernels.cuh"
+#include "conv_kernels_pf.cuh"
+#include "conv_kernels_mr.cuh"
 
 namespace adsp {
 
@@ -54,6 +55,7 @@ struct FftChoice {
     long long N = 0;       // transform length
     int N1 = 1, N2 = 0;    // N = N1*N2 (N1 == 1: single-kernel path)
     int lgN = 0;
+    int P = 1;             // odd factor of N1 (mixed-radix columns, N1 = 16*P); 1: power-of-two transform
     long long D = 0, S = 0;  // discard / step per block
     int parts = 1;           // IR partitions (only when K-1 exceeds half the largest transform)
     long long part_len = 0;  // taps per partition
@@ -110,6 +112,7 @@ template <typename T> struct FftConv {
     FftChoice ch;
     cpx<T> *H = nullptr;  // cached spectrum (four-step order, scaled 1/N)
     const cpx<T> *tw_rows = nullptr, *tw_cols = nullptr, *tw_hi = nullptr, *tw_lo = nullptr;
+    bool no_discard = false;  // next run(): single zero-padded block, D = 0, S = N (set by the caller per segment)
 
     adsp_status init(adsp_ctx *c, const T *d_kernel, long long K_, const FftChoice &choice);
     void destroy();
@@ -120,7 +123,9 @@ template <typename T> struct FftConv {
 };
 
 template <typename T> adsp_status get_tw_table(adsp_ctx *ctx, int L, const cpx<T> **out);
-template <typename T> adsp_status get_tw4_tables(adsp_ctx *ctx, int lgN, const cpx<T> **hi, const cpx<T> **lo);
+template <typename T> adsp_status get_tw4_tables(adsp_ctx *ctx, long long N, const cpx<T> **hi, const cpx<T> **lo);
+template <typename T> adsp_status get_twp_table(adsp_ctx *ctx, int P, const cpx<T> **out);
+bool fft_size_supported(long long N);
 
 // full linear convolution of `channels` signals with one kernel (device pointers), any K:
 // splits long kernels into partitions.  Builds the spectra on the fly (one-shot use).

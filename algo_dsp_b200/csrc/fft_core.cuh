@@ -21,10 +21,14 @@ namespace adsp {
 // H prefetch+multiply, bit3 cols_fwd load, bit4 cols_fwd store, bit5 cols_inv load, bit6 cols_inv store,
 // bit7 all butterfly/twiddle arithmetic, bit8 all shared-memory exchange traffic (barriers kept).
 #ifdef ADSP_PHASE_DEBUG
-static __device__ int g_phase_skip = 0;
+static __constant__ int g_phase_skip = 0;
 #define ADSP_SKIP(bit) ((g_phase_skip >> (bit)) & 1)
+// steady-state timing aid: map every block pair's scratch onto the first g_scratch_alias slots (results WRONG)
+static __constant__ int g_scratch_alias = 0;
+#define ADSP_ALIAS(pl) (g_scratch_alias > 0 ? (pl) % g_scratch_alias : (pl))
 #else
 #define ADSP_SKIP(bit) 0
+#define ADSP_ALIAS(pl) (pl)
 #endif
 
 template <typename T> struct cpx_of;
@@ -125,6 +129,70 @@ template <int S, bool INV, typename C> struct Dft<16, S, INV, C> {
     }
 };
 
+// ---------------------------------------------------------------- small odd DFTs (mixed-radix column passes)
+// cos / sin of 2*pi*m/P for m = 0..(P-1)/2 (long-double values rounded once); ternary chains fold to
+// immediates once the caller's loops are unrolled.
+template <int P> struct OddRoots;
+template <> struct OddRoots<3> {
+    static __host__ __device__ constexpr double c(int m) { return m == 0 ? 1.0 : -0.5; }
+    static __host__ __device__ constexpr double s(int m) { return m == 0 ? 0.0 : 0.8660254037844386; }
+};
+template <> struct OddRoots<5> {
+    static __host__ __device__ constexpr double c(int m) { return m == 0 ? 1.0 : m == 1 ? 0.30901699437494745 : -0.8090169943749475; }
+    static __host__ __device__ constexpr double s(int m) { return m == 0 ? 0.0 : m == 1 ? 0.9510565162951535 : 0.5877852522924731; }
+};
+template <> struct OddRoots<7> {
+    static __host__ __device__ constexpr double c(int m) {
+        return m == 0 ? 1.0 : m == 1 ? 0.6234898018587335 : m == 2 ? -0.2225209339563144 : -0.9009688679024191;
+    }
+    static __host__ __device__ constexpr double s(int m) {
+        return m == 0 ? 0.0 : m == 1 ? 0.7818314824680298 : m == 2 ? 0.9749279121818236 : 0.4338837391175581;
+    }
+};
+template <> struct OddRoots<9> {
+    static __host__ __device__ constexpr double c(int m) {
+        return m == 0 ? 1.0 : m == 1 ? 0.766044443118978 : m == 2 ? 0.17364817766693036 : m == 3 ? -0.5 : -0.9396926207859084;
+    }
+    static __host__ __device__ constexpr double s(int m) {
+        return m == 0 ? 0.0 : m == 1 ? 0.6427876096865394 : m == 2 ? 0.984807753012208 : m == 3 ? 0.8660254037844386 : 0.3420201433256687;
+    }
+};
+
+// In-place P-point DFT (P odd), natural order in and out: X[k] = x0 + sum_m (a_m cos(t k m) -/+ i b_m sin(t k m)),
+// a_m = x[m] + x[P-m], b_m = x[m] - x[P-m], t = 2*pi/P; X[P-k] uses the opposite sign.
+template <int P, bool INV, typename C> __device__ __forceinline__ void odd_dft(C (&e)[P]) {
+    using T = typename real_of<C>::type;
+    constexpr int H = (P - 1) / 2;
+    C a[H + 1], b[H + 1];
+#pragma unroll
+    for (int m = 1; m <= H; m++) { a[m] = cadd(e[m], e[P - m]); b[m] = csub(e[m], e[P - m]); }
+    const C x0 = e[0];
+    C sum = x0;
+#pragma unroll
+    for (int m = 1; m <= H; m++) sum = cadd(sum, a[m]);
+    e[0] = sum;
+#pragma unroll
+    for (int k = 1; k <= H; k++) {
+        C R = x0, I;
+        I.x = (T)0; I.y = (T)0;
+#pragma unroll
+        for (int m = 1; m <= H; m++) {
+            const int r0 = (k * m) % P;
+            const int r = r0 > H ? P - r0 : r0;
+            const T cs = (T)OddRoots<P>::c(r);
+            const T sn = (T)(r0 > H ? -OddRoots<P>::s(r) : OddRoots<P>::s(r));
+            R.x += a[m].x * cs; R.y += a[m].y * cs;
+            I.x += b[m].x * sn; I.y += b[m].y * sn;
+        }
+        // forward: X[k] = R - i*I, X[P-k] = R + i*I ; inverse: the other way round
+        C lo, hi;
+        lo.x = R.x + I.y; lo.y = R.y - I.x;     // R - i*I
+        hi.x = R.x - I.y; hi.y = R.y + I.x;     // R + i*I
+        e[k] = INV ? hi : lo;
+        e[P - k] = INV ? lo : hi;
+    }
+}
+
 // ---------------------------------------------------------------- transform geometry
 constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n >> 1); }
 
@@ -171,14 +239,26 @@ template <int TC> struct ColAddr {
 struct NoHook {
     template <typename C> __device__ __forceinline__ void operator()(C * /*buf*/) const {}
 };
+struct NoHook0 {
+    __device__ __forceinline__ void operator()() const {}
+};
 
 // 16-byte / 8-byte asynchronous global -> shared copy (LDGSTS), used to prefetch the spectrum
 template <typename C> __device__ __forceinline__ void cp_async_elem(C *smem_dst, const C *gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    if (sizeof(C) == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
-    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc));
+    if (sizeof(C) == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int PENDING> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(PENDING) : "memory"); }
+// real element (8 / 4 bytes) global -> shared; !valid writes a zero without touching global memory
+template <typename T> __device__ __forceinline__ void cp_async_real_zfill(T *smem_dst, const T *gsrc, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int n = valid ? (int)sizeof(T) : 0;
+    if (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
 
 
 // cooperative ASYNCHRONOUS copy of the compact twiddle table (global -> shared, cp.async: no register
@@ -237,11 +317,14 @@ struct PingPongGate {
 //      thread may then reuse exactly the slots it read: addr.at(j + q*TPF, P-1)).
 // gate: barrier/phase policy (see above).  D_OPEN_IN: the caller already holds the D phase;
 //      D_OPEN_OUT: leave the final D phase open for the caller to close (gate.d_end()).
+// hook0(): called once, right after the pass-0 butterflies (every input register has been consumed).
+// WAIT_TW: wait for the asynchronous twiddle-table copy before the first twiddled pass (kernels that
+//      keep other cp.async groups in flight wait for the table themselves, once, and pass false).
 // All threads of the CTA (or ping-pong group) must call this together.
-template <typename T, int L, bool INV, bool D_OPEN_IN = false, bool D_OPEN_OUT = false, typename Addr, typename Gate,
-          typename Hook = NoHook>
+template <typename T, int L, bool INV, bool D_OPEN_IN = false, bool D_OPEN_OUT = false, bool WAIT_TW = true, typename Addr,
+          typename Gate, typename Hook = NoHook, typename Hook0 = NoHook0>
 __device__ __forceinline__ void cta_fft(cpx<T> (&e)[16], cpx<T> *buf, const Addr &addr, const cpx<T> *stw, int j,
-                                        Gate &gate, const Hook &hook = Hook()) {
+                                        Gate &gate, const Hook &hook = Hook(), const Hook0 &hook0 = Hook0()) {
     using C = cpx<T>;
     using Sh = FftShape<L>;
     constexpr int R0 = Sh::R0, P = Sh::P, TPF = Sh::TPF, S0 = 16 / R0;
@@ -252,6 +335,7 @@ __device__ __forceinline__ void cta_fft(cpx<T> (&e)[16], cpx<T> *buf, const Addr
 #pragma unroll
         for (int u = 0; u < S0; u++) Dft<R0, S0, INV, C>::run(&e[u]);
     }
+    hook0();
     if (P == 0) {
         if (!D_OPEN_OUT) gate.d_end();
         return;
@@ -268,7 +352,7 @@ __device__ __forceinline__ void cta_fft(cpx<T> (&e)[16], cpx<T> *buf, const Addr
             for (int r = 0; r < R0; r++) buf[addr.at(R0 * b + r, 0)] = e[u + r * S0];
         }
     }
-    cp_async_wait_all();   // twiddle table copy (load_tw_smem) issued by this thread has landed
+    if (WAIT_TW) cp_async_wait_all();   // twiddle table copy (load_tw_smem) issued by this thread has landed
     gate.sync();
 
     int ns = R0;

@@ -75,16 +75,37 @@ template <typename T> adsp_status get_tw_table(adsp_ctx *ctx, int L, const cpx<T
     return ADSP_OK;
 }
 
-template <typename T> adsp_status get_tw4_tables(adsp_ctx *ctx, int lgN, const cpx<T> **hi, const cpx<T> **lo) {
+// mixed-radix column twiddles W_(16P)^(j*kp) at [kp*16 + j]
+template <typename T> adsp_status get_twp_table(adsp_ctx *ctx, int P, const cpx<T> **out) {
     const int prec = sizeof(T) == 8 ? 0 : 1;
-    auto key = std::make_pair(lgN, prec);
+    auto key = std::make_pair(-P, prec);
+    auto it = ctx->tw_tables.find(key);
+    if (it != ctx->tw_tables.end()) { *out = (const cpx<T> *)it->second; return ADSP_OK; }
+    std::vector<cpx<T>> h((size_t)16 * P);
+    for (int kp = 0; kp < P; kp++)
+        for (int j = 0; j < 16; j++) {
+            long double re, im;
+            unit_root((long long)j * kp, 16LL * P, &re, &im);
+            h[(size_t)kp * 16 + j].x = (T)re;
+            h[(size_t)kp * 16 + j].y = (T)im;
+        }
+    void *d = nullptr;
+    ADSP_CUDA(cudaMalloc(&d, h.size() * sizeof(cpx<T>)));
+    ADSP_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(cpx<T>), cudaMemcpyHostToDevice));
+    ctx->tw_tables[key] = d;
+    *out = (const cpx<T> *)d;
+    return ADSP_OK;
+}
+
+template <typename T> adsp_status get_tw4_tables(adsp_ctx *ctx, long long N, const cpx<T> **hi, const cpx<T> **lo) {
+    const int prec = sizeof(T) == 8 ? 0 : 1;
+    auto key = std::make_pair((int)(N >> 8), prec);
     auto it = ctx->tw4_tables.find(key);
     if (it != ctx->tw4_tables.end()) {
         *hi = (const cpx<T> *)it->second.first;
         *lo = (const cpx<T> *)it->second.second;
         return ADSP_OK;
     }
-    const long long N = 1LL << lgN;
     const long long nhi = (N >> 10) > 0 ? (N >> 10) : 1;
     std::vector<cpx<T>> hhi((size_t)nhi), hlo(1024);
     for (long long a = 0; a < nhi; a++) {
@@ -230,6 +251,137 @@ static adsp_status launch_cols(adsp_ctx *ctx, cudaStream_t st, int N1, bool inve
     case 512:  return launch_cols_t<T, 512>(ctx, st, inverse, g, x, y, scratch, N2, lgN, tw, hi, lo, pair0, pairs);
     case 1024: return launch_cols_t<T, 1024>(ctx, st, inverse, g, x, y, scratch, N2, lgN, tw, hi, lo, pair0, pairs);
     default: set_error("unsupported column FFT length"); return ADSP_ERR_INVALID_ARG;
+    }
+}
+
+// ------------------------------------------------------------------ mixed-radix columns (N1 = 16*P)
+template <typename T, int P>
+static adsp_status launch_cols_mr_t(adsp_ctx *ctx, cudaStream_t st, bool inverse, const ConvGeom &g, const T *x, T *y,
+                                    cpx<T> *scratch, int N2, long long N, const cpx<T> *tw, const cpx<T> *hi, const cpx<T> *lo,
+                                    long long pair0, int pairs) {
+    using CS = ColShapeMR<P>;
+    const int ntiles = (N2 / CS::TC) * pairs;
+    LaunchTimer lt(ctx, st, inverse ? KK_COLS_INV : KK_COLS_FWD);
+    if (!inverse)
+        fftconv_cols_fwd_mr<T, P><<<ntiles, CS::THREADS, 0, st>>>(g, x, scratch, N2, (unsigned)N, tw, hi, lo, pair0, ntiles);
+    else
+        fftconv_cols_inv_mr<T, P><<<ntiles, CS::THREADS, 0, st>>>(g, scratch, x, y, N2, (unsigned)N, tw, hi, lo, pair0, ntiles);
+    count_launch(ctx);
+    ADSP_CUDA(cudaGetLastError());
+    return ADSP_OK;
+}
+
+template <typename T>
+static adsp_status launch_cols_mr(adsp_ctx *ctx, cudaStream_t st, int P, bool inverse, const ConvGeom &g, const T *x, T *y,
+                                  cpx<T> *scratch, int N2, long long N, const cpx<T> *tw, const cpx<T> *hi, const cpx<T> *lo,
+                                  long long pair0, int pairs) {
+    switch (P) {
+    case 3: return launch_cols_mr_t<T, 3>(ctx, st, inverse, g, x, y, scratch, N2, N, tw, hi, lo, pair0, pairs);
+    case 5: return launch_cols_mr_t<T, 5>(ctx, st, inverse, g, x, y, scratch, N2, N, tw, hi, lo, pair0, pairs);
+    case 7: return launch_cols_mr_t<T, 7>(ctx, st, inverse, g, x, y, scratch, N2, N, tw, hi, lo, pair0, pairs);
+    case 9: return launch_cols_mr_t<T, 9>(ctx, st, inverse, g, x, y, scratch, N2, N, tw, hi, lo, pair0, pairs);
+    default: set_error("unsupported odd column factor"); return ADSP_ERR_INVALID_ARG;
+    }
+}
+
+// column pass of either kind, chosen by the transform geometry
+template <typename T>
+static adsp_status launch_cols_any(adsp_ctx *ctx, cudaStream_t st, const FftChoice &ch, bool inverse, const ConvGeom &g, const T *x,
+                                   T *y, cpx<T> *scratch, const cpx<T> *tw, const cpx<T> *hi, const cpx<T> *lo, long long pair0,
+                                   int pairs) {
+    if (ch.P > 1) return launch_cols_mr<T>(ctx, st, ch.P, inverse, g, x, y, scratch, ch.N2, ch.N, tw, hi, lo, pair0, pairs);
+    return launch_cols<T>(ctx, st, ch.N1, inverse, g, x, y, scratch, ch.N2, ch.lgN, tw, hi, lo, pair0, pairs);
+}
+
+// ------------------------------------------------------------------ prefetching persistent kernels
+// grid = resident CTAs (occupancy x SMs, queried once per kernel and device), never more than tiles
+template <typename K> static adsp_status pf_grid(adsp_ctx *ctx, K kern, int threads, size_t smem, int ntiles, int *cache, int *grid) {
+    if (*cache <= 0) {
+        ADSP_TRY(set_smem(kern, smem));
+        int per_sm = 0;
+        ADSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+        if (per_sm < 1) { set_error("prefetching kernel does not fit on an SM"); return ADSP_ERR_CUDA; }
+        *cache = per_sm;
+    }
+    const long long cap = env_ll("ADSP_PF_GRID_CTAS", 0);   // tuning: resident CTAs per SM to use
+    const int per_sm = (cap > 0 && cap < *cache) ? (int)cap : *cache;
+    const long long resident = (long long)per_sm * ctx->sm_count;
+    *grid = (int)std::min<long long>(resident, ntiles);
+    return ADSP_OK;
+}
+
+struct OccCache {
+    int v[64] = {};
+    int *at(int dev) { return &v[(dev >= 0 && dev < 64) ? dev : 0]; }
+};
+
+template <typename T, int N1>
+static adsp_status launch_cols_pf_t(adsp_ctx *ctx, cudaStream_t st, bool inverse, const ConvGeom &g, const T *x, T *y,
+                                    cpx<T> *scratch, int N2, int lgN, const cpx<T> *tw, const cpx<T> *hi, const cpx<T> *lo,
+                                    long long pair0, int pairs) {
+    using CS = ColShape<N1>;
+    using PF = ColShapePF<T, N1>;
+    static OccCache occ_f, occ_i;
+    const int ntiles = (N2 / CS::TC) * pairs;
+    int grid = 0;
+    LaunchTimer lt(ctx, st, inverse ? KK_COLS_INV : KK_COLS_FWD);
+    if (!inverse) {
+        ADSP_TRY(pf_grid(ctx, fftconv_cols_fwd_pf<T, N1>, CS::THREADS, PF::SMEM, ntiles, occ_f.at(ctx->device), &grid));
+        fftconv_cols_fwd_pf<T, N1><<<grid, CS::THREADS, PF::SMEM, st>>>(g, x, scratch, N2, lgN, tw, hi, lo, pair0, ntiles);
+    } else {
+        ADSP_TRY(pf_grid(ctx, fftconv_cols_inv_pf<T, N1>, CS::THREADS, PF::SMEM, ntiles, occ_i.at(ctx->device), &grid));
+        fftconv_cols_inv_pf<T, N1><<<grid, CS::THREADS, PF::SMEM, st>>>(g, scratch, x, y, N2, lgN, tw, hi, lo, pair0, ntiles);
+    }
+    count_launch(ctx);
+    ADSP_CUDA(cudaGetLastError());
+    return ADSP_OK;
+}
+
+template <typename T, int L>
+static adsp_status launch_rows_pf_t(adsp_ctx *ctx, cudaStream_t st, cpx<T> *scratch, const cpx<T> *H, int N1, const cpx<T> *tw,
+                                    int pairs) {
+    using PF = RowShapePF<T, L>;
+    static OccCache occ;
+    const int ntiles = (N1 / PF::ROWS) * pairs;
+    int grid = 0;
+    LaunchTimer lt(ctx, st, KK_ROWS);
+    ADSP_TRY(pf_grid(ctx, fftconv_rows_pf<T, L>, PF::THREADS, PF::SMEM, ntiles, occ.at(ctx->device), &grid));
+    fftconv_rows_pf<T, L><<<grid, PF::THREADS, PF::SMEM, st>>>(scratch, H, N1, tw, ntiles);
+    count_launch(ctx);
+    ADSP_CUDA(cudaGetLastError());
+    return ADSP_OK;
+}
+
+// shapes the prefetching kernels are instantiated for: 128-thread tiles whose exchange buffer + landing zone
+// leave room for three CTAs per SM
+static bool pf_supported(int N1, int N2) {
+    return (N1 == 16 || N1 == 32 || N1 == 64 || N1 == 128 || N1 == 256) && (N2 == 256 || N2 == 512 || N2 == 1024 || N2 == 2048) &&
+           N1 <= N2 * 8;
+}
+
+template <typename T>
+static adsp_status launch_cols_pf(adsp_ctx *ctx, cudaStream_t st, int N1, bool inverse, const ConvGeom &g, const T *x, T *y,
+                                  cpx<T> *scratch, int N2, int lgN, const cpx<T> *tw, const cpx<T> *hi, const cpx<T> *lo,
+                                  long long pair0, int pairs) {
+    switch (N1) {
+    case 16:   return launch_cols_pf_t<T, 16>(ctx, st, inverse, g, x, y, scratch, N2, lgN, tw, hi, lo, pair0, pairs);
+    case 32:   return launch_cols_pf_t<T, 32>(ctx, st, inverse, g, x, y, scratch, N2, lgN, tw, hi, lo, pair0, pairs);
+    case 64:   return launch_cols_pf_t<T, 64>(ctx, st, inverse, g, x, y, scratch, N2, lgN, tw, hi, lo, pair0, pairs);
+    case 128:  return launch_cols_pf_t<T, 128>(ctx, st, inverse, g, x, y, scratch, N2, lgN, tw, hi, lo, pair0, pairs);
+    case 256:  return launch_cols_pf_t<T, 256>(ctx, st, inverse, g, x, y, scratch, N2, lgN, tw, hi, lo, pair0, pairs);
+    default: set_error("unsupported column FFT length (prefetching path)"); return ADSP_ERR_INVALID_ARG;
+    }
+}
+
+template <typename T>
+static adsp_status launch_rows_pf(adsp_ctx *ctx, cudaStream_t st, int L, cpx<T> *scratch, const cpx<T> *H, int N1,
+                                  const cpx<T> *tw, int pairs) {
+    switch (L) {
+    case 256:  return launch_rows_pf_t<T, 256>(ctx, st, scratch, H, N1, tw, pairs);
+    case 512:  return launch_rows_pf_t<T, 512>(ctx, st, scratch, H, N1, tw, pairs);
+    case 1024: return launch_rows_pf_t<T, 1024>(ctx, st, scratch, H, N1, tw, pairs);
+    case 2048: return launch_rows_pf_t<T, 2048>(ctx, st, scratch, H, N1, tw, pairs);
+    default: set_error("unsupported row FFT length (prefetching path)"); return ADSP_ERR_INVALID_ARG;
     }
 }
 
@@ -487,12 +639,12 @@ adsp_status FftConv<T>::init(adsp_ctx *c, const T *d_kernel, long long K_, const
         ADSP_TRY((launch_full<T, true>(ctx, ctx->main, ch.N2, g, d_kernel, (T *)nullptr, (const cpx<T> *)nullptr, H,
                                        scale, tw_rows, 1)));
     } else {
-        ADSP_TRY(get_tw_table<T>(ctx, ch.N1, &tw_cols));
-        ADSP_TRY(get_tw4_tables<T>(ctx, ch.lgN, &tw_hi, &tw_lo));
+        if (ch.P > 1) ADSP_TRY(get_twp_table<T>(ctx, ch.P, &tw_cols));
+        else ADSP_TRY(get_tw_table<T>(ctx, ch.N1, &tw_cols));
+        ADSP_TRY(get_tw4_tables<T>(ctx, ch.N, &tw_hi, &tw_lo));
         ADSP_TRY(ctx->scratch.reserve(hbytes));
         cpx<T> *scr = (cpx<T> *)ctx->scratch.p;
-        ADSP_TRY(launch_cols<T>(ctx, ctx->main, ch.N1, false, g, d_kernel, (T *)nullptr, scr, ch.N2, ch.lgN, tw_cols,
-                                tw_hi, tw_lo, 0, 1));
+        ADSP_TRY(launch_cols_any<T>(ctx, ctx->main, ch, false, g, d_kernel, (T *)nullptr, scr, tw_cols, tw_hi, tw_lo, 0, 1));
         ADSP_TRY((launch_rows<T, true>(ctx, ctx->main, ch.N2, scr, (const cpx<T> *)nullptr, H, scale, ch.N1, tw_rows, 1)));
     }
     ADSP_CUDA(cudaStreamSynchronize(ctx->main));
@@ -511,12 +663,14 @@ adsp_status FftConv<T>::run(const T *d_x, long long n, long long channels, long 
                             long long out_stride, long long out_len, long long in_shift, long long out_shift,
                             bool accumulate) {
 #ifdef ADSP_PHASE_DEBUG
-    { const int f = (int)env_ll("ADSP_PHASE_SKIP", 0); cudaMemcpyToSymbol(g_phase_skip, &f, sizeof f); }
+    { const int f = (int)env_ll("ADSP_PHASE_SKIP", 0); cudaMemcpyToSymbol(g_phase_skip, &f, sizeof f);
+      const int a = (int)env_ll("ADSP_SCRATCH_ALIAS", 0); cudaMemcpyToSymbol(g_scratch_alias, &a, sizeof a); }
 #endif
     ConvGeom g{};
     g.n = n; g.out_len = out_len; g.in_stride = in_stride; g.out_stride = out_stride;
     g.S = ch.S; g.D = ch.D;
-    g.nblk = (int)((out_len + ch.S - 1) / ch.S);
+    if (no_discard) { g.S = ch.N; g.D = 0; no_discard = false; }   // single zero-padded block
+    g.nblk = (int)((out_len + g.S - 1) / g.S);
     g.total_blocks = channels * (long long)g.nblk;
     g.in_shift = in_shift; g.out_shift = out_shift; g.accumulate = accumulate ? 1 : 0;
     const long long npairs = (g.total_blocks + 1) / 2;
@@ -527,14 +681,14 @@ adsp_status FftConv<T>::run(const T *d_x, long long n, long long channels, long 
 
     // four-step, persistent fused kernel (one launch for the whole batch) when the batch is large enough
     // (opt-in, ADSP_FUSED=1: measured slower than the three-kernel path)
-    if (ADSP_FUSED_AVAILABLE && npairs >= env_ll("ADSP_FUSED_MIN_PAIRS", 12) && env_ll("ADSP_FUSED", 0) != 0 && env_ll("ADSP_NO_FUSED", 0) == 0) {
+    if (ch.P <= 1 && ADSP_FUSED_AVAILABLE && npairs >= env_ll("ADSP_FUSED_MIN_PAIRS", 12) && env_ll("ADSP_FUSED", 0) != 0 && env_ll("ADSP_NO_FUSED", 0) == 0) {
         bool done = false;
         ADSP_TRY(launch_fused<T>(ctx, ch.N1, ch.N2, g, npairs, ch.lgN, d_x, d_y, H, tw_rows, tw_cols, tw_hi, tw_lo, fused, &done));
         if (done) return ADSP_OK;
     }
     // four-step, stage-merged: one launch per group step (rows of group t-1 + forward columns of t + inverse columns of t-2).
     // Opt-in (ADSP_STAGES=1): measured 2.17 ms vs 1.97 ms for the three-kernel, three-stream schedule below.
-    if (env_ll("ADSP_STAGES", 0) != 0) {
+    if (ch.P <= 1 && env_ll("ADSP_STAGES", 0) != 0) {
         bool done = false;
         ADSP_TRY(run_stages<T>(ctx, ch, g, npairs, d_x, d_y, H, tw_rows, tw_cols, tw_hi, tw_lo, &done));
         if (done) return ADSP_OK;
@@ -548,7 +702,8 @@ adsp_status FftConv<T>::run(const T *d_x, long long n, long long channels, long 
     // ping-pong kernels: persistent 512-thread CTAs, two phase-locked tiles per SM
     const int conc = 2 * ctx->sm_count;   // tiles in flight
     const int tiles_r = ch.N1 / (256 / (ch.N2 / 16) > 0 ? 256 / (ch.N2 / 16) : 1);
-    const bool use_pp = pp_supported(ch.N1, ch.N2) && env_ll("ADSP_PINGPONG", 0) != 0 && npairs * (long long)tiles_r >= conc;
+    const bool use_pp = ch.P <= 1 && pp_supported(ch.N1, ch.N2) && env_ll("ADSP_PINGPONG", 0) != 0 && npairs * (long long)tiles_r >= conc;
+    const bool use_pf = ch.P <= 1 && !use_pp && pf_supported(ch.N1, ch.N2) && env_ll("ADSP_PF", 0) != 0;
     int nstreams = (int)env_ll("ADSP_STREAMS", 3);
     if (nstreams < 1) nstreams = 1;
     if (nstreams > kWorkerStreams) nstreams = kWorkerStreams;
@@ -592,9 +747,15 @@ adsp_status FftConv<T>::run(const T *d_x, long long n, long long channels, long 
         bool done = false;
         if (use_pp) ADSP_TRY(launch_pp<T>(ctx, st, ch.N1, ch.N2, g, d_x, d_y, sl, H, ch.lgN, tw_rows, tw_cols, tw_hi, tw_lo, pair0, gp, &done));
         if (done) continue;
-        ADSP_TRY(launch_cols<T>(ctx, st, ch.N1, false, g, d_x, d_y, sl, ch.N2, ch.lgN, tw_cols, tw_hi, tw_lo, pair0, gp));
+        if (use_pf) {
+            ADSP_TRY(launch_cols_pf<T>(ctx, st, ch.N1, false, g, d_x, d_y, sl, ch.N2, ch.lgN, tw_cols, tw_hi, tw_lo, pair0, gp));
+            ADSP_TRY(launch_rows_pf<T>(ctx, st, ch.N2, sl, H, ch.N1, tw_rows, gp));
+            ADSP_TRY(launch_cols_pf<T>(ctx, st, ch.N1, true, g, d_x, d_y, sl, ch.N2, ch.lgN, tw_cols, tw_hi, tw_lo, pair0, gp));
+            continue;
+        }
+        ADSP_TRY(launch_cols_any<T>(ctx, st, ch, false, g, d_x, d_y, sl, tw_cols, tw_hi, tw_lo, pair0, gp));
         ADSP_TRY((launch_rows<T, false>(ctx, st, ch.N2, sl, H, (cpx<T> *)nullptr, (T)0, ch.N1, tw_rows, gp)));
-        ADSP_TRY(launch_cols<T>(ctx, st, ch.N1, true, g, d_x, d_y, sl, ch.N2, ch.lgN, tw_cols, tw_hi, tw_lo, pair0, gp));
+        ADSP_TRY(launch_cols_any<T>(ctx, st, ch, true, g, d_x, d_y, sl, tw_cols, tw_hi, tw_lo, pair0, gp));
     }
     if (nslots > 1) {
         for (int s = 0; s < nslots; s++) {
@@ -665,7 +826,7 @@ adsp_status fft_correlate_pairs_device(adsp_ctx *ctx, const T *a, long long n, l
     const cpx<T> *tw_rows, *tw_cols, *tw_hi, *tw_lo;
     ADSP_TRY(get_tw_table<T>(ctx, ch.N2, &tw_rows));
     ADSP_TRY(get_tw_table<T>(ctx, ch.N1, &tw_cols));
-    ADSP_TRY(get_tw4_tables<T>(ctx, ch.lgN, &tw_hi, &tw_lo));
+    ADSP_TRY(get_tw4_tables<T>(ctx, ch.N, &tw_hi, &tw_lo));
     const size_t per_pair = (size_t)N * sizeof(cpx<T>);
     ADSP_TRY(ctx->scratch.reserve(2 * per_pair));
     cpx<T> *ZA = (cpx<T> *)ctx->scratch.p, *ZB = ZA + N;
@@ -700,7 +861,8 @@ template adsp_status fft_correlate_pairs_device<ADSP_REAL>(adsp_ctx *, const ADS
 
 template struct FftConv<ADSP_REAL>;
 template adsp_status get_tw_table<ADSP_REAL>(adsp_ctx *, int, const cpx<ADSP_REAL> **);
-template adsp_status get_tw4_tables<ADSP_REAL>(adsp_ctx *, int, const cpx<ADSP_REAL> **, const cpx<ADSP_REAL> **);
+template adsp_status get_tw4_tables<ADSP_REAL>(adsp_ctx *, long long, const cpx<ADSP_REAL> **, const cpx<ADSP_REAL> **);
+template adsp_status get_twp_table<ADSP_REAL>(adsp_ctx *, int, const cpx<ADSP_REAL> **);
 template adsp_status fft_convolve_device<ADSP_REAL>(adsp_ctx *, const ADSP_REAL *, long long, long long, long long,
                                                     const ADSP_REAL *, long long, ADSP_REAL *, long long);
 

@@ -290,3 +290,36 @@ def test_time_block_sharding_with_halo(conv, oracle):
         out[lo:lo + take] = ys[skip:skip + take]
     assert rel(out, full) <= 1e-13
     assert rel(out, oracle.overlap_save(h, 0, x)) <= TOL64
+
+
+# ---------------------------------------------------------------- mixed-radix transform lengths (P * 2^k, P in {3,5,7,9})
+@pytest.mark.parametrize("P,n2", [(3, 256), (5, 256), (7, 512), (9, 256), (9, 1024), (3, 2048), (9, 4096), (5, 4096)])
+def test_forced_odd_transform_lengths_overlap_save(conv, oracle, monkeypatch, P, n2):
+    """Overlap-save blocks (with discard) on every odd column factor; forced because the planner only
+    picks these lengths where they win."""
+    N = 16 * P * n2
+    K = max(2, N // 5)
+    n = int(2.6 * N)
+    monkeypatch.setenv("ADSP_FFT_N", str(N))
+    h, x = G.decaying_ir(K, seed=P), G.white(n, seed=N)
+    ols = conv.NewOverlapSave(h, 0)
+    geom = ols.internal_geometry()
+    assert geom["fft_n"] == N and geom["n1"] == 16 * P
+    assert rel(ols.Process(x), oracle.overlap_save(h, 0, x)) <= TOL64
+    y32 = conv.NewOverlapSave(h, 0, dtype=np.float32).Process(x)
+    assert rel(y32, oracle.overlap_save(h, 0, x)) <= TOL32
+
+
+@pytest.mark.parametrize("K,n", [(2000, 9000), (3000, 17000), (96000, 480000), (30000, 199000), (50000, 390000), (7000, 49000)])
+def test_single_zero_padded_block_lengths(conv, oracle, K, n):
+    """Shapes whose full result fits one P*2^k transform run as a single zero-padded block
+    (planner option B); results and lengths are unchanged (overlap_save.go:146-251)."""
+    h, x = G.decaying_ir(K, seed=11), G.white(n, seed=K)
+    ref = oracle.overlap_save(h, 0, x)
+    y = conv.NewOverlapSave(h, 0).Process(x)
+    assert len(y) == n + K - 1 and rel(y, ref) <= TOL64
+    # batch of channels (odd count: the last block pair is half empty)
+    xb = np.stack([G.white(n, seed=K + c) for c in range(3)])
+    yb = conv.NewOverlapSave(h, 0).ProcessBatch(xb)
+    for c in range(3):
+        assert rel(yb[c], oracle.overlap_save(h, 0, xb[c])) <= TOL64
