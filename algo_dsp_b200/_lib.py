@@ -72,6 +72,7 @@ PROTOTYPES = {
     "adsp_plan_step_size": (c_i64, [c_vp]),
     "adsp_plan_block_size": (c_i64, [c_vp]),
     "adsp_plan_internal_geometry": (None, [c_vp] + [C.POINTER(c_i64)] * 5),
+    "adsp_plan_describe_cover": (C.c_int, [c_vp, c_i64, C.POINTER(c_i64), C.c_int]),
     "adsp_plan_process": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64]),
     "adsp_plan_process_batch": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64]),
     "adsp_plan_process_device": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64]),

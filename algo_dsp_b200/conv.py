@@ -357,6 +357,13 @@ class _Plan:
         L.load().adsp_plan_internal_geometry(self._h, *[C.byref(x) for x in v])
         return dict(zip(("fft_n", "n1", "n2", "step", "partitions"), (x.value for x in v)))
 
+    def describe_cover(self, n):
+        """Transforms the GPU runs for Process() on n samples: [{fft_n, out_offset, out_len, single_block}] (diagnostic)."""
+        buf = (C.c_int64 * 32)()
+        k = L.load().adsp_plan_describe_cover(self._h, int(n), buf, 8)
+        return [dict(fft_n=buf[4 * i], out_offset=buf[4 * i + 1], out_len=buf[4 * i + 2], single_block=bool(buf[4 * i + 3]))
+                for i in range(min(k, 8))]
+
     def Process(self, input):
         """Process(input) -> full linear convolution, len(input)+KernelLen()-1 samples."""
         x = self._np(input)

@@ -447,7 +447,9 @@ adsp_status adsp_ctx_create(int device, adsp_ctx **out) {
     c->sm_count = prop.multiProcessorCount;
     c->l2_bytes = (size_t)prop.l2CacheSize;
     long long budget_mb = env_ll("ADSP_SCRATCH_MB", 0);
-    if (budget_mb <= 0) budget_mb = (long long)(c->l2_bytes >> 20) * 5 / 8;  // leave room for the IR spectrum + streams
+    // four-step intermediates in flight across all worker streams.  Measured optimum on B200 (126 MB L2, two
+    // partitions): ~40 MB; beyond ~56 MB the streaming signals start evicting scratch lines (tools/hint_sweep.sh)
+    if (budget_mb <= 0) budget_mb = (long long)(c->l2_bytes >> 20) * 32 / 100;
     if (budget_mb < 8) budget_mb = 8;
     c->scratch_budget = (size_t)budget_mb << 20;
     ADSP_CUDA(cudaStreamCreateWithFlags(&c->main, cudaStreamNonBlocking));
@@ -899,6 +901,20 @@ void adsp_plan_internal_geometry(const adsp_plan *p, int64_t *fft_n, int64_t *n1
     if (n2) *n2 = p->ch.N2;
     if (step) *step = p->ch.S;
     if (parts) *parts = p->ch.parts;
+}
+
+int adsp_plan_describe_cover(const adsp_plan *p, int64_t n, int64_t *out4, int cap) {
+    if (!p || n <= 0) return 0;
+    const long long out_len = n + p->K - 1;
+    std::vector<Segment> segs;
+    if (p->ch.parts == 1) segs = plan_segments(out_len, p->K, p->ch);
+    else segs.push_back({p->ch.N, 0, out_len, false});   // partitioned IR: every partition runs the plan's transform
+    int k = 0;
+    for (const Segment &sg : segs) {
+        if (out4 && k < cap) { out4[4 * k] = sg.N; out4[4 * k + 1] = sg.off; out4[4 * k + 2] = sg.len; out4[4 * k + 3] = sg.no_discard ? 1 : 0; }
+        k++;
+    }
+    return k;
 }
 
 static adsp_status plan_run_device_any(adsp_plan *p, const void *in, int64_t n, int64_t channels, int64_t in_stride,

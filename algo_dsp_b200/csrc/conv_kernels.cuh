@@ -247,8 +247,9 @@ __device__ __forceinline__ void cols_fwd_tile(const ConvGeom &g, const T *__rest
     gate.d_end();
     if (active && !ADSP_SKIP(4)) {
         C *dst = scratch_pair + n2;
+        const uint64_t keep = l2_policy_keep();
 #pragma unroll
-        for (int r = 0; r < 16; r++) __stcg(&dst[(size_t)(j + r * TPF) * N2], e[r]);
+        for (int r = 0; r < 16; r++) st_scratch(&dst[(size_t)(j + r * TPF) * N2], e[r], keep);
     }
 }
 
@@ -269,9 +270,10 @@ __device__ __forceinline__ void rows_tile(cpx<T> *__restrict__ scratch_pair, con
     C *p = scratch_pair + hoff;
 
     C e[16];
+    const uint64_t keep = l2_policy_keep();
     if (active && !ADSP_SKIP(0)) {
 #pragma unroll
-        for (int q = 0; q < 16; q++) e[q] = __ldcg(&p[q * TPF]);
+        for (int q = 0; q < 16; q++) e[q] = ld_scratch(&p[q * TPF], keep);
     } else {
 #pragma unroll
         for (int q = 0; q < 16; q++) { e[q].x = (T)0; e[q].y = (T)0; }
@@ -279,7 +281,7 @@ __device__ __forceinline__ void rows_tile(cpx<T> *__restrict__ scratch_pair, con
     auto prefetch_h = [&](C *b) {
         if (active && !ADSP_SKIP(2)) {
 #pragma unroll
-            for (int q = 0; q < 16; q++) cp_async_elem(&b[addr.at(j + q * TPF, Sh::P - 1)], &H[hoff + q * TPF]);
+            for (int q = 0; q < 16; q++) cp_async_elem_keep(&b[addr.at(j + q * TPF, Sh::P - 1)], &H[hoff + q * TPF], keep);
         }
     };
     cta_fft<T, L, false, false, true>(e, buf, addr, stw, j, gate, prefetch_h);   // D phase stays open ...
@@ -291,7 +293,7 @@ __device__ __forceinline__ void rows_tile(cpx<T> *__restrict__ scratch_pair, con
     cta_fft<T, L, true, true, false>(e, buf, addr, stw, j, gate);                // ... through the inverse's first pass
     if (active && !ADSP_SKIP(1)) {
 #pragma unroll
-        for (int q = 0; q < 16; q++) __stcg(&p[q * TPF], e[q]);
+        for (int q = 0; q < 16; q++) st_scratch(&p[q * TPF], e[q], keep);
     }
 }
 
@@ -316,8 +318,9 @@ __device__ __forceinline__ void cols_inv_tile(const ConvGeom &g, const cpx<T> *_
     const C *src = scratch_pair + n2;
     C e[16];
     if (active && !ADSP_SKIP(5)) {
+        const uint64_t drop = l2_policy_drop();   // last use of these scratch lines
 #pragma unroll
-        for (int q = 0; q < 16; q++) e[q] = __ldcg(&src[(size_t)(j + q * TPF) * N2]);
+        for (int q = 0; q < 16; q++) e[q] = ld_scratch(&src[(size_t)(j + q * TPF) * N2], drop);
     } else {
 #pragma unroll
         for (int q = 0; q < 16; q++) { e[q].x = (T)0; e[q].y = (T)0; }

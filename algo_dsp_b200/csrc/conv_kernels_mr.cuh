@@ -17,9 +17,15 @@
 
 namespace adsp {
 
+#ifndef ADSP_MR_TC
+#define ADSP_MR_TC 8
+#endif
+#ifndef ADSP_MR_MIN_CTAS
+#define ADSP_MR_MIN_CTAS (ADSP_MR_TC == 8 ? 5 : 2)   // 5 x 128 threads per SM: 102 registers, measured +3.7 % over 4
+#endif
 template <int P> struct ColShapeMR {
     static constexpr int N1 = 16 * P;
-    static constexpr int TC = 8;                 // columns per tile
+    static constexpr int TC = ADSP_MR_TC;        // columns per tile
     static constexpr int THREADS = 16 * TC;      // 16 threads per column
     static constexpr int SMEM_ELEMS = N1 * TC;
     static constexpr int TW_ENTRIES = 16 * P;    // W_N1^(j*kp) at [kp*16 + j]
@@ -32,7 +38,7 @@ __device__ __forceinline__ cpx<T> twiddle_any(const cpx<T> *__restrict__ tw_hi, 
 }
 
 template <typename T, int P>
-__global__ void __launch_bounds__(ColShapeMR<P>::THREADS, 4)
+__global__ void __launch_bounds__(ColShapeMR<P>::THREADS, ADSP_MR_MIN_CTAS)
 fftconv_cols_fwd_mr(ConvGeom g, const T *__restrict__ x, cpx<T> *__restrict__ scratch, int N2, unsigned N,
                     const cpx<T> *__restrict__ tw, const cpx<T> *__restrict__ tw_hi, const cpx<T> *__restrict__ tw_lo,
                     long long pair0, int ntiles) {
@@ -46,6 +52,7 @@ fftconv_cols_fwd_mr(ConvGeom g, const T *__restrict__ x, cpx<T> *__restrict__ sc
     const int j = threadIdx.x / TC;
     const int tiles_per_pair = N2 / TC;
     const size_t pair_elems = (size_t)N1 * N2;
+    const uint64_t keep = l2_policy_keep();
     __syncthreads();
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int pl = t / tiles_per_pair, tile = t - pl * tiles_per_pair;
@@ -77,15 +84,15 @@ fftconv_cols_fwd_mr(ConvGeom g, const T *__restrict__ x, cpx<T> *__restrict__ sc
             for (int jj = 0; jj < 16; jj++) f[jj] = buf[(j * 16 + jj) * TC + c];
             Dft<16, 1, false, C>::run(&f[0]);
             apply_geometric16<false>(f, tw_base, tw_rho);
-            C *dst = scratch + (size_t)pl * pair_elems + n2;
+            C *dst = scratch + (size_t)ADSP_ALIAS(pl) * pair_elems + n2;
 #pragma unroll
-            for (int r = 0; r < 16; r++) __stcg(&dst[(size_t)(j + P * r) * N2], f[r]);
+            for (int r = 0; r < 16; r++) st_scratch(&dst[(size_t)(j + P * r) * N2], f[r], keep);
         }
     }
 }
 
 template <typename T, int P>
-__global__ void __launch_bounds__(ColShapeMR<P>::THREADS, 4)
+__global__ void __launch_bounds__(ColShapeMR<P>::THREADS, ADSP_MR_MIN_CTAS)
 fftconv_cols_inv_mr(ConvGeom g, const cpx<T> *__restrict__ scratch, const T *__restrict__ x, T *__restrict__ y, int N2, unsigned N,
                     const cpx<T> *__restrict__ tw, const cpx<T> *__restrict__ tw_hi, const cpx<T> *__restrict__ tw_lo,
                     long long pair0, int ntiles) {
@@ -99,6 +106,7 @@ fftconv_cols_inv_mr(ConvGeom g, const cpx<T> *__restrict__ scratch, const T *__r
     const int j = threadIdx.x / TC;
     const int tiles_per_pair = N2 / TC;
     const size_t pair_elems = (size_t)N1 * N2;
+    const uint64_t drop = l2_policy_drop();   // last use of these scratch lines
     __syncthreads();
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int pl = t / tiles_per_pair, tile = t - pl * tiles_per_pair;
@@ -107,10 +115,10 @@ fftconv_cols_inv_mr(ConvGeom g, const cpx<T> *__restrict__ scratch, const T *__r
         if (j < P) {
             const C tw_base = twiddle_any<T>(tw_hi, tw_lo, ((unsigned)n2 * (unsigned)j) % N);
             const C tw_rho = twiddle_any<T>(tw_hi, tw_lo, ((unsigned)n2 * (unsigned)P) % N);
-            const C *src = scratch + (size_t)pl * pair_elems + n2;
+            const C *src = scratch + (size_t)ADSP_ALIAS(pl) * pair_elems + n2;
             C f[16];
 #pragma unroll
-            for (int r = 0; r < 16; r++) f[r] = __ldcg(&src[(size_t)(j + P * r) * N2]);
+            for (int r = 0; r < 16; r++) f[r] = ld_scratch(&src[(size_t)(j + P * r) * N2], drop);
             apply_geometric16<true>(f, tw_base, tw_rho);
             Dft<16, 1, true, C>::run(&f[0]);
 #pragma unroll

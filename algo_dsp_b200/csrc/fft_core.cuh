@@ -31,6 +31,12 @@ static __constant__ int g_scratch_alias = 0;
 #define ADSP_ALIAS(pl) (pl)
 #endif
 
+// 1: form the 15 twiddle powers of EVERY twiddled pass from the first power (14 complex products) instead of
+// reading all 15 from the shared-memory table in the short passes: trades 15 LDS.128 for 56 FP64 instructions
+#ifndef ADSP_TW_TREE_ALL
+#define ADSP_TW_TREE_ALL 0
+#endif
+
 template <typename T> struct cpx_of;
 template <> struct cpx_of<double> { using type = double2; };
 template <> struct cpx_of<float> { using type = float2; };
@@ -261,6 +267,66 @@ template <typename T> __device__ __forceinline__ void cp_async_real_zfill(T *sme
 }
 
 
+// ---------------------------------------------------------------- L2 residency hints
+// The four-step intermediates ("scratch") and the cached IR spectrum must stay L2 resident while the input and
+// output signals stream through the same cache.  Scratch/spectrum accesses carry an evict_last policy, the
+// final read of a scratch line (inverse columns) an evict_first one; signals use ld.cs / st.cs already.
+#ifndef ADSP_L2_HINTS
+#define ADSP_L2_HINTS 1
+#endif
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_drop() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ double2 ld_scratch(const double2 *p, uint64_t pol) {
+#if ADSP_L2_HINTS
+    double2 r;
+    asm volatile("ld.global.cg.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(pol));
+    return r;
+#else
+    return __ldcg(p);
+#endif
+}
+__device__ __forceinline__ float2 ld_scratch(const float2 *p, uint64_t pol) {
+#if ADSP_L2_HINTS
+    float2 r;
+    asm volatile("ld.global.cg.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(r.x), "=f"(r.y) : "l"(p), "l"(pol));
+    return r;
+#else
+    return __ldcg(p);
+#endif
+}
+__device__ __forceinline__ void st_scratch(double2 *p, double2 v, uint64_t pol) {
+#if ADSP_L2_HINTS
+    asm volatile("st.global.cg.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+#else
+    __stcg(p, v);
+#endif
+}
+__device__ __forceinline__ void st_scratch(float2 *p, float2 v, uint64_t pol) {
+#if ADSP_L2_HINTS
+    asm volatile("st.global.cg.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+#else
+    __stcg(p, v);
+#endif
+}
+// asynchronous global -> shared copy of one complex element with an L2 policy (IR spectrum prefetch)
+template <typename C> __device__ __forceinline__ void cp_async_elem_keep(C *smem_dst, const C *gsrc, uint64_t pol) {
+#if ADSP_L2_HINTS
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    if (sizeof(C) == 16) asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "l"(pol) : "memory");
+    else asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "l"(pol) : "memory");
+#else
+    cp_async_elem(smem_dst, gsrc);
+#endif
+}
+
 // cooperative ASYNCHRONOUS copy of the compact twiddle table (global -> shared, cp.async: no register
 // dependency, so the tile's own global loads issue right behind it instead of waiting a full memory
 // round trip).  cta_fft waits for it (cp.async.wait_all + barrier) just before the first twiddled pass.
@@ -369,7 +435,7 @@ __device__ __forceinline__ void cta_fft(cpx<T> (&e)[16], cpx<T> *buf, const Addr
         gate.d_begin();
         const int k = j & (ns - 1);
         if (ADSP_SKIP(7)) {
-        } else if (ns <= 16) {
+        } else if (ns <= 16 && !ADSP_TW_TREE_ALL) {
             const C *twp = stw + off + k;
 #pragma unroll
             for (int r = 1; r < 16; r++) e[r] = cmul_tw<INV>(e[r], twp[(r - 1) * ns]);

@@ -704,11 +704,13 @@ adsp_status FftConv<T>::run(const T *d_x, long long n, long long channels, long 
     const int tiles_r = ch.N1 / (256 / (ch.N2 / 16) > 0 ? 256 / (ch.N2 / 16) : 1);
     const bool use_pp = ch.P <= 1 && pp_supported(ch.N1, ch.N2) && env_ll("ADSP_PINGPONG", 0) != 0 && npairs * (long long)tiles_r >= conc;
     const bool use_pf = ch.P <= 1 && !use_pp && pf_supported(ch.N1, ch.N2) && env_ll("ADSP_PF", 0) != 0;
-    int nstreams = (int)env_ll("ADSP_STREAMS", 3);
+    int nstreams = (int)env_ll("ADSP_STREAMS", 4);
     if (nstreams < 1) nstreams = 1;
     if (nstreams > kWorkerStreams) nstreams = kWorkerStreams;
     int nslots_max = use_pp ? 2 : nstreams;
     long long G = (long long)(budget / nslots_max / per_pair);
+    const long long forced_g = env_ll("ADSP_GROUP_PAIRS", 0);   // tuning override
+    if (forced_g > 0) G = forced_g;
     if (G < 1) G = 1;
     if (G > npairs) G = npairs;
     if (G > 32768) G = 32768;

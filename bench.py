@@ -242,6 +242,7 @@ def run_ours(args):
     h = G.decaying_ir(K_TAPS)
     plan = conv.OverlapSave(h, 0, ctx=ctx)
     geom = plan.internal_geometry()
+    geom["cover"] = plan.describe_cover(N_SAMPLES)   # the transforms one Process() actually runs
 
     # synthetic white noise, (u*2-1), distinct per rank/channel; generated on the device for the
     # HBM-resident leg, copied once to pinned host memory for the end-to-end leg
@@ -353,7 +354,7 @@ def run_ours(args):
             "avg_launch_ms": dom_avg_ms, "launches": dom_n, "algorithmic_bytes_per_launch": samples_per_launch * ALGO_BYTES_PER_SAMPLE,
             "kernel_device_ms_over_timed_steps": kshare,
             "path_achieved": path_achieved * 1.0, "path_frac": path_achieved / peak,
-            "co_bound": "fp64 pipe and shared-memory pipe (DESIGN.md 3: ~80 DP instr and ~160 B of LSU traffic per output sample cap the path near 45% of HBM peak); ncu: fp64 pipe 39% / LSU 44% in fftconv_rows",
+            "co_bound": "shared-memory (LSU) pipe and fp64 pipe (DESIGN.md 3: ~390 B of LSU traffic and ~150 DP instr per complex point cap the path near 45% of HBM peak); ncu steady state: LSU 54-70%, fp64 pipe 42-50% in fftconv_rows",
         }
         cpu_threads = os.cpu_count() or 1
         cpu_ch = max(2 * cpu_threads, 8)

@@ -149,6 +149,11 @@ ADSP_API int64_t adsp_plan_block_size(const adsp_plan *plan); /* BlockSize() (OL
 /* Internal transform geometry actually used on the GPU (free to differ from the getters). */
 ADSP_API void adsp_plan_internal_geometry(const adsp_plan *plan, int64_t *fft_n, int64_t *n1, int64_t *n2,
                                           int64_t *step, int64_t *partitions);
+/* Transforms the GPU will run for Process() on n input samples: up to `cap` segments, each written as
+ * 4 values {transform length, first output sample, output samples, 1 if a single zero-padded block
+ * (nothing discarded) else 0}.  Returns the number of segments.  Diagnostic only: results, lengths and
+ * the reference getters (overlap_save.go:115-124) never depend on it. */
+ADSP_API int adsp_plan_describe_cover(const adsp_plan *plan, int64_t n, int64_t *out4, int cap);
 
 /* Process(input) / ProcessTo(output, input): out_len must equal n + kernel_len - 1
  * (ErrLengthMismatch otherwise, overlap_save.go:259-262).  Host pointers. */

@@ -316,7 +316,12 @@ def test_single_zero_padded_block_lengths(conv, oracle, K, n):
     (planner option B); results and lengths are unchanged (overlap_save.go:146-251)."""
     h, x = G.decaying_ir(K, seed=11), G.white(n, seed=K)
     ref = oracle.overlap_save(h, 0, x)
-    y = conv.NewOverlapSave(h, 0).Process(x)
+    plan = conv.NewOverlapSave(h, 0)
+    cover = plan.describe_cover(n)
+    assert len(cover) == 1 and cover[0]["single_block"] and cover[0]["fft_n"] >= n + K - 1
+    if (K, n) == (96000, 480000):
+        assert cover[0]["fft_n"] == 9 * 65536          # the bench shape: 589 824 points instead of 2^19 + 2^18
+    y = plan.Process(x)
     assert len(y) == n + K - 1 and rel(y, ref) <= TOL64
     # batch of channels (odd count: the last block pair is half empty)
     xb = np.stack([G.white(n, seed=K + c) for c in range(3)])

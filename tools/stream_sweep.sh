@@ -1,3 +1,6 @@
 #!/bin/bash
+# worker streams x group size sweep on the bench workload (ADSP_GROUP_PAIRS forces the pairs per launch)
 cd "$(dirname "$0")/.."
-for st in 2 3 4 6 8; do for mb in 40 80 160; do ADSP_STREAMS=$st ADSP_SCRATCH_MB=$mb LABEL="streams=$st scratch=$mb" python tools/bench_one.py | cut -c1-75; done; done
+for s in ${STREAMS:-2 3 4 6 8}; do for g in ${GROUPS_:-1 2 3}; do
+  ADSP_STREAMS=$s ADSP_GROUP_PAIRS=$g LABEL="streams=$s pairs/launch=$g" python tools/bench_one.py | cut -c1-100
+done; done
