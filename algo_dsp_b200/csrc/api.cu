@@ -101,18 +101,31 @@ FftChoice make_choice(long long Kp, long long N) {
 }
 
 FftChoice choose_fft(long long K) {
-    const long long NMAX = env_ll("ADSP_MAX_FFT", 1LL << 20);
+    // Preferred largest transform 2^20 (N1 = 256 columns, the fastest kernels).  A kernel that does not fit half
+    // of it used to be split into partitions of 2^19 taps; measured on B200 one 2^22-point transform
+    // (N1 = 1024) is 2.6x faster for 2^20 taps (48.7 vs 18.9 Gsamples/s), so long kernels take N = 2^22 and
+    // are only partitioned beyond 2^21 taps.  ADSP_MAX_FFT forces the old single-size rule (tests, tuning).
+    const long long forced_max = env_ll("ADSP_MAX_FFT", 0);
+    const long long NMAX = forced_max > 0 ? forced_max : (1LL << 20);
+    const long long NBIG = 1LL << 22;
     long long Kp = K;
     int parts = 1;
-    if (K - 1 > NMAX / 2) {
-        parts = (int)((K + NMAX / 2 - 1) / (NMAX / 2));
+    long long N;
+    if (K - 1 <= NMAX / 2 || forced_max > 0) {
+        if (K - 1 > NMAX / 2) {
+            parts = (int)((K + NMAX / 2 - 1) / (NMAX / 2));
+            Kp = (K + parts - 1) / parts;
+        }
+        N = next_pow2_ll(8 * Kp);
+        if (N < 256) N = 256;
+        if (N > NMAX) N = NMAX;
+    } else {
+        parts = (int)((K + NBIG / 2 - 1) / (NBIG / 2));
         Kp = (K + parts - 1) / parts;
+        N = NBIG;
     }
-    long long N = next_pow2_ll(8 * Kp);
     const long long forced = env_ll("ADSP_FFT_N", 0);
     if (forced > 0) N = forced;
-    if (N < 256) N = 256;
-    if (N > NMAX) N = NMAX;
     while (N < 2 * Kp && N < (1LL << 22)) N *= 2;
     FftChoice c = make_choice(Kp, N);
     c.parts = parts;

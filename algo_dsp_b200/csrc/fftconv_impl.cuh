@@ -707,6 +707,7 @@ adsp_status FftConv<T>::run(const T *d_x, long long n, long long channels, long 
     int nstreams = (int)env_ll("ADSP_STREAMS", 4);
     if (nstreams < 1) nstreams = 1;
     if (nstreams > kWorkerStreams) nstreams = kWorkerStreams;
+    if (per_pair * 2 >= budget && nstreams > 2) nstreams = 2;   // pairs that alone fill the budget (N >= 2^21): two in flight
     int nslots_max = use_pp ? 2 : nstreams;
     long long G = (long long)(budget / nslots_max / per_pair);
     const long long forced_g = env_ll("ADSP_GROUP_PAIRS", 0);   // tuning override

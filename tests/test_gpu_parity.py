@@ -262,13 +262,32 @@ def test_large_batch_groups_and_streams(conv, oracle, monkeypatch):
     assert rel(y32[5], oracle.overlap_save(h, 0, x[5])) <= TOL32
 
 
-def test_long_kernel_partitions_config5_shape(conv, oracle):
-    """Kernel longer than half the largest transform -> summed IR partitions (config 5 shape, reduced)."""
+def test_long_kernel_config5_shape(conv, oracle):
+    """Kernel longer than half of the preferred 2^20 transform (config 5 shape, reduced): one 2^22-point
+    transform; and, forced back to 2^20, the sum over IR partitions."""
+    K, n = 600000, 700000
+    h, x = G.decaying_ir(K), G.white(n, seed=5)
+    ref = oracle.overlap_save(h, 0, x)
+    c = conv.NewOverlapSave(h, 0)
+    assert c.internal_geometry()["fft_n"] == 1 << 22 and c.internal_geometry()["partitions"] == 1
+    assert rel(c.Process(x), ref) <= TOL64
+
+
+def test_long_kernel_partition_sum(conv, oracle, monkeypatch):
+    monkeypatch.setenv("ADSP_MAX_FFT", str(1 << 20))
     K, n = 600000, 700000
     h, x = G.decaying_ir(K), G.white(n, seed=5)
     c = conv.NewOverlapSave(h, 0)
     assert c.internal_geometry()["partitions"] >= 2
     assert rel(c.Process(x), oracle.overlap_save(h, 0, x)) <= TOL64
+    monkeypatch.setenv("ADSP_MAX_FFT", str(1 << 13))          # many partitions, small transforms
+    K, n = 30000, 50000
+    h, x = G.decaying_ir(K), G.white(n, seed=6)
+    c = conv.NewOverlapSave(h, 0)
+    assert c.internal_geometry()["partitions"] >= 7
+    assert rel(c.Process(x), oracle.overlap_save(h, 0, x)) <= TOL64
+    y32 = conv.NewOverlapSave(h, 0, dtype=np.float32).Process(x)
+    assert rel(y32, oracle.overlap_save(h, 0, x)) <= TOL32
 
 
 def test_time_block_sharding_with_halo(conv, oracle):
