@@ -61,15 +61,16 @@ long long env_ll(const char *name, long long dflt) {
 // geometry for a given transform length N and (partition) kernel length Kp
 static int odd_part(long long N) { while (N > 1 && (N & 1) == 0) N >>= 1; return (int)N; }
 
-// transform lengths the engine has kernels for: powers of two 256 .. 2^22, and P * 2^k with P in {3,5,7,9}
-// as (16*P) x N2 four-step transforms, N2 = 256 .. 4096 (conv_kernels_mr.cuh)
+// transform lengths the engine has kernels for: powers of two 256 .. 2^22, and P * 2^k with P in {3,5,7,9},
+// k = 12 .. 17, as (16*M) x N2 four-step transforms (conv_kernels_mr.cuh): M = P with N2 = 2^(k-4) up to k = 15,
+// M = 2P with N2 = 2^(k-5) for k = 16, 17 (keeps the rows at 2048 / 4096 points)
 bool fft_size_supported(long long N) {
     if (N < 256) return false;
     const int P = odd_part(N);
     if (P == 1) return N <= (1LL << 22);
     if (P != 3 && P != 5 && P != 7 && P != 9) return false;
-    const long long n2 = N / (16 * P);
-    return n2 >= 256 && n2 <= 4096;
+    const long long pow2 = N / P;
+    return pow2 >= (1LL << 12) && pow2 <= (1LL << 17);
 }
 
 FftChoice make_choice(long long Kp, long long N) {
@@ -80,7 +81,11 @@ FftChoice make_choice(long long Kp, long long N) {
     while ((1LL << lg) < N) lg++;
     c.lgN = lg;
     c.P = odd_part(N);
-    if (c.P > 1) { c.N1 = 16 * c.P; c.N2 = (int)(N / c.N1); c.lgN = 0; }
+    if (c.P > 1) {
+        const long long pow2 = N / c.P;   // 2^17 needs M = 2P (rows stop at 4096 points); 2^16 prefers it (2048-point rows)
+        c.M = (pow2 >= (1LL << 17) || (pow2 == (1LL << 16) && env_ll("ADSP_MR_NO_2P", 0) == 0)) ? 2 * c.P : c.P;
+        c.N1 = 16 * c.M; c.N2 = (int)(N / c.N1); c.lgN = 0;
+    }
     else if (N <= 4096) { c.N1 = 1; c.N2 = (int)N; }
     else {
         // rows of 2048 points run as 128-thread CTAs (4 per SM); 2^20-point transforms keep 4096-point

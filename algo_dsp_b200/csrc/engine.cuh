@@ -55,7 +55,8 @@ struct FftChoice {
     long long N = 0;       // transform length
     int N1 = 1, N2 = 0;    // N = N1*N2 (N1 == 1: single-kernel path)
     int lgN = 0;
-    int P = 1;             // odd factor of N1 (mixed-radix columns, N1 = 16*P); 1: power-of-two transform
+    int P = 1;             // odd factor of N (mixed-radix columns); 1: power-of-two transform
+    int M = 1;             // length of the in-register column DFT: P or 2P; N1 = 16*M
     long long D = 0, S = 0;  // discard / step per block
     int parts = 1;           // IR partitions (only when K-1 exceeds half the largest transform)
     long long part_len = 0;  // taps per partition
@@ -124,7 +125,7 @@ template <typename T> struct FftConv {
 
 template <typename T> adsp_status get_tw_table(adsp_ctx *ctx, int L, const cpx<T> **out);
 template <typename T> adsp_status get_tw4_tables(adsp_ctx *ctx, long long N, const cpx<T> **hi, const cpx<T> **lo);
-template <typename T> adsp_status get_twp_table(adsp_ctx *ctx, int P, const cpx<T> **out);
+template <typename T> adsp_status get_twp_table(adsp_ctx *ctx, int M, const cpx<T> **out);
 bool fft_size_supported(long long N);
 
 // full linear convolution of `channels` signals with one kernel (device pointers), any K:

@@ -199,6 +199,27 @@ template <int P, bool INV, typename C> __device__ __forceinline__ void odd_dft(C
     }
 }
 
+// In-place M-point DFT for the mixed-radix column passes: M = P (odd) or M = 2P, the latter by the prime-factor
+// (Good-Thomas) map i = (P*i1 + 2*i2) mod 2P, k = (P*k1 + (P+1)*k2) mod 2P -- two P-point DFTs and P two-point
+// butterflies, no twiddles between them (2 and P are coprime).
+template <int M, bool INV, typename C> __device__ __forceinline__ void small_dft(C (&e)[M]) {
+    if constexpr (M % 2 == 1) {
+        odd_dft<M, INV>(e);
+    } else {
+        constexpr int P = M / 2;
+        C g0[P], g1[P];
+#pragma unroll
+        for (int i2 = 0; i2 < P; i2++) { g0[i2] = e[(2 * i2) % M]; g1[i2] = e[(P + 2 * i2) % M]; }
+        odd_dft<P, INV>(g0);
+        odd_dft<P, INV>(g1);
+#pragma unroll
+        for (int k2 = 0; k2 < P; k2++) {
+            e[((P + 1) * k2) % M] = cadd(g0[k2], g1[k2]);
+            e[(P + (P + 1) * k2) % M] = csub(g0[k2], g1[k2]);
+        }
+    }
+}
+
 // ---------------------------------------------------------------- transform geometry
 constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n >> 1); }
 

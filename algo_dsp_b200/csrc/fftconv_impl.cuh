@@ -75,7 +75,7 @@ template <typename T> adsp_status get_tw_table(adsp_ctx *ctx, int L, const cpx<T
     return ADSP_OK;
 }
 
-// mixed-radix column twiddles W_(16P)^(j*kp) at [kp*16 + j]
+// mixed-radix column twiddles W_(16M)^(j*km) at [km*16 + j]
 template <typename T> adsp_status get_twp_table(adsp_ctx *ctx, int P, const cpx<T> **out) {
     const int prec = sizeof(T) == 8 ? 0 : 1;
     auto key = std::make_pair(-P, prec);
@@ -275,7 +275,11 @@ template <typename T>
 static adsp_status launch_cols_mr(adsp_ctx *ctx, cudaStream_t st, int P, bool inverse, const ConvGeom &g, const T *x, T *y,
                                   cpx<T> *scratch, int N2, long long N, const cpx<T> *tw, const cpx<T> *hi, const cpx<T> *lo,
                                   long long pair0, int pairs) {
-    switch (P) {
+    switch (P) {   // P here is M, the in-register DFT length (odd P, or 2P)
+    case 6: return launch_cols_mr_t<T, 6>(ctx, st, inverse, g, x, y, scratch, N2, N, tw, hi, lo, pair0, pairs);
+    case 10: return launch_cols_mr_t<T, 10>(ctx, st, inverse, g, x, y, scratch, N2, N, tw, hi, lo, pair0, pairs);
+    case 14: return launch_cols_mr_t<T, 14>(ctx, st, inverse, g, x, y, scratch, N2, N, tw, hi, lo, pair0, pairs);
+    case 18: return launch_cols_mr_t<T, 18>(ctx, st, inverse, g, x, y, scratch, N2, N, tw, hi, lo, pair0, pairs);
     case 3: return launch_cols_mr_t<T, 3>(ctx, st, inverse, g, x, y, scratch, N2, N, tw, hi, lo, pair0, pairs);
     case 5: return launch_cols_mr_t<T, 5>(ctx, st, inverse, g, x, y, scratch, N2, N, tw, hi, lo, pair0, pairs);
     case 7: return launch_cols_mr_t<T, 7>(ctx, st, inverse, g, x, y, scratch, N2, N, tw, hi, lo, pair0, pairs);
@@ -289,7 +293,7 @@ template <typename T>
 static adsp_status launch_cols_any(adsp_ctx *ctx, cudaStream_t st, const FftChoice &ch, bool inverse, const ConvGeom &g, const T *x,
                                    T *y, cpx<T> *scratch, const cpx<T> *tw, const cpx<T> *hi, const cpx<T> *lo, long long pair0,
                                    int pairs) {
-    if (ch.P > 1) return launch_cols_mr<T>(ctx, st, ch.P, inverse, g, x, y, scratch, ch.N2, ch.N, tw, hi, lo, pair0, pairs);
+    if (ch.P > 1) return launch_cols_mr<T>(ctx, st, ch.M, inverse, g, x, y, scratch, ch.N2, ch.N, tw, hi, lo, pair0, pairs);
     return launch_cols<T>(ctx, st, ch.N1, inverse, g, x, y, scratch, ch.N2, ch.lgN, tw, hi, lo, pair0, pairs);
 }
 
@@ -639,7 +643,7 @@ adsp_status FftConv<T>::init(adsp_ctx *c, const T *d_kernel, long long K_, const
         ADSP_TRY((launch_full<T, true>(ctx, ctx->main, ch.N2, g, d_kernel, (T *)nullptr, (const cpx<T> *)nullptr, H,
                                        scale, tw_rows, 1)));
     } else {
-        if (ch.P > 1) ADSP_TRY(get_twp_table<T>(ctx, ch.P, &tw_cols));
+        if (ch.P > 1) ADSP_TRY(get_twp_table<T>(ctx, ch.M, &tw_cols));
         else ADSP_TRY(get_tw_table<T>(ctx, ch.N1, &tw_cols));
         ADSP_TRY(get_tw4_tables<T>(ctx, ch.N, &tw_hi, &tw_lo));
         ADSP_TRY(ctx->scratch.reserve(hbytes));

@@ -312,21 +312,32 @@ def test_time_block_sharding_with_halo(conv, oracle):
 
 
 # ---------------------------------------------------------------- mixed-radix transform lengths (P * 2^k, P in {3,5,7,9})
-@pytest.mark.parametrize("P,n2", [(3, 256), (5, 256), (7, 512), (9, 256), (9, 1024), (3, 2048), (9, 4096), (5, 4096)])
-def test_forced_odd_transform_lengths_overlap_save(conv, oracle, monkeypatch, P, n2):
-    """Overlap-save blocks (with discard) on every odd column factor; forced because the planner only
-    picks these lengths where they win."""
-    N = 16 * P * n2
+@pytest.mark.parametrize("N,n1", [(16 * 3 * 256, 48), (16 * 5 * 256, 80), (16 * 7 * 512, 112), (16 * 9 * 256, 144), (16 * 9 * 1024, 144),
+                                   (16 * 3 * 2048, 48), (9 << 15, 144), (3 << 16, 96), (5 << 16, 160), (7 << 16, 224), (9 << 16, 288),
+                                   (3 << 17, 96), (5 << 17, 160), (7 << 17, 224)])
+def test_forced_odd_transform_lengths_overlap_save(conv, oracle, monkeypatch, N, n1):
+    """Overlap-save blocks (with discard) on every mixed-radix column shape (N1 = 16*P and 32*P); forced
+    because the planner only picks these lengths where they win."""
     K = max(2, N // 5)
     n = int(2.6 * N)
     monkeypatch.setenv("ADSP_FFT_N", str(N))
-    h, x = G.decaying_ir(K, seed=P), G.white(n, seed=N)
+    h, x = G.decaying_ir(K, seed=n1), G.white(n, seed=N)
+    ref = oracle.overlap_save(h, 0, x)
     ols = conv.NewOverlapSave(h, 0)
     geom = ols.internal_geometry()
-    assert geom["fft_n"] == N and geom["n1"] == 16 * P
-    assert rel(ols.Process(x), oracle.overlap_save(h, 0, x)) <= TOL64
+    assert geom["fft_n"] == N and geom["n1"] == n1
+    assert rel(ols.Process(x), ref) <= TOL64
     y32 = conv.NewOverlapSave(h, 0, dtype=np.float32).Process(x)
-    assert rel(y32, oracle.overlap_save(h, 0, x)) <= TOL32
+    assert rel(y32, ref) <= TOL32
+
+
+def test_mixed_radix_16p_columns_at_2_16(conv, oracle, monkeypatch):
+    """P * 2^16 through the N1 = 16*P kernels with 4096-point rows (the shape the 32*P kernels replaced)."""
+    monkeypatch.setenv("ADSP_MR_NO_2P", "1")
+    K, n = 96000, 480000
+    h, x = G.decaying_ir(K), G.white(n, seed=1)
+    plan = conv.NewOverlapSave(h, 0)
+    assert rel(plan.Process(x), oracle.overlap_save(h, 0, x)) <= TOL64
 
 
 @pytest.mark.parametrize("K,n", [(2000, 9000), (3000, 17000), (96000, 480000), (30000, 199000), (50000, 390000), (7000, 49000)])
