@@ -24,6 +24,9 @@ namespace adsp {
 #ifndef ADSP_MR_MIN_CTAS
 #define ADSP_MR_MIN_CTAS (ADSP_MR_TC == 8 ? 5 : 2)   // 5 x 128 threads per SM: 102 registers, measured +3.7 % over 4
 #endif
+#ifndef ADSP_MR_WIDE_CTAS
+#define ADSP_MR_WIDE_CTAS 3
+#endif
 template <int M> struct ColShapeMR {
     static constexpr int N1 = 16 * M;
     static constexpr int TC = ADSP_MR_TC;        // columns per tile
@@ -31,7 +34,7 @@ template <int M> struct ColShapeMR {
     static constexpr int THREADS = TPC * TC;
     static constexpr int SMEM_ELEMS = N1 * TC;
     static constexpr int TW_ENTRIES = 16 * M;    // W_N1^(j*km) at [km*16 + j]
-    static constexpr int MIN_CTAS = M > 16 ? 3 : ADSP_MR_MIN_CTAS;
+    static constexpr int MIN_CTAS = M > 16 ? (ADSP_MR_TC == 8 ? ADSP_MR_WIDE_CTAS : 2) : ADSP_MR_MIN_CTAS;
 };
 
 // W_N^m for any N that is a multiple of 1024: hi[m >> 10] * lo[m & 1023]
@@ -48,8 +51,9 @@ fftconv_cols_fwd_mr(ConvGeom g, const T *__restrict__ x, cpx<T> *__restrict__ sc
     using C = cpx<T>;
     using CS = ColShapeMR<M>;
     constexpr int TC = CS::TC, N1 = CS::N1;
-    __shared__ __align__(16) C buf[CS::SMEM_ELEMS];
-    __shared__ __align__(16) C stw[CS::TW_ENTRIES];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C *buf = reinterpret_cast<C *>(smem_raw);
+    C *stw = buf + CS::SMEM_ELEMS;
     for (int i = threadIdx.x; i < CS::TW_ENTRIES; i += CS::THREADS) stw[i] = tw[i];
     const int c = threadIdx.x % TC;
     const int j = threadIdx.x / TC;
@@ -105,8 +109,9 @@ fftconv_cols_inv_mr(ConvGeom g, const cpx<T> *__restrict__ scratch, const T *__r
     using C = cpx<T>;
     using CS = ColShapeMR<M>;
     constexpr int TC = CS::TC, N1 = CS::N1;
-    __shared__ __align__(16) C buf[CS::SMEM_ELEMS];
-    __shared__ __align__(16) C stw[CS::TW_ENTRIES];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C *buf = reinterpret_cast<C *>(smem_raw);
+    C *stw = buf + CS::SMEM_ELEMS;
     for (int i = threadIdx.x; i < CS::TW_ENTRIES; i += CS::THREADS) stw[i] = tw[i];
     const int c = threadIdx.x % TC;
     const int j = threadIdx.x / TC;

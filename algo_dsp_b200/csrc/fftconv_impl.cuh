@@ -261,11 +261,17 @@ static adsp_status launch_cols_mr_t(adsp_ctx *ctx, cudaStream_t st, bool inverse
                                     long long pair0, int pairs) {
     using CS = ColShapeMR<P>;
     const int ntiles = (N2 / CS::TC) * pairs;
+    const size_t smem = ((size_t)CS::SMEM_ELEMS + CS::TW_ENTRIES) * sizeof(cpx<T>);
+    static AttrOnce once;
+    if (once.need(ctx->device)) {
+        ADSP_TRY(set_smem(fftconv_cols_fwd_mr<T, P>, smem));
+        ADSP_TRY(set_smem(fftconv_cols_inv_mr<T, P>, smem));
+    }
     LaunchTimer lt(ctx, st, inverse ? KK_COLS_INV : KK_COLS_FWD);
     if (!inverse)
-        fftconv_cols_fwd_mr<T, P><<<ntiles, CS::THREADS, 0, st>>>(g, x, scratch, N2, (unsigned)N, tw, hi, lo, pair0, ntiles);
+        fftconv_cols_fwd_mr<T, P><<<ntiles, CS::THREADS, smem, st>>>(g, x, scratch, N2, (unsigned)N, tw, hi, lo, pair0, ntiles);
     else
-        fftconv_cols_inv_mr<T, P><<<ntiles, CS::THREADS, 0, st>>>(g, scratch, x, y, N2, (unsigned)N, tw, hi, lo, pair0, ntiles);
+        fftconv_cols_inv_mr<T, P><<<ntiles, CS::THREADS, smem, st>>>(g, scratch, x, y, N2, (unsigned)N, tw, hi, lo, pair0, ntiles);
     count_launch(ctx);
     ADSP_CUDA(cudaGetLastError());
     return ADSP_OK;

@@ -3,7 +3,7 @@
 # L2-resident slots (results wrong, timing valid).  Needs libvar_dbg.so (-DADSP_PHASE_DEBUG).
 cd "$(dirname "$0")/.."
 export ADSP_LIB_PATH=$PWD/algo_dsp_b200/${LIBV:-libvar_dbg.so}
-for odd in 0 1; do
-  ADSP_NO_ODD=$odd LABEL="no_odd=$odd default schedule" python tools/ktimes.py
-  ADSP_NO_ODD=$odd ADSP_STREAMS=1 ADSP_SCRATCH_MB=100000 ADSP_SCRATCH_ALIAS=3 LABEL="no_odd=$odd steady alias=3" python tools/ktimes.py
-done
+LABEL="default schedule" python tools/ktimes.py
+LABEL="default schedule" python tools/bench_one.py | cut -c1-100
+ADSP_STREAMS=1 ADSP_GROUP_PAIRS=100000 ADSP_SCRATCH_ALIAS=3 LABEL="steady alias=3" python tools/ktimes.py
+ADSP_STREAMS=1 ADSP_GROUP_PAIRS=100000 ADSP_SCRATCH_ALIAS=3 LABEL="steady alias=3" python tools/bench_one.py | cut -c1-100
