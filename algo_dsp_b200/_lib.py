@@ -79,6 +79,15 @@ PROTOTYPES = {
     "adsp_plan_sync": (C.c_int, [c_vp]),
     "adsp_partitioned_create": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, C.c_int, C.c_int, C.POINTER(c_vp)]),
     "adsp_partitioned_process_block": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64]),
+    "adsp_partitioned_create_batch": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(c_vp)]),
+    "adsp_partitioned_process_block_batch": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64]),
+    "adsp_partitioned_process_block_batch_device": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64]),
+    "adsp_partitioned_set_wet_dry": (C.c_int, [c_vp, C.c_double, C.c_double]),
+    "adsp_partitioned_process_in_place_batch": (C.c_int, [c_vp, c_vp, c_i64, c_i64]),
+    "adsp_partitioned_process_in_place_batch_device": (C.c_int, [c_vp, c_vp, c_i64, c_i64]),
+    "adsp_partitioned_channels": (C.c_int, [c_vp]),
+    "adsp_partitioned_internal_stage_count": (C.c_int, [c_vp]),
+    "adsp_partitioned_internal_stage_info": (C.c_int, [c_vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(c_i64)]),
     "adsp_partitioned_latency": (C.c_int, [c_vp]),
     "adsp_partitioned_stage_count": (C.c_int, [c_vp]),
     "adsp_partitioned_stage_info": (C.c_int, [c_vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

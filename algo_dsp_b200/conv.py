@@ -449,16 +449,22 @@ def NewOverlapAdd(kernel, blockSize=0, ctx=None, dtype=np.float64):
 
 
 class PartitionedConvolution(_Plan):
-    """PartitionedConvolutionT -- partitioned.go:27 (f64: PartitionedConvolution, f32: PartitionedConvolution32)."""
+    """PartitionedConvolutionT -- partitioned.go:27 (f64: PartitionedConvolution, f32: PartitionedConvolution32).
+    channels > 1: that many independent streams through one IR, one launch set per call (rows of 2-D blocks)."""
 
-    def __init__(self, kernel, minBlockOrder, maxBlockOrder, ctx=None, dtype=np.float64):
+    def __init__(self, kernel, minBlockOrder, maxBlockOrder, ctx=None, dtype=np.float64, channels=1):
         super().__init__()
         self._dtype = np.dtype(dtype).type
         self._ctx_obj = ctx or default_context()
+        self._channels = int(channels)
         k = self._np(kernel)
         prec = L.F64 if self._dtype == np.float64 else L.F32
-        _check(L.load().adsp_partitioned_create(self._ctx_obj.handle, _p(k), k.size, int(minBlockOrder), int(maxBlockOrder),
-                                                prec, C.byref(self._h)))
+        if self._channels == 1:
+            _check(L.load().adsp_partitioned_create(self._ctx_obj.handle, _p(k), k.size, int(minBlockOrder), int(maxBlockOrder),
+                                                    prec, C.byref(self._h)))
+        else:
+            _check(L.load().adsp_partitioned_create_batch(self._ctx_obj.handle, _p(k), k.size, int(minBlockOrder), int(maxBlockOrder),
+                                                          self._channels, prec, C.byref(self._h)))
 
     def ProcessBlock(self, input, output):
         """ProcessBlock(input, output): equal lengths; output delayed by Latency() samples."""
@@ -466,6 +472,34 @@ class PartitionedConvolution(_Plan):
         if not (isinstance(output, np.ndarray) and output.dtype == self._dtype and output.flags.c_contiguous):
             raise TypeError("output must be a contiguous numpy array of the plan's dtype")
         _check(L.load().adsp_partitioned_process_block(self._h, _p(x), x.size, _p(output), output.size))
+
+    def ProcessBlockBatch(self, input2d, output2d=None):
+        """Rows = channels: every row is ProcessBlock'ed as its own stream (same call for all channels)."""
+        x = np.ascontiguousarray(input2d, dtype=self._dtype)
+        if x.ndim != 2 or x.shape[0] != self._channels:
+            raise ValueError("input must be [channels, n]")
+        out = np.empty_like(x) if output2d is None else output2d
+        _check(L.load().adsp_partitioned_process_block_batch(self._h, _p(x), x.shape[1], x.shape[1], _p(out), out.shape[1]))
+        return out
+
+    def process_block_device(self, in_ptr, n, in_stride, out_ptr, out_stride):
+        _check(L.load().adsp_partitioned_process_block_batch_device(self._h, C.c_void_p(in_ptr), int(n), int(in_stride),
+                                                                    C.c_void_p(out_ptr), int(out_stride)))
+
+    def SetWetDry(self, wet, dry):
+        """ConvolutionReverb.SetWetDry -- dsp/effects/reverb/convolution.go:51."""
+        _check(L.load().adsp_partitioned_set_wet_dry(self._h, float(wet), float(dry)))
+
+    def ProcessInPlace(self, block):
+        """ConvolutionReverb.ProcessInPlace -- convolution.go:60: block = dry*block + wet*reverb(block); 1-D (mono plan) or
+        [channels, n]."""
+        if not (isinstance(block, np.ndarray) and block.dtype == self._dtype and block.flags.c_contiguous):
+            raise TypeError("block must be a contiguous numpy array of the plan's dtype")
+        n = block.shape[-1]
+        rows = 1 if block.ndim == 1 else block.shape[0]
+        if rows != self._channels:
+            raise ValueError("block must have one row per channel")
+        _check(L.load().adsp_partitioned_process_in_place_batch(self._h, _p(block), n, n))
 
     def Latency(self):
         return int(L.load().adsp_partitioned_latency(self._h))
@@ -478,15 +512,30 @@ class PartitionedConvolution(_Plan):
         _check(L.load().adsp_partitioned_stage_info(self._h, int(index), C.byref(ps), C.byref(bc)))
         return ps.value, bc.value
 
+    def internal_stages(self):
+        """[(partition size, partitions, IR offset)] of the delay-line engine (diagnostic)."""
+        out = []
+        for i in range(int(L.load().adsp_partitioned_internal_stage_count(self._h))):
+            ps, cnt, off = C.c_int(), C.c_int(), C.c_int64()
+            _check(L.load().adsp_partitioned_internal_stage_info(self._h, i, C.byref(ps), C.byref(cnt), C.byref(off)))
+            out.append((ps.value, cnt.value, off.value))
+        return out
 
-def NewPartitionedConvolution(kernel, minBlockOrder, maxBlockOrder, ctx=None):
+
+def NewPartitionedConvolution(kernel, minBlockOrder, maxBlockOrder, ctx=None, channels=1):
     """NewPartitionedConvolution -- partitioned.go:335."""
-    return PartitionedConvolution(kernel, minBlockOrder, maxBlockOrder, ctx, np.float64)
+    return PartitionedConvolution(kernel, minBlockOrder, maxBlockOrder, ctx, np.float64, channels)
 
 
-def NewPartitionedConvolution32(kernel, minBlockOrder, maxBlockOrder, ctx=None):
+def NewPartitionedConvolution32(kernel, minBlockOrder, maxBlockOrder, ctx=None, channels=1):
     """NewPartitionedConvolution32 -- partitioned.go:340."""
-    return PartitionedConvolution(kernel, minBlockOrder, maxBlockOrder, ctx, np.float32)
+    return PartitionedConvolution(kernel, minBlockOrder, maxBlockOrder, ctx, np.float32, channels)
+
+
+def NewConvolutionReverb(kernel, minBlockOrder, ctx=None, channels=1, dtype=np.float64):
+    """NewConvolutionReverb -- dsp/effects/reverb/convolution.go:27 (maxBlockOrder 13, wet = dry = 1): use SetWetDry and
+    ProcessInPlace on the returned engine."""
+    return PartitionedConvolution(kernel, minBlockOrder, 13, ctx, dtype, channels)
 
 
 class _Streaming(_Plan):

@@ -293,6 +293,8 @@ struct adsp_plan {
     int hist_cur = 0;
     long long hist_len = 0;
     DevBuf blk_in, blk_out;
+    FdlEngine *fdl = nullptr;   // frequency-domain delay-line engine (partitioned plans with minBlockOrder >= 3)
+    int channels = 1;
     // CUDA-graph cache of whole device-resident calls (same pointers/sizes as a previous call)
     struct GraphEntry {
         const void *in; void *out; long long n, channels, in_stride, out_stride;
@@ -903,6 +905,7 @@ void adsp_plan_destroy(adsp_plan *p) {
     for (auto &g : p->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (auto &kv : p->extra64) kv.second.destroy();
     for (auto &kv : p->extra32) kv.second.destroy();
+    if (p->fdl) fdl_destroy(p->fdl);
     p->d_kernel.release();
     p->hist[0].release(); p->hist[1].release(); p->blk_in.release(); p->blk_out.release();
     delete p;
@@ -1085,7 +1088,7 @@ adsp_status part_process(adsp_plan *p, const T *in, int64_t n, T *out) {
 }
 
 template <typename T>
-adsp_status part_create(adsp_ctx *ctx, const T *kernel, int64_t K, int min_order, int max_order, adsp_plan **out) {
+adsp_status part_create(adsp_ctx *ctx, const T *kernel, int64_t K, int min_order, int max_order, int channels, adsp_plan **out) {
     if (!out) return ADSP_ERR_INVALID_ARG;
     *out = nullptr;
     if (!ctx) return ADSP_ERR_INVALID_ARG;
@@ -1093,18 +1096,31 @@ adsp_status part_create(adsp_ctx *ctx, const T *kernel, int64_t K, int min_order
     if (min_order < 1) { set_error("conv: invalid block order: minBlockOrder must be >= 1"); return ADSP_ERR_INVALID_BLOCK_ORDER; }
     if (max_order < min_order) { set_error("conv: invalid block order: maxBlockOrder must be >= minBlockOrder"); return ADSP_ERR_INVALID_BLOCK_ORDER; }
     if (min_order > 24) { set_error("conv: invalid block order: too large"); return ADSP_ERR_INVALID_BLOCK_ORDER; }
+    if (channels < 1) { set_error("partitioned: channels must be >= 1"); return ADSP_ERR_INVALID_ARG; }
     std::lock_guard<std::mutex> lk(ctx->mu);
     ADSP_CUDA(cudaSetDevice(ctx->device));
     adsp_plan *p = new adsp_plan();
-    p->ctx = ctx; p->kind = PLAN_PART; p->prec = sizeof(T) == 8 ? ADSP_F64 : ADSP_F32; p->K = K;
+    p->ctx = ctx; p->kind = PLAN_PART; p->prec = sizeof(T) == 8 ? ADSP_F64 : ADSP_F32; p->K = K; p->channels = channels;
     p->latency = 1 << min_order; p->min_order = min_order; p->max_order = max_order;
     const long long padded = ((K + p->latency - 1) / p->latency) * p->latency;
     p->stages = partition_layout(padded, min_order, max_order);
     p->hist_len = K - 1 + p->latency;
-    adsp_status st = plan_build<T>(p, kernel);
-    for (int i = 0; i < 2 && st == ADSP_OK; i++) {
-        st = p->hist[i].reserve((size_t)p->hist_len * sizeof(T));
-        if (st == ADSP_OK && cudaMemsetAsync(p->hist[i].p, 0, (size_t)p->hist_len * sizeof(T), ctx->main) != cudaSuccess) st = ADSP_ERR_CUDA;
+    adsp_status st = ADSP_OK;
+    const bool use_fdl = fdl_supported(min_order) && env_ll("ADSP_NO_FDL", 0) == 0;
+    if (use_fdl) {
+        // streaming engine on a frequency-domain delay line (fdl.cu); the IR only has to reach the device
+        st = p->d_kernel.reserve((size_t)K * sizeof(T));
+        if (st == ADSP_OK && cudaMemcpyAsync(p->d_kernel.p, kernel, (size_t)K * sizeof(T), cudaMemcpyHostToDevice, ctx->main) != cudaSuccess) st = ADSP_ERR_CUDA;
+        if (st == ADSP_OK && cudaStreamSynchronize(ctx->main) != cudaSuccess) st = ADSP_ERR_CUDA;
+        p->ch = choose_fft(K);
+        if (st == ADSP_OK) st = fdl_create(ctx, p->d_kernel.p, K, min_order, max_order, channels, p->prec, &p->fdl);
+    } else {
+        if (channels != 1) { set_error("partitioned: multi-channel plans need minBlockOrder >= 3"); st = ADSP_ERR_INVALID_ARG; }
+        if (st == ADSP_OK) st = plan_build<T>(p, kernel);
+        for (int i = 0; i < 2 && st == ADSP_OK; i++) {
+            st = p->hist[i].reserve((size_t)p->hist_len * sizeof(T));
+            if (st == ADSP_OK && cudaMemsetAsync(p->hist[i].p, 0, (size_t)p->hist_len * sizeof(T), ctx->main) != cudaSuccess) st = ADSP_ERR_CUDA;
+        }
     }
     if (st != ADSP_OK) { adsp_plan_destroy(p); return st; }
     *out = p;
@@ -1117,8 +1133,24 @@ extern "C" {
 
 adsp_status adsp_partitioned_create(adsp_ctx *ctx, const void *kernel, int64_t K, int min_order, int max_order,
                                     adsp_precision prec, adsp_plan **out) {
-    if (prec == ADSP_F64) return part_create<double>(ctx, (const double *)kernel, K, min_order, max_order, out);
-    return part_create<float>(ctx, (const float *)kernel, K, min_order, max_order, out);
+    if (prec == ADSP_F64) return part_create<double>(ctx, (const double *)kernel, K, min_order, max_order, 1, out);
+    return part_create<float>(ctx, (const float *)kernel, K, min_order, max_order, 1, out);
+}
+
+adsp_status adsp_partitioned_create_batch(adsp_ctx *ctx, const void *kernel, int64_t K, int min_order, int max_order, int channels,
+                                          adsp_precision prec, adsp_plan **out) {
+    if (prec == ADSP_F64) return part_create<double>(ctx, (const double *)kernel, K, min_order, max_order, channels, out);
+    return part_create<float>(ctx, (const float *)kernel, K, min_order, max_order, channels, out);
+}
+
+static adsp_status part_batch(adsp_plan *p, const void *in, int64_t n, int64_t in_stride, void *out, int64_t out_stride, bool host, bool mix) {
+    if (!p || p->kind != PLAN_PART || !p->fdl) return ADSP_ERR_INVALID_ARG;
+    if (n <= 0) return ADSP_OK;
+    if (!in || !out) return ADSP_ERR_INVALID_ARG;
+    if (p->channels > 1 && (in_stride < n || out_stride < n)) { set_error("partitioned: stride shorter than the block"); return ADSP_ERR_INVALID_ARG; }
+    std::lock_guard<std::mutex> lk(p->ctx->mu);
+    ADSP_CUDA(cudaSetDevice(p->ctx->device));
+    return fdl_process(p->fdl, in, n, in_stride, out, out_stride, host, mix);
 }
 
 adsp_status adsp_partitioned_process_block(adsp_plan *p, const void *in, int64_t n, void *out, int64_t n_out) {
@@ -1129,14 +1161,47 @@ adsp_status adsp_partitioned_process_block(adsp_plan *p, const void *in, int64_t
     }
     if (n <= 0) return ADSP_OK;
     if (!in || !out) return ADSP_ERR_INVALID_ARG;
+    if (p->fdl) {
+        if (p->channels != 1) { set_error("partitioned: use the batch entry points on a multi-channel plan"); return ADSP_ERR_INVALID_ARG; }
+        return part_batch(p, in, n, n, out, n, true, false);
+    }
     std::lock_guard<std::mutex> lk(p->ctx->mu);
     ADSP_CUDA(cudaSetDevice(p->ctx->device));
     if (p->prec == ADSP_F64) return part_process<double>(p, (const double *)in, n, (double *)out);
     return part_process<float>(p, (const float *)in, n, (float *)out);
 }
 
+adsp_status adsp_partitioned_process_block_batch(adsp_plan *p, const void *in, int64_t n, int64_t in_stride, void *out, int64_t out_stride) {
+    return part_batch(p, in, n, in_stride, out, out_stride, true, false);
+}
+adsp_status adsp_partitioned_process_block_batch_device(adsp_plan *p, const void *in, int64_t n, int64_t in_stride, void *out,
+                                                        int64_t out_stride) {
+    return part_batch(p, in, n, in_stride, out, out_stride, false, false);
+}
+adsp_status adsp_partitioned_set_wet_dry(adsp_plan *p, double wet, double dry) {
+    if (!p || p->kind != PLAN_PART || !p->fdl) return ADSP_ERR_INVALID_ARG;
+    fdl_set_wet_dry(p->fdl, wet, dry);
+    return ADSP_OK;
+}
+adsp_status adsp_partitioned_process_in_place_batch(adsp_plan *p, void *block, int64_t n, int64_t stride) {
+    return part_batch(p, block, n, stride, block, stride, true, true);
+}
+adsp_status adsp_partitioned_process_in_place_batch_device(adsp_plan *p, void *block, int64_t n, int64_t stride) {
+    return part_batch(p, block, n, stride, block, stride, false, true);
+}
+int adsp_partitioned_channels(const adsp_plan *p) { return (p && p->kind == PLAN_PART) ? p->channels : 0; }
+int adsp_partitioned_internal_stage_count(const adsp_plan *p) { return (p && p->fdl) ? fdl_stage_count(p->fdl) : 0; }
+adsp_status adsp_partitioned_internal_stage_info(const adsp_plan *p, int index, int *part_size, int *count, int64_t *ir_offset) {
+    if (!p || !p->fdl || index < 0 || index >= fdl_stage_count(p->fdl)) return ADSP_ERR_STAGE_INDEX;
+    long long off = 0;
+    fdl_stage_info(p->fdl, index, part_size, count, &off);
+    if (ir_offset) *ir_offset = off;
+    return ADSP_OK;
+}
+
 void adsp_plan_reset(adsp_plan *p) {
     if (!p) return;
+    if (p->fdl) { cudaSetDevice(p->ctx->device); fdl_reset(p->fdl); return; }   // partitioned.go:399-407
     if (p->kind == PLAN_PART || p->kind == PLAN_STREAM) {                    // partitioned.go:399-407, streaming_overlap_save.go:167-169
         cudaSetDevice(p->ctx->device);
         const size_t es = p->prec == ADSP_F64 ? 8 : 4;

@@ -16,6 +16,7 @@
 #include "../../include/algodsp_cuda.h"
 #include "conv_kernels_pf.cuh"
 #include "conv_kernels_mr.cuh"
+#include "conv_kernels_il.cuh"
 
 namespace adsp {
 
@@ -141,6 +142,21 @@ adsp_status fft_correlate_pairs_device(adsp_ctx *ctx, const T *a, long long n, l
 template <typename T>
 adsp_status direct_device(adsp_ctx *ctx, const T *d_a, long long n, long long a_stride, const T *d_b, long long m,
                           long long b_stride, long long batch, T *d_out, long long out_stride);
+
+// Streaming partitioned convolution on a frequency-domain delay line, many channels per launch (fdl.cu)
+struct FdlEngine;
+bool fdl_supported(int min_order);
+adsp_status fdl_create(adsp_ctx *ctx, const void *d_kernel, long long K, int min_order, int max_order, int channels,
+                       adsp_precision prec, FdlEngine **out);
+void fdl_destroy(FdlEngine *e);
+adsp_status fdl_reset(FdlEngine *e);
+void fdl_set_wet_dry(FdlEngine *e, double wet, double dry);
+int fdl_channels(const FdlEngine *e);
+int fdl_stage_count(const FdlEngine *e);
+void fdl_stage_info(const FdlEngine *e, int i, int *part, int *count, long long *off);
+// in/out: `channels` rows of n samples (strides in elements), host or device pointers; mix: out = dry*in + wet*y
+adsp_status fdl_process(FdlEngine *e, const void *in, long long n, long long in_stride, void *out, long long out_stride, bool host_ptrs,
+                        bool mix);
 
 inline void count_launch(adsp_ctx *ctx, int n = 1) { ctx->launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 

@@ -395,6 +395,38 @@ static adsp_status launch_rows_pf(adsp_ctx *ctx, cudaStream_t st, int L, cpx<T> 
     }
 }
 
+// ------------------------------------------------------------------ interleaved (two tiles per thread) rows
+template <typename T, int L>
+static adsp_status launch_rows_il_t(adsp_ctx *ctx, cudaStream_t st, cpx<T> *scratch, const cpx<T> *H, int N1, const cpx<T> *tw,
+                                    int pairs) {
+    constexpr int THREADS = rows_cta_threads(L);
+    constexpr int ROWS = THREADS / FftShape<L>::TPF;
+    const size_t smem = (2 * (size_t)ROWS * L + FftShape<L>::TW_ENTRIES) * sizeof(cpx<T>);
+    static AttrOnce once;
+    if (once.need(ctx->device)) ADSP_TRY(set_smem(fftconv_rows_il<T, L>, smem));
+    const int ntiles = (N1 / ROWS) * pairs;
+    int grid = (ntiles + 1) / 2;
+    const long long k = env_ll("ADSP_IL_TILEPAIRS_PER_CTA", 1);
+    if (k > 1) grid = (int)std::max<long long>(std::min<long long>(grid, (long long)ctx->sm_count * 2), (grid + k - 1) / k);
+    LaunchTimer lt(ctx, st, KK_ROWS);
+    fftconv_rows_il<T, L><<<grid, THREADS, smem, st>>>(scratch, H, N1, tw, ntiles);
+    count_launch(ctx);
+    ADSP_CUDA(cudaGetLastError());
+    return ADSP_OK;
+}
+
+template <typename T>
+static adsp_status launch_rows_il(adsp_ctx *ctx, cudaStream_t st, int L, cpx<T> *scratch, const cpx<T> *H, int N1,
+                                  const cpx<T> *tw, int pairs) {
+    switch (L) {
+    case 1024: return launch_rows_il_t<T, 1024>(ctx, st, scratch, H, N1, tw, pairs);
+    case 2048: return launch_rows_il_t<T, 2048>(ctx, st, scratch, H, N1, tw, pairs);
+    case 4096: return launch_rows_il_t<T, 4096>(ctx, st, scratch, H, N1, tw, pairs);
+    default: set_error("unsupported row FFT length (interleaved rows)"); return ADSP_ERR_INVALID_ARG;
+    }
+}
+static bool il_supported(int N2) { return N2 == 1024 || N2 == 2048 || N2 == 4096; }
+
 // ------------------------------------------------------------------ stage-merged kernel
 #define ADSP_STAGES_AVAILABLE (ADSP_COLS_CTA_THREADS == 128 && ADSP_ROWS_SMALL_CTA)
 #if ADSP_STAGES_AVAILABLE
@@ -714,6 +746,7 @@ adsp_status FftConv<T>::run(const T *d_x, long long n, long long channels, long 
     const int tiles_r = ch.N1 / (256 / (ch.N2 / 16) > 0 ? 256 / (ch.N2 / 16) : 1);
     const bool use_pp = ch.P <= 1 && pp_supported(ch.N1, ch.N2) && env_ll("ADSP_PINGPONG", 0) != 0 && npairs * (long long)tiles_r >= conc;
     const bool use_pf = ch.P <= 1 && !use_pp && pf_supported(ch.N1, ch.N2) && env_ll("ADSP_PF", 0) != 0;
+    const bool use_il = il_supported(ch.N2) && env_ll("ADSP_IL", 0) != 0;
     int nstreams = (int)env_ll("ADSP_STREAMS", 4);
     if (nstreams < 1) nstreams = 1;
     if (nstreams > kWorkerStreams) nstreams = kWorkerStreams;
@@ -767,7 +800,8 @@ adsp_status FftConv<T>::run(const T *d_x, long long n, long long channels, long 
             continue;
         }
         ADSP_TRY(launch_cols_any<T>(ctx, st, ch, false, g, d_x, d_y, sl, tw_cols, tw_hi, tw_lo, pair0, gp));
-        ADSP_TRY((launch_rows<T, false>(ctx, st, ch.N2, sl, H, (cpx<T> *)nullptr, (T)0, ch.N1, tw_rows, gp)));
+        if (use_il) ADSP_TRY(launch_rows_il<T>(ctx, st, ch.N2, sl, H, ch.N1, tw_rows, gp));
+        else ADSP_TRY((launch_rows<T, false>(ctx, st, ch.N2, sl, H, (cpx<T> *)nullptr, (T)0, ch.N1, tw_rows, gp)));
         ADSP_TRY(launch_cols_any<T>(ctx, st, ch, true, g, d_x, d_y, sl, tw_cols, tw_hi, tw_lo, pair0, gp));
     }
     if (nslots > 1) {

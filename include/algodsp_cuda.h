@@ -176,6 +176,27 @@ ADSP_API int adsp_partitioned_latency(const adsp_plan *plan);      /* partitione
 ADSP_API int adsp_partitioned_stage_count(const adsp_plan *plan);  /* partitioned.go:420 */
 ADSP_API adsp_status adsp_partitioned_stage_info(const adsp_plan *plan, int index, int *part_size, int *block_count); /* :426 */
 
+/* Many channels per launch: `channels` independent streams through one IR, each row behaving exactly
+ * like its own PartitionedConvolution (partitioned.go:348-396): row c of `out` = full linear convolution of row c
+ * of `in`, delayed by Latency(), arbitrary n per call.  Runs on a device-resident frequency-domain delay line with
+ * a fused spectral multiply-accumulate (csrc/fdl.cu); needs min_block_order >= 3.  Strides in elements. */
+ADSP_API adsp_status adsp_partitioned_create_batch(adsp_ctx *, const void *kernel, int64_t kernel_len, int min_block_order,
+                                                   int max_block_order, int channels, adsp_precision prec, adsp_plan **out);
+ADSP_API adsp_status adsp_partitioned_process_block_batch(adsp_plan *plan, const void *in, int64_t n, int64_t in_stride,
+                                                          void *out, int64_t out_stride);
+ADSP_API adsp_status adsp_partitioned_process_block_batch_device(adsp_plan *plan, const void *in_dev, int64_t n, int64_t in_stride,
+                                                                 void *out_dev, int64_t out_stride);
+/* ConvolutionReverb.SetWetDry / ProcessInPlace (dsp/effects/reverb/convolution.go:51-83), the mix fused into the
+ * output kernel: block[c][i] = dry * block[c][i] + wet * reverb(block[c])[i]. */
+ADSP_API adsp_status adsp_partitioned_set_wet_dry(adsp_plan *plan, double wet, double dry);
+ADSP_API adsp_status adsp_partitioned_process_in_place_batch(adsp_plan *plan, void *block, int64_t n, int64_t stride);
+ADSP_API adsp_status adsp_partitioned_process_in_place_batch_device(adsp_plan *plan, void *block_dev, int64_t n, int64_t stride);
+ADSP_API int adsp_partitioned_channels(const adsp_plan *plan);
+/* Internal stage layout of the delay-line engine (diagnostic; StageCount/StageInfo report the reference's layout). */
+ADSP_API int adsp_partitioned_internal_stage_count(const adsp_plan *plan);
+ADSP_API adsp_status adsp_partitioned_internal_stage_info(const adsp_plan *plan, int index, int *part_size, int *count,
+                                                          int64_t *ir_offset);
+
 /* ---------------------------------------------------------------- fixed-block streaming convolvers
  * NewStreamingOverlapAdd(kernel, blockSize) streaming_overlap_add.go:41 / NewStreamingOverlapSave
  * streaming_overlap_save.go:44 (+ the float32 twins): ProcessBlock(input[blockSize]) -> output[blockSize],
