@@ -29,6 +29,7 @@ namespace {
 
 constexpr int FDL_MAX_B = 2048;          // largest partition: 4096-point transforms fit one CTA (fft_core.cuh)
 constexpr long long FDL_CHUNK = 16384;   // a call is processed in chunks of at most this many samples
+constexpr int FDL_SPLIT_MIN_COUNT = 8;   // stages with at least this many partitions use the bin-tiled MAC kernel
 
 template <int L2> struct FdlShape {
     static constexpr int TPF = L2 / 16;                                   // threads per transform
@@ -124,7 +125,10 @@ fdl_mac_inverse(const cpx<T> *__restrict__ fdl, const cpx<T> *__restrict__ H, in
         for (int q0 = 0; q0 < 16; q0 += 4) {          // 4 + 4 loads in flight per step keeps the kernel inside 128 registers
             C xv[4], hv[4];
 #pragma unroll
-            for (int q = 0; q < 4; q++) { xv[q] = __ldcg(&xr[(q0 + q) * TPF]); hv[q] = __ldg(&hr[(q0 + q) * TPF]); }
+            for (int q = 0; q < 4; q++) {
+                xv[q] = __ldcg(&xr[(q0 + q) * TPF]);
+                if (H) hv[q] = __ldg(&hr[(q0 + q) * TPF]); else { hv[q].x = (T)1; hv[q].y = (T)0; }   // H == null: Y is already summed
+            }
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 e[q0 + q].x += xv[q].x * hv[q].x - xv[q].y * hv[q].y;
@@ -150,6 +154,52 @@ fdl_mac_inverse(const cpx<T> *__restrict__ fdl, const cpx<T> *__restrict__ H, in
                 if (cb < channels) ab[t] += e[q].y;
             }
         }
+    }
+}
+
+// Spectral multiply-accumulate of a long stage, tiled over BINS instead of firings: one thread owns one bin of FT
+// consecutive firings of a channel pair,
+//     Y_m[k] = sum_{p < count} X_{m-p}[k] * H_p[k],   m = mA .. mA + FT - 1,
+// walks the delay line once (count + FT - 1 slots, newest first) and keeps the FT spectrum values each slot meets
+// in a shift register -- every delay-line value is loaded once per FT firings instead of once per firing, and a
+// single firing still spreads over pairs * L2/128 CTAs (a real-time block is one firing: 32 pairs alone would
+// leave most SMs idle).  Y goes to a small scratch; fdl_mac_inverse (H == null) then inverts and accumulates it.
+template <typename T, int FT>
+__global__ void __launch_bounds__(128)
+fdl_mac_bins(const cpx<T> *__restrict__ fdl, const cpx<T> *__restrict__ H, int count, int ring, long long m0, int nfire, int L2,
+             cpx<T> *__restrict__ Y, int yring) {
+    using C = cpx<T>;
+    const int bin = blockIdx.x * 128 + threadIdx.x;
+    const int pair = blockIdx.y;
+    const long long mA = m0 + (long long)blockIdx.z * FT;
+    const C *ring_base = fdl + (size_t)pair * ring * L2 + bin;
+    const C *hb = H + bin;
+    C acc[FT], hw[FT];
+#pragma unroll
+    for (int f = 0; f < FT; f++) { acc[f].x = acc[f].y = (T)0; hw[f].x = hw[f].y = (T)0; }
+    const long long s_hi = mA + FT - 1;
+    long long s_lo = mA - count + 1;
+    if (s_lo < 0) s_lo = 0;                                  // blocks before the stream start are zero
+    int slot = (int)(s_hi % ring);
+    int ptop = 0;                                            // spectrum index met by the newest firing at this slot
+#pragma unroll 4
+    for (long long sidx = s_hi; sidx >= s_lo; sidx--) {
+#pragma unroll
+        for (int f = 0; f < FT - 1; f++) hw[f] = hw[f + 1];
+        if (ptop < count) hw[FT - 1] = __ldg(&hb[(size_t)ptop * L2]); else { hw[FT - 1].x = (T)0; hw[FT - 1].y = (T)0; }
+        const C x = __ldcg(&ring_base[(size_t)slot * L2]);
+#pragma unroll
+        for (int f = 0; f < FT; f++) {
+            acc[f].x += x.x * hw[f].x - x.y * hw[f].y;
+            acc[f].y += x.x * hw[f].y + x.y * hw[f].x;
+        }
+        ptop++;
+        slot = (slot == 0) ? ring - 1 : slot - 1;
+    }
+#pragma unroll
+    for (int f = 0; f < FT; f++) {
+        const long long m = mA + f;
+        if (m < m0 + nfire) Y[((size_t)pair * yring + (size_t)(m % yring)) * L2 + bin] = acc[f];
     }
 }
 
@@ -188,7 +238,7 @@ struct FdlEngine {
     std::vector<void *> d_H, d_fdl;           // per stage: spectra [count][2B], delay line [pairs][ring][2B]
     std::vector<const void *> d_tw;           // per stage: twiddle table of the 2B-point transform
     long long HX = 0;                         // input history kept in front of each chunk (2*B_max)
-    DevBuf xbuf, acc, d_io_in, d_io_out;
+    DevBuf xbuf, xbuf_alt, acc, d_io_in, d_io_out, yscratch;   // xbuf / xbuf_alt: input rows [history | chunk], ping-pong
     long long acc_len = 0;
     long long pos = 0;                        // samples consumed so far
     double wet = 1.0, dry = 1.0;
@@ -258,6 +308,7 @@ template <typename T> adsp_status fdl_build(FdlEngine *e, const T *d_kernel) {
     e->d_H.assign(ns, nullptr); e->d_fdl.assign(ns, nullptr); e->d_tw.assign(ns, nullptr);
     const long long xstride = e->HX + FDL_CHUNK;
     ADSP_TRY(e->xbuf.reserve((size_t)xstride * (size_t)(2 * e->pairs) * sizeof(T)));
+    ADSP_TRY(e->xbuf_alt.reserve((size_t)xstride * (size_t)(2 * e->pairs) * sizeof(T)));
     ADSP_TRY(e->acc.reserve((size_t)e->acc_len * (size_t)(2 * e->pairs) * sizeof(T)));
     for (size_t s = 0; s < ns; s++) {
         const StageGeom &g = e->stages[s];
@@ -301,6 +352,7 @@ template <typename T> adsp_status fdl_reset_t(FdlEngine *e) {
     for (size_t s = 0; s < e->stages.size(); s++)
         ADSP_CUDA(cudaMemsetAsync(e->d_fdl[s], 0, (size_t)e->pairs * e->stages[s].ring * 2 * e->stages[s].B * sizeof(cpx<T>), ctx->main));
     ADSP_CUDA(cudaMemsetAsync(e->xbuf.p, 0, e->xbuf.cap, ctx->main));
+    ADSP_CUDA(cudaMemsetAsync(e->xbuf_alt.p, 0, e->xbuf_alt.cap, ctx->main));
     ADSP_CUDA(cudaMemsetAsync(e->acc.p, 0, e->acc.cap, ctx->main));
     e->pos = 0;
     ADSP_CUDA(cudaStreamSynchronize(ctx->main));
@@ -321,27 +373,35 @@ adsp_status fdl_chunk(FdlEngine *e, long long n, const T *d_in, long long in_str
         if (nf <= 0) continue;
         FwdArgs fa{e->xbuf.p, xstride, t0, e->channels, e->pairs, m_first, (int)nf, g.ring, e->d_fdl[s], e->d_tw[s]};
         ADSP_TRY(fdl_forward_any<T>(ctx, 2 * g.B, fa));
-        MacArgs ma{e->d_fdl[s], e->d_H[s], g.count, g.ring, m_first, (int)nf, g.off, e->acc.p, e->acc_len, e->channels, e->pairs, e->d_tw[s]};
-        ADSP_TRY(fdl_mac_any<T>(ctx, 2 * g.B, ma));
+        if (g.count >= FDL_SPLIT_MIN_COUNT && 2 * g.B >= 128) {
+            // long stage: bin-tiled MAC into a scratch spectrum, then the inverse kernel on Y (H == null, one "tap")
+            const int L2 = 2 * g.B, yring = (int)nf;
+            ADSP_TRY(e->yscratch.reserve((size_t)e->pairs * (size_t)yring * L2 * sizeof(cpx<T>)));
+            const int FT = nf >= 4 ? 4 : (nf >= 2 ? 2 : 1);
+            dim3 grid((unsigned)(L2 / 128), (unsigned)e->pairs, (unsigned)((nf + FT - 1) / FT));
+            {
+                LaunchTimer lt(ctx, ctx->main, KK_OTHER);
+                if (FT == 4) fdl_mac_bins<T, 4><<<grid, 128, 0, ctx->main>>>((const cpx<T> *)e->d_fdl[s], (const cpx<T> *)e->d_H[s], g.count, g.ring, m_first, (int)nf, L2, (cpx<T> *)e->yscratch.p, yring);
+                else if (FT == 2) fdl_mac_bins<T, 2><<<grid, 128, 0, ctx->main>>>((const cpx<T> *)e->d_fdl[s], (const cpx<T> *)e->d_H[s], g.count, g.ring, m_first, (int)nf, L2, (cpx<T> *)e->yscratch.p, yring);
+                else fdl_mac_bins<T, 1><<<grid, 128, 0, ctx->main>>>((const cpx<T> *)e->d_fdl[s], (const cpx<T> *)e->d_H[s], g.count, g.ring, m_first, (int)nf, L2, (cpx<T> *)e->yscratch.p, yring);
+                count_launch(ctx);
+            }
+            MacArgs ma{e->yscratch.p, nullptr, 1, yring, m_first, (int)nf, g.off, e->acc.p, e->acc_len, e->channels, e->pairs, e->d_tw[s]};
+            ADSP_TRY(fdl_mac_any<T>(ctx, L2, ma));
+        } else {
+            MacArgs ma{e->d_fdl[s], e->d_H[s], g.count, g.ring, m_first, (int)nf, g.off, e->acc.p, e->acc_len, e->channels, e->pairs, e->d_tw[s]};
+            ADSP_TRY(fdl_mac_any<T>(ctx, 2 * g.B, ma));
+        }
     }
     dim3 grid((unsigned)((n + 255) / 256), (unsigned)e->channels);
     fdl_emit<T><<<grid, 256, 0, ctx->main>>>((T *)e->acc.p, e->acc_len, e->acc_len - 1, e->pos - e->latency, n, d_in, in_stride, d_out,
                                              out_stride, mix ? 1 : 0, (T)e->wet, (T)e->dry);
     count_launch(ctx);
-    // slide the input history: xbuf[.][0, HX) <- xbuf[.][n, n + HX)   (ranges overlap when n < HX: go through the tail copy
-    // in ascending order, which cudaMemcpy2D does not promise -> use a scratch-free two-step only when they overlap)
+    // keep the last HX input samples as the history of the next chunk: one strided copy into the other buffer
     T *xb = (T *)e->xbuf.p;
-    if (n >= e->HX) {
-        ADSP_CUDA(cudaMemcpy2DAsync(xb, (size_t)xstride * sizeof(T), xb + n, (size_t)xstride * sizeof(T), (size_t)e->HX * sizeof(T),
-                                    (size_t)e->channels, cudaMemcpyDeviceToDevice, ctx->main));
-    } else {
-        // move in pieces of n (each piece's source and destination are disjoint)
-        for (long long o = 0; o < e->HX; o += n) {
-            const long long len = std::min(n, e->HX - o);
-            ADSP_CUDA(cudaMemcpy2DAsync(xb + o, (size_t)xstride * sizeof(T), xb + o + n, (size_t)xstride * sizeof(T), (size_t)len * sizeof(T),
-                                        (size_t)e->channels, cudaMemcpyDeviceToDevice, ctx->main));
-        }
-    }
+    ADSP_CUDA(cudaMemcpy2DAsync(e->xbuf_alt.p, (size_t)xstride * sizeof(T), xb + n, (size_t)xstride * sizeof(T), (size_t)e->HX * sizeof(T),
+                                (size_t)e->channels, cudaMemcpyDeviceToDevice, ctx->main));
+    std::swap(e->xbuf, e->xbuf_alt);
     e->pos += n;
     ADSP_CUDA(cudaGetLastError());
     return ADSP_OK;
@@ -351,8 +411,8 @@ template <typename T>
 adsp_status fdl_process_t(FdlEngine *e, const T *in, long long n, long long in_stride, T *out, long long out_stride, bool host, bool mix) {
     adsp_ctx *ctx = e->ctx;
     const long long xstride = e->HX + FDL_CHUNK;
-    T *xb = (T *)e->xbuf.p;
     for (long long o = 0; o < n; o += FDL_CHUNK) {
+        T *xb = (T *)e->xbuf.p;                 // ping-pongs with xbuf_alt every chunk
         const long long len = std::min(FDL_CHUNK, n - o);
         const cudaMemcpyKind kin = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
         ADSP_CUDA(cudaMemcpy2DAsync(xb + e->HX, (size_t)xstride * sizeof(T), in + o, (size_t)in_stride * sizeof(T), (size_t)len * sizeof(T),
@@ -415,7 +475,7 @@ void fdl_destroy(FdlEngine *e) {
     if (!e) return;
     for (void *p : e->d_H) if (p) cudaFree(p);
     for (void *p : e->d_fdl) if (p) cudaFree(p);
-    e->xbuf.release(); e->acc.release(); e->d_io_in.release(); e->d_io_out.release();
+    e->xbuf.release(); e->xbuf_alt.release(); e->acc.release(); e->d_io_in.release(); e->d_io_out.release(); e->yscratch.release();
     delete e;
 }
 
