@@ -162,4 +162,22 @@ public:
 };
 inline PartitionedConvolution NewPartitionedConvolution(const Vec &k, int mn, int mx, Context &c = Context::Default()) { return PartitionedConvolution(k, mn, mx, c); }
 
+// ConvolutionReverb -- dsp/effects/reverb/convolution.go:17-101, extended to `channels` independent streams per call
+// (rows of a [channels][n] block with the given stride); channels = 1 is the reference's mono effect.
+class ConvolutionReverb : public Plan {
+public:
+    ConvolutionReverb(const Vec &kernel, int minBlockOrder, int channels = 1, Context &c = Context::Default()) {   // :27 (maxBlockOrder 13)
+        check(adsp_partitioned_create_batch(c.handle(), kernel.data(), (int64_t)kernel.size(), minBlockOrder, 13, channels, ADSP_F64, &h_));
+    }
+    void SetWetDry(double wet, double dry) { check(adsp_partitioned_set_wet_dry(h_, wet, dry)); }                    // :51
+    void ProcessInPlace(Vec &block) {                                                                              // :60
+        const int64_t ch = adsp_partitioned_channels(h_);
+        check(adsp_partitioned_process_in_place_batch(h_, block.data(), (int64_t)block.size() / ch, (int64_t)block.size() / ch));
+    }
+    int Latency() const { return adsp_partitioned_latency(h_); }                                                   // :98
+};
+inline ConvolutionReverb NewConvolutionReverb(const Vec &k, int minBlockOrder, int channels = 1, Context &c = Context::Default()) {
+    return ConvolutionReverb(k, minBlockOrder, channels, c);
+}
+
 }  // namespace conv

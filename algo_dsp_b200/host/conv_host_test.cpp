@@ -46,6 +46,25 @@ int main() {
         try { conv::NewOverlapSave({0.25, 0.5, 0.25}, 100); EXPECT(false); }
         catch (const conv::Error &e) { EXPECT(conv::errors_is(e, conv::ErrInvalidBlockSize)); }
     }
+    {   // ConvolutionReverb: wet/dry in place equals dry*x + wet*(delayed convolution), convolution.go:60-83
+        Vec kernel(3000);
+        for (size_t i = 0; i < kernel.size(); i++) kernel[i] = std::pow(0.999, (double)i) * ((i % 7) ? 0.1 : -0.2);
+        Vec x(8000);
+        for (size_t i = 0; i < x.size(); i++) x[i] = std::sin(0.01 * (double)i) + ((i * 2654435761u) % 1000) / 1000.0 - 0.5;
+        auto rv = conv::NewConvolutionReverb(kernel, 7);
+        rv.SetWetDry(0.25, 0.5);
+        Vec blk = x;
+        rv.ProcessInPlace(blk);
+        Vec full = conv::OverlapSaveConvolve(x, kernel);
+        const int L = rv.Latency();
+        EXPECT(L == 128);
+        double mx = 0;
+        for (size_t i = 0; i < x.size(); i++) {
+            const double wet = (i >= (size_t)L) ? full[i - L] : 0.0;
+            mx = std::fmax(mx, std::fabs(blk[i] - (0.5 * x[i] + 0.25 * wet)));
+        }
+        EXPECT(mx <= 1e-10);
+    }
     std::printf("conv_host_test: ok\n");
     return 0;
 }

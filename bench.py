@@ -204,6 +204,17 @@ def other_configs(torch, conv, G, ctx, stream):
                                   "internal_fft": plan.internal_geometry()}
     plan.Close()
     del x, y
+    # config 3 as a real-time stream: 64 channels through the same 288k-tap IR in 8192- and 128-sample blocks, wet/dry mixed in
+    # place (ConvolutionReverb.ProcessInPlace) on the device-resident frequency-domain delay line
+    rv = conv.NewConvolutionReverb(G.decaying_ir(K), 7, ctx=ctx, channels=64)
+    rv.SetWetDry(0.3, 0.7)
+    stream_res = {"channels": 64, "latency_samples": rv.Latency(), "internal_stages": rv.internal_stages()}
+    for nblk in (8192, 128):
+        xb = torch.rand((64, nblk), device="cuda", dtype=torch.float64) * 2 - 1
+        ms = timeit(lambda: lib.adsp_partitioned_process_in_place_batch_device(rv._h, C.c_void_p(xb.data_ptr()), nblk, nblk), iters=50)
+        stream_res[f"block_{nblk}"] = {"ms_per_call": ms, "samples_per_s": 64 * nblk / ms * 1e3, "x_realtime_48k": nblk / 48000.0 / (ms * 1e-3)}
+    out["config3_streaming_reverb_288k"] = stream_res
+    rv.Close()
     # config 4: sweep/response correlation + peak lag, 16 of the 1024 pairs x 2^20
     pairs, n = 16, 1 << 20
     sweep = G.log_sweep(n)

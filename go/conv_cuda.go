@@ -215,5 +215,48 @@ func (os *OverlapSave) ProcessTo(output, input []float64) error {
 	return statusErr(C.adsp_plan_process(os.plan, unsafe.Pointer(ptr(input)), C.int64_t(len(input)), unsafe.Pointer(ptr(output)), C.int64_t(len(output))))
 }
 
+// ConvolutionReverb backed by the device-resident frequency-domain delay line -- the reference type
+// dsp/effects/reverb/convolution.go:17 keeps its API; `channels` > 1 is the GPU extension (rows of a block).
+type ConvolutionReverb struct {
+	plan     *C.adsp_plan
+	channels int
+}
+
+// NewConvolutionReverb -- convolution.go:27 (maxBlockOrder 13).
+func NewConvolutionReverb(kernel []float64, minBlockOrder, channels int) (*ConvolutionReverb, error) {
+	if len(kernel) == 0 {
+		return nil, errors.New("reverb: empty impulse response kernel")
+	}
+	c, err := context()
+	if err != nil {
+		return nil, err
+	}
+	var p *C.adsp_plan
+	if st := C.adsp_partitioned_create_batch(c, unsafe.Pointer(ptr(kernel)), C.int64_t(len(kernel)), C.int(minBlockOrder), 13,
+		C.int(channels), C.ADSP_F64, &p); st != C.ADSP_OK {
+		return nil, statusErr(st)
+	}
+	r := &ConvolutionReverb{plan: p, channels: channels}
+	runtime.SetFinalizer(r, func(r *ConvolutionReverb) { C.adsp_plan_destroy(r.plan) })
+	return r, nil
+}
+
+// SetWetDry -- convolution.go:51.
+func (r *ConvolutionReverb) SetWetDry(wet, dry float64) {
+	C.adsp_partitioned_set_wet_dry(r.plan, C.double(wet), C.double(dry))
+}
+
+// ProcessInPlace -- convolution.go:60; block holds `channels` rows of len(block)/channels samples.
+func (r *ConvolutionReverb) ProcessInPlace(block []float64) error {
+	if len(block) == 0 {
+		return nil
+	}
+	n := len(block) / r.channels
+	return statusErr(C.adsp_partitioned_process_in_place_batch(r.plan, unsafe.Pointer(ptr(block)), C.int64_t(n), C.int64_t(n)))
+}
+
+func (r *ConvolutionReverb) Reset()       { C.adsp_plan_reset(r.plan) }                      // convolution.go:88
+func (r *ConvolutionReverb) Latency() int { return int(C.adsp_partitioned_latency(r.plan)) } // convolution.go:98
+
 // OverlapAdd, PartitionedConvolution, CorrelateFFT, CorrelateNormalized, ... follow the same
 // pattern over adsp_overlap_add_create / adsp_partitioned_* / adsp_correlate_* (INTEGRATION.md).
