@@ -195,9 +195,15 @@ template <typename C> __device__ __forceinline__ void geometric16(C base, C rho,
     }
 }
 
+#ifndef ADSP_COLS_TC_512
+#define ADSP_COLS_TC_512 8      // 256-thread CTAs (3 per SM); 16 columns / 512 threads measured 9 % slower
+#endif
+#ifndef ADSP_COLS_TC_1024
+#define ADSP_COLS_TC_1024 4     // 256-thread CTAs; 8 columns / 512 threads measured 6 % slower
+#endif
 template <int N1> struct ColShape {
     static constexpr int TPF = N1 / 16;                         // threads per column transform
-    static constexpr int TC = (N1 <= 256) ? (ADSP_COLS_CTA_THREADS / TPF) : ((N1 == 512) ? 16 : 8);  // columns per tile
+    static constexpr int TC = (N1 <= 256) ? (ADSP_COLS_CTA_THREADS / TPF) : ((N1 == 512) ? ADSP_COLS_TC_512 : ADSP_COLS_TC_1024);  // columns per tile
     static constexpr int THREADS = TPF * TC;
     static constexpr int SMEM_ELEMS = N1 * TC;
     static constexpr int MIN_CTAS = (THREADS <= 128) ? ADSP_MIN_CTAS_128 : ((THREADS <= 256) ? 2 : 1);

@@ -303,6 +303,7 @@ static adsp_status launch_cols_any(adsp_ctx *ctx, cudaStream_t st, const FftChoi
     return launch_cols<T>(ctx, st, ch.N1, inverse, g, x, y, scratch, ch.N2, ch.lgN, tw, hi, lo, pair0, pairs);
 }
 
+#if ADSP_EXPERIMENTAL
 // ------------------------------------------------------------------ prefetching persistent kernels
 // grid = resident CTAs (occupancy x SMs, queried once per kernel and device), never more than tiles
 template <typename K> static adsp_status pf_grid(adsp_ctx *ctx, K kern, int threads, size_t smem, int ntiles, int *cache, int *grid) {
@@ -426,6 +427,8 @@ static adsp_status launch_rows_il(adsp_ctx *ctx, cudaStream_t st, int L, cpx<T> 
     }
 }
 static bool il_supported(int N2) { return N2 == 1024 || N2 == 2048 || N2 == 4096; }
+
+#endif  // ADSP_EXPERIMENTAL
 
 // ------------------------------------------------------------------ stage-merged kernel
 #define ADSP_STAGES_AVAILABLE (ADSP_COLS_CTA_THREADS == 128 && ADSP_ROWS_SMALL_CTA)
@@ -745,8 +748,12 @@ adsp_status FftConv<T>::run(const T *d_x, long long n, long long channels, long 
     const int conc = 2 * ctx->sm_count;   // tiles in flight
     const int tiles_r = ch.N1 / (256 / (ch.N2 / 16) > 0 ? 256 / (ch.N2 / 16) : 1);
     const bool use_pp = ch.P <= 1 && pp_supported(ch.N1, ch.N2) && env_ll("ADSP_PINGPONG", 0) != 0 && npairs * (long long)tiles_r >= conc;
+#if ADSP_EXPERIMENTAL
     const bool use_pf = ch.P <= 1 && !use_pp && pf_supported(ch.N1, ch.N2) && env_ll("ADSP_PF", 0) != 0;
     const bool use_il = il_supported(ch.N2) && env_ll("ADSP_IL", 0) != 0;
+#else
+    const bool use_pf = false, use_il = false;
+#endif
     int nstreams = (int)env_ll("ADSP_STREAMS", 4);
     if (nstreams < 1) nstreams = 1;
     if (nstreams > kWorkerStreams) nstreams = kWorkerStreams;
@@ -793,15 +800,20 @@ adsp_status FftConv<T>::run(const T *d_x, long long n, long long channels, long 
         bool done = false;
         if (use_pp) ADSP_TRY(launch_pp<T>(ctx, st, ch.N1, ch.N2, g, d_x, d_y, sl, H, ch.lgN, tw_rows, tw_cols, tw_hi, tw_lo, pair0, gp, &done));
         if (done) continue;
+#if ADSP_EXPERIMENTAL
         if (use_pf) {
             ADSP_TRY(launch_cols_pf<T>(ctx, st, ch.N1, false, g, d_x, d_y, sl, ch.N2, ch.lgN, tw_cols, tw_hi, tw_lo, pair0, gp));
             ADSP_TRY(launch_rows_pf<T>(ctx, st, ch.N2, sl, H, ch.N1, tw_rows, gp));
             ADSP_TRY(launch_cols_pf<T>(ctx, st, ch.N1, true, g, d_x, d_y, sl, ch.N2, ch.lgN, tw_cols, tw_hi, tw_lo, pair0, gp));
             continue;
         }
+#endif
         ADSP_TRY(launch_cols_any<T>(ctx, st, ch, false, g, d_x, d_y, sl, tw_cols, tw_hi, tw_lo, pair0, gp));
+#if ADSP_EXPERIMENTAL
         if (use_il) ADSP_TRY(launch_rows_il<T>(ctx, st, ch.N2, sl, H, ch.N1, tw_rows, gp));
-        else ADSP_TRY((launch_rows<T, false>(ctx, st, ch.N2, sl, H, (cpx<T> *)nullptr, (T)0, ch.N1, tw_rows, gp)));
+        else
+#endif
+        ADSP_TRY((launch_rows<T, false>(ctx, st, ch.N2, sl, H, (cpx<T> *)nullptr, (T)0, ch.N1, tw_rows, gp)));
         ADSP_TRY(launch_cols_any<T>(ctx, st, ch, true, g, d_x, d_y, sl, tw_cols, tw_hi, tw_lo, pair0, gp));
     }
     if (nslots > 1) {
