@@ -16,7 +16,7 @@ c_dp = C.POINTER(C.c_double)
 
 # status codes (adsp_status)
 OK, ERR_EMPTY_INPUT, ERR_EMPTY_KERNEL, ERR_LENGTH_MISMATCH, ERR_INVALID_BLOCK_SIZE, ERR_INVALID_BLOCK_ORDER, \
-    ERR_EMPTY_IR, ERR_STAGE_INDEX, ERR_INVALID_ARG, ERR_CUDA, ERR_OOM = range(11)
+    ERR_EMPTY_IR, ERR_STAGE_INDEX, ERR_INVALID_ARG, ERR_CUDA, ERR_OOM, ERR_DIVISION_BY_ZERO = range(12)
 F64, F32 = 0, 1
 
 # name -> (restype, argtypes); every symbol the header declares
@@ -78,6 +78,11 @@ PROTOTYPES = {
     "adsp_plan_process_device": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64]),
     "adsp_plan_sync": (C.c_int, [c_vp]),
     "adsp_partitioned_create": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, C.c_int, C.c_int, C.POINTER(c_vp)]),
+    "adsp_deconv_out_len": (c_i64, [c_i64, c_i64]),
+    "adsp_deconvolve": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, C.c_int, C.c_double, C.c_double, C.c_double, c_vp, c_i64]),
+    "adsp_inverse_filter": (C.c_int, [c_vp, c_vp, c_i64, c_i64, C.c_double, c_vp]),
+    "adsp_snr": (C.c_double, [c_vp, c_i64, c_vp, c_i64]),
+    "adsp_deconvolve_batch_device": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, C.c_double, c_vp, c_i64]),
     "adsp_partitioned_process_block": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64]),
     "adsp_partitioned_create_batch": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(c_vp)]),
     "adsp_partitioned_process_block_batch": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64]),

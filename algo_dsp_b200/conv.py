@@ -37,6 +37,9 @@ ErrInvalidBlockSize = _Sentinel("ErrInvalidBlockSize", "conv: invalid block size
 ErrInvalidBlockOrder = _Sentinel("ErrInvalidBlockOrder", "conv: invalid block order")
 ErrEmptyImpulseResponse = _Sentinel("ErrEmptyImpulseResponse", "conv: empty impulse response")
 ErrStageIndexOutOfRange = _Sentinel("ErrStageIndexOutOfRange", "conv: stage index out of range")
+ErrDivisionByZero = _Sentinel("ErrDivisionByZero", "conv: division by zero in deconvolution")      # deconvolve.go:14
+ErrInvalidEpsilon = _Sentinel("ErrInvalidEpsilon", "conv: epsilon must be positive")                # deconvolve.go:15 (never returned by the reference)
+ErrInvalidNoiseVar = _Sentinel("ErrInvalidNoiseVar", "conv: noise variance must be positive")       # deconvolve.go:16 (never returned)
 ErrInvalidArgument = _Sentinel("ErrInvalidArgument", "algodsp: invalid argument")
 ErrCUDA = _Sentinel("ErrCUDA", "algodsp: CUDA error")
 ErrOutOfMemory = _Sentinel("ErrOutOfMemory", "algodsp: out of memory")
@@ -46,6 +49,7 @@ _SENTINELS = {
     L.ERR_INVALID_BLOCK_SIZE: ErrInvalidBlockSize, L.ERR_INVALID_BLOCK_ORDER: ErrInvalidBlockOrder,
     L.ERR_EMPTY_IR: ErrEmptyImpulseResponse, L.ERR_STAGE_INDEX: ErrStageIndexOutOfRange,
     L.ERR_INVALID_ARG: ErrInvalidArgument, L.ERR_CUDA: ErrCUDA, L.ERR_OOM: ErrOutOfMemory,
+    L.ERR_DIVISION_BY_ZERO: ErrDivisionByZero,
 }
 
 
@@ -64,7 +68,7 @@ def errors_is(err, sentinel) -> bool:
 
 def _check(st):
     if st != L.OK:
-        detail = L.last_error() if st in (L.ERR_CUDA, L.ERR_OOM, L.ERR_INVALID_ARG) else ""
+        detail = L.last_error() if st in (L.ERR_CUDA, L.ERR_OOM, L.ERR_INVALID_ARG, L.ERR_DIVISION_BY_ZERO) else ""
         raise ConvError(st, detail)
 
 
@@ -260,6 +264,54 @@ def AutoCorrelateNormalized(a, ctx=None):
 def CorrelateNormalized(a, b, ctx=None):
     """CorrelateNormalized -- correlate.go:86."""
     return _binary("adsp_correlate_normalized", a, b, ctx)
+
+
+# ---------------------------------------------------------------- deconvolution (deconvolve.go)
+DeconvNaive, DeconvRegularized, DeconvWiener = 0, 1, 2        # DeconvMethod, deconvolve.go:20-35
+
+
+class DeconvOptions:
+    """DeconvOptions -- deconvolve.go:37-54."""
+
+    def __init__(self, Method=DeconvRegularized, Epsilon=0.0, NoiseVariance=0.0, SignalVariance=0.0):
+        self.Method, self.Epsilon, self.NoiseVariance, self.SignalVariance = Method, Epsilon, NoiseVariance, SignalVariance
+
+
+def DefaultDeconvOptions():
+    """DefaultDeconvOptions -- deconvolve.go:56."""
+    return DeconvOptions(DeconvRegularized, 1e-6)
+
+
+def Deconvolve(signal, kernel, opts=None, ctx=None):
+    """Deconvolve -- deconvolve.go:72: len(signal)-len(kernel)+1 samples (len(signal) if that is not positive)."""
+    opts = opts or DefaultDeconvOptions()
+    x, k = _f64(signal), _f64(kernel)
+    if len(signal) == 0:
+        raise ConvError(L.ERR_EMPTY_INPUT)
+    if len(kernel) == 0:
+        raise ConvError(L.ERR_EMPTY_KERNEL)
+    n_out = int(L.load().adsp_deconv_out_len(x.size, k.size))
+    out = np.empty(n_out)
+    _check(L.load().adsp_deconvolve(_ctx(ctx), _p(x), x.size, _p(k), k.size, int(opts.Method), float(opts.Epsilon),
+                                    float(opts.NoiseVariance), float(opts.SignalVariance), _p(out), n_out))
+    return out
+
+
+def InverseFilter(kernel, length, epsilon, ctx=None):
+    """InverseFilter -- deconvolve.go:359."""
+    k = _f64(kernel)
+    if len(kernel) == 0:
+        raise ConvError(L.ERR_EMPTY_KERNEL)
+    out = np.empty(max(int(length), 0))
+    if length > 0:
+        _check(L.load().adsp_inverse_filter(_ctx(ctx), _p(k), k.size, int(length), float(epsilon), _p(out)))
+    return out
+
+
+def SNR(original, recovered):
+    """SNR -- deconvolve.go:417 (dB; +Inf for identical signals, -Inf for mismatched or empty ones)."""
+    a, b = _f64(original), _f64(recovered)
+    return float(L.load().adsp_snr(_p(a), len(original), _p(b), len(recovered)))
 
 
 def FindPeak(corr, ctx=None):

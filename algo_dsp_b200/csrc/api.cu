@@ -428,6 +428,7 @@ const char *adsp_status_string(adsp_status st) {
     case ADSP_ERR_INVALID_ARG: return "algodsp: invalid argument";
     case ADSP_ERR_CUDA: return "algodsp: CUDA error";
     case ADSP_ERR_OOM: return "algodsp: out of memory";
+    case ADSP_ERR_DIVISION_BY_ZERO: return "conv: division by zero in deconvolution";
     }
     return "algodsp: unknown status";
 }
@@ -705,6 +706,109 @@ adsp_status adsp_overlap_save_convolve(adsp_ctx *c, const double *s, int64_t n, 
 }
 adsp_status adsp_correlate(adsp_ctx *c, const double *a, int64_t n, const double *b, int64_t m, double *out) { return oneshot<double>(c, OS_CORRELATE, a, n, b, m, out, 0); }
 adsp_status adsp_correlate_direct(adsp_ctx *c, const double *a, int64_t n, const double *b, int64_t m, double *out) { return oneshot<double>(c, OS_CORRELATE_DIRECT, a, n, b, m, out, 0); }
+// ---------------------------------------------------------------- deconvolution (deconvolve.go)
+int64_t adsp_deconv_out_len(int64_t n, int64_t m) { const int64_t o = n - m + 1; return o <= 0 ? n : o; }   // deconvolve.go:101-105
+
+static adsp_status deconv_run(adsp_ctx *ctx, const double *d_sig, int64_t n, int64_t ss, const double *d_ker, int64_t m, int64_t ks,
+                              int64_t batch, double reg, double *d_out, int64_t os, int64_t out_len) {
+    ADSP_TRY(ctx->d_small.reserve(64));
+    long long *d_bad = (long long *)ctx->d_small.p;
+    const long long none = 0x7fffffffffffffffLL;
+    ADSP_CUDA(cudaMemcpyAsync(d_bad, &none, sizeof none, cudaMemcpyHostToDevice, ctx->main));
+    ADSP_TRY(fft_deconvolve_device<double>(ctx, d_sig, n, ss, d_ker, m, ks, batch, d_out, os, out_len, reg, d_bad));
+    if (reg < 0) {
+        long long bad = none;
+        ADSP_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, ctx->main));
+        ADSP_CUDA(cudaStreamSynchronize(ctx->main));
+        if (bad != none) {                                                  // deconvolve.go:146-148
+            set_error("conv: division by zero in deconvolution: at frequency bin " + std::to_string(bad));
+            return ADSP_ERR_DIVISION_BY_ZERO;
+        }
+    }
+    return ADSP_OK;
+}
+
+adsp_status adsp_deconvolve(adsp_ctx *ctx, const double *signal, int64_t n, const double *kernel, int64_t m, int method, double epsilon,
+                            double noise_variance, double signal_variance, double *out, int64_t out_len) {
+    if (!ctx) return ADSP_ERR_INVALID_ARG;
+    if (n <= 0) return ADSP_ERR_EMPTY_INPUT;                                 // deconvolve.go:73-79
+    if (m <= 0) return ADSP_ERR_EMPTY_KERNEL;
+    if (!signal || !kernel || !out) return ADSP_ERR_INVALID_ARG;
+    if (out_len != adsp_deconv_out_len(n, m)) { set_error("conv: buffer length mismatch"); return ADSP_ERR_LENGTH_MISMATCH; }
+    double reg;
+    if (method == 0) reg = -1.0;
+    else if (method == 2) {                                                  // deconvolve.go:254-270
+        double sv = signal_variance, nv = noise_variance;
+        if (sv <= 0) {                                                       // variance(), deconvolve.go:332-353
+            double mean = 0;
+            for (int64_t i = 0; i < n; i++) mean += signal[i];
+            mean /= (double)n;
+            double sum = 0;
+            for (int64_t i = 0; i < n; i++) { const double d = signal[i] - mean; sum += d * d; }
+            sv = sum / (double)n;
+        }
+        if (nv <= 0) nv = sv * 0.01;
+        reg = nv / sv;
+        if (!(reg > 0)) reg = 1e-6;
+    } else if (method == 1) reg = epsilon <= 0 ? 1e-6 : epsilon;             // deconvolve.go:84-88
+    else reg = 1e-6;                                                         // deconvolve.go:91-93
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ADSP_CUDA(cudaSetDevice(ctx->device));
+    ADSP_TRY(ctx->d_in.reserve((size_t)n * sizeof(double)));
+    ADSP_TRY(ctx->d_tmp.reserve((size_t)m * sizeof(double)));
+    ADSP_TRY(ctx->d_out.reserve((size_t)out_len * sizeof(double)));
+    ADSP_CUDA(cudaMemcpyAsync(ctx->d_in.p, signal, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->main));
+    ADSP_CUDA(cudaMemcpyAsync(ctx->d_tmp.p, kernel, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, ctx->main));
+    ADSP_TRY(deconv_run(ctx, (const double *)ctx->d_in.p, n, n, (const double *)ctx->d_tmp.p, m, m, 1, reg, (double *)ctx->d_out.p, out_len, out_len));
+    ADSP_CUDA(cudaMemcpyAsync(out, ctx->d_out.p, (size_t)out_len * sizeof(double), cudaMemcpyDeviceToHost, ctx->main));
+    ADSP_CUDA(cudaStreamSynchronize(ctx->main));
+    return ADSP_OK;
+}
+
+adsp_status adsp_inverse_filter(adsp_ctx *ctx, const double *kernel, int64_t m, int64_t length, double epsilon, double *out) {
+    if (!ctx) return ADSP_ERR_INVALID_ARG;
+    if (m <= 0) return ADSP_ERR_EMPTY_KERNEL;                                // deconvolve.go:360-362
+    if (length <= 0) return ADSP_OK;
+    if (!kernel || !out) return ADSP_ERR_INVALID_ARG;
+    if (epsilon <= 0) epsilon = 1e-6;                                        // :364-366
+    int64_t N = 1;
+    while (N < length) N *= 2;
+    const int64_t mm = std::min(m, N);                                       // :377-379 kernel truncated to the transform
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ADSP_CUDA(cudaSetDevice(ctx->device));
+    // the signal is a unit impulse: S[k] = 1, so R = conj(H) / (|H|^2 + eps)  (:391-395)
+    ADSP_TRY(ctx->d_in.reserve((size_t)length * sizeof(double)));
+    ADSP_TRY(ctx->d_tmp.reserve((size_t)mm * sizeof(double)));
+    ADSP_TRY(ctx->d_out.reserve((size_t)length * sizeof(double)));
+    ADSP_CUDA(cudaMemsetAsync(ctx->d_in.p, 0, (size_t)length * sizeof(double), ctx->main));
+    const double one = 1.0;
+    ADSP_CUDA(cudaMemcpyAsync(ctx->d_in.p, &one, sizeof one, cudaMemcpyHostToDevice, ctx->main));
+    ADSP_CUDA(cudaMemcpyAsync(ctx->d_tmp.p, kernel, (size_t)mm * sizeof(double), cudaMemcpyHostToDevice, ctx->main));
+    ADSP_TRY(deconv_run(ctx, (const double *)ctx->d_in.p, length, length, (const double *)ctx->d_tmp.p, mm, mm, 1, epsilon, (double *)ctx->d_out.p, length, length));
+    ADSP_CUDA(cudaMemcpyAsync(out, ctx->d_out.p, (size_t)length * sizeof(double), cudaMemcpyDeviceToHost, ctx->main));
+    ADSP_CUDA(cudaStreamSynchronize(ctx->main));
+    return ADSP_OK;
+}
+
+double adsp_snr(const double *original, int64_t n, const double *recovered, int64_t n2) {     // deconvolve.go:417-434
+    if (n != n2 || n <= 0 || !original || !recovered) return -INFINITY;
+    double sp = 0, np = 0;
+    for (int64_t i = 0; i < n; i++) { sp += original[i] * original[i]; const double d = original[i] - recovered[i]; np += d * d; }
+    if (np == 0) return INFINITY;
+    return 10 * log10(sp / np);
+}
+
+adsp_status adsp_deconvolve_batch_device(adsp_ctx *ctx, const double *sig, int64_t n, int64_t ss, const double *ker, int64_t m, int64_t ks,
+                                         int64_t batch, double reg, double *out, int64_t os) {
+    if (!ctx) return ADSP_ERR_INVALID_ARG;
+    if (n <= 0) return ADSP_ERR_EMPTY_INPUT;
+    if (m <= 0) return ADSP_ERR_EMPTY_KERNEL;
+    if (!sig || !ker || !out || batch <= 0) return ADSP_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ADSP_CUDA(cudaSetDevice(ctx->device));
+    return deconv_run(ctx, sig, n, ss, ker, m, ks, batch, reg, out, os, adsp_deconv_out_len(n, m));
+}
+
 adsp_status adsp_correlate_fft(adsp_ctx *c, const double *a, int64_t n, const double *b, int64_t m, double *out) { return oneshot<double>(c, OS_CORRELATE_FFT, a, n, b, m, out, 0); }
 adsp_status adsp_correlate_normalized(adsp_ctx *c, const double *a, int64_t n, const double *b, int64_t m, double *out) { return oneshot<double>(c, OS_CORRELATE, a, n, b, m, out, 1); }
 adsp_status adsp_autocorrelate_normalized(adsp_ctx *c, const double *a, int64_t n, double *out) { return oneshot<double>(c, OS_CORRELATE, a, n, a, n, out, 2); }

@@ -504,7 +504,7 @@ template <typename T, int N1>
 __global__ void __launch_bounds__(ColShape<N1>::THREADS, ColShape<N1>::MIN_CTAS)
 corr_cols_fwd(const T *__restrict__ a, long long n, long long a_stride, const T *__restrict__ b, long long m,
               long long b_stride, cpx<T> *__restrict__ scratch, int N2, int lgN, const cpx<T> *__restrict__ tw,
-              const cpx<T> *__restrict__ tw_hi, const cpx<T> *__restrict__ tw_lo, long long pair0) {
+              const cpx<T> *__restrict__ tw_hi, const cpx<T> *__restrict__ tw_lo, long long pair0, int reverse_b) {
     using C = cpx<T>;
     using CS = ColShape<N1>;
     constexpr int TPF = CS::TPF, TC = CS::TC;
@@ -527,7 +527,7 @@ corr_cols_fwd(const T *__restrict__ a, long long n, long long a_stride, const T 
     for (int q = 0; q < 16; q++) {
         const long long i = (long long)(j + q * TPF) * N2 + n2;
         e[q].x = (i < n) ? ld_stream(ap + i) : (T)0;
-        e[q].y = (i < m) ? ld_stream(bp + (m - 1 - i)) : (T)0;   // reverse(b): correlate.go:22-25
+        e[q].y = (i < m) ? ld_stream(bp + (reverse_b ? (m - 1 - i) : i)) : (T)0;   // reverse(b): correlate.go:22-25; plain b: deconvolve.go:121-123
     }
     CtaGate gate;
     cta_fft<T, N1, false, false, true>(e, buf, addr, stw, j, gate);
@@ -569,6 +569,118 @@ __global__ void corr_pointwise(cpx<T> *ZA, const cpx<T> *ZB, int N1, int N2, T s
     qm.x = pa.x + pb.y; qm.y = -pa.y + pb.x;
     __stcg(&ZA[idx], qk);
     if (midx != idx) __stcg(&ZA[midx], qm);
+}
+
+// Regularised / naive spectral division for deconvolution (deconvolve.go:143-151, 216-220, 304-308), in four-step order,
+// in place.  Z is the transform of z = signal + i*kernel; for real signal and kernel
+//     S[k] = (Z[k] + conj(Z[N-k])) / 2,   H[k] = (Z[k] - conj(Z[N-k])) / (2i),
+//     R[k] = S[k] * conj(H[k]) / (|H[k]|^2 + reg)        (reg < 0: naive S/H, bins with |H| < 1e-15 reported in *bad_bin)
+// and R[N-k] = conj(R[k]) because the result is real.  One thread handles k and N-k.
+template <typename T>
+__global__ void deconv_pointwise(cpx<T> *Z, int N1, int N2, T scale, T reg, long long *bad_bin) {
+    using C = cpx<T>;
+    const long long N = (long long)N1 * N2;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N) return;
+    const long long k1 = idx / N2, k2 = idx - k1 * N2;
+    const long long k = k1 + (long long)N1 * k2;
+    const long long km = (N - k) & (N - 1);
+    if (k > km) return;
+    const long long m1 = km & (N1 - 1), m2 = km / N1;
+    const long long midx = m1 * N2 + m2;
+    const C zk = __ldcg(&Z[idx]), zm = __ldcg(&Z[midx]);
+    const T sr = (zk.x + zm.x) * (T)0.5, si = (zk.y - zm.y) * (T)0.5;          // S = (zk + conj(zm))/2
+    const T hr = (zk.y + zm.y) * (T)0.5, hi = (zm.x - zk.x) * (T)0.5;          // H = (zk - conj(zm))/(2i)
+    T den = hr * hr + hi * hi;
+    if (reg < (T)0) {
+        if (sqrt((double)den) < 1e-15) { atomicMin((unsigned long long *)bad_bin, (unsigned long long)k); den = (T)1; }
+    } else den += reg;
+    C r;
+    r.x = (sr * hr + si * hi) / den * scale;                                     // S * conj(H) / den
+    r.y = (si * hr - sr * hi) / den * scale;
+    __stcg(&Z[idx], r);
+    if (midx != idx) { C rc; rc.x = r.x; rc.y = -r.y; __stcg(&Z[midx], rc); }
+}
+
+// Deconvolution with a transform that fits one CTA (N = L <= 4096): load z = signal + i*kernel, FFT, division through a
+// mirrored read of the spectrum in shared memory, inverse FFT, keep the first out_len samples.  grid = problems.
+template <typename T, int L>
+__global__ void __launch_bounds__(FftShape<L>::TPF)
+deconv_small(const T *__restrict__ sig, long long n, long long s_stride, const T *__restrict__ ker, long long m, long long k_stride,
+             T *__restrict__ out, long long out_stride, long long out_len, T reg, const cpx<T> *__restrict__ tw, long long *bad_bin) {
+    using C = cpx<T>;
+    using Sh = FftShape<L>;
+    constexpr int TPF = Sh::TPF;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C *buf = reinterpret_cast<C *>(smem_raw);
+    C *stw = buf + L;
+    load_tw_smem<T, L>(stw, tw, threadIdx.x, TPF);
+    const int j = threadIdx.x;
+    const T *sp = sig + (long long)blockIdx.x * s_stride;
+    const T *kp = ker + (long long)blockIdx.x * k_stride;
+    C e[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        const long long i = j + q * TPF;
+        e[q].x = (i < n) ? sp[i] : (T)0;
+        e[q].y = (i < m) ? kp[i] : (T)0;
+    }
+    RowAddr<T, Sh::R0> addr{0};
+    CtaGate gate;
+    cta_fft<T, L, false>(e, buf, addr, stw, j, gate);
+    __syncthreads();                                   // everyone is done reading the exchange buffer
+#pragma unroll
+    for (int q = 0; q < 16; q++) buf[j + q * TPF] = e[q];
+    __syncthreads();
+    const T scale = (T)1 / (T)L;
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        const int k = j + q * TPF;
+        const C zk = e[q], zm = buf[(L - k) & (L - 1)];
+        const T sr = (zk.x + zm.x) * (T)0.5, si = (zk.y - zm.y) * (T)0.5;
+        const T hr = (zk.y + zm.y) * (T)0.5, hi = (zm.x - zk.x) * (T)0.5;
+        T den = hr * hr + hi * hi;
+        if (reg < (T)0) {
+            if (sqrt((double)den) < 1e-15) { atomicMin((unsigned long long *)bad_bin, (unsigned long long)k); den = (T)1; }
+        } else den += reg;
+        e[q].x = (sr * hr + si * hi) / den * scale;
+        e[q].y = (si * hr - sr * hi) / den * scale;
+    }
+    __syncthreads();                                   // mirrored reads done before the inverse reuses the buffer
+    cta_fft<T, L, true>(e, buf, addr, stw, j, gate);
+    T *op = out + (long long)blockIdx.x * out_stride;
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        const long long i = j + q * TPF;
+        if (i < out_len) op[i] = e[q].x;
+    }
+}
+
+// N = 1, 2, 4, 8: direct DFT by one thread per problem (same formulas); grid = problems, one thread each
+template <typename T>
+__global__ void deconv_tiny(const T *sig, long long n, long long s_stride, const T *ker, long long m, long long k_stride, T *out,
+                            long long out_stride, long long out_len, int N, T reg, long long *bad_bin) {
+    const T *sp = sig + (long long)blockIdx.x * s_stride;
+    const T *kp = ker + (long long)blockIdx.x * k_stride;
+    double rr[8], ri[8];
+    for (int k = 0; k < N; k++) {
+        double sr = 0, si = 0, hr = 0, hi = 0;
+        for (int i = 0; i < N; i++) {
+            const double c = cospi(2.0 * (double)((k * i) % N) / N), s = -sinpi(2.0 * (double)((k * i) % N) / N);
+            const double xs = i < n ? (double)sp[i] : 0.0, xk = i < m ? (double)kp[i] : 0.0;
+            sr += xs * c; si += xs * s; hr += xk * c; hi += xk * s;
+        }
+        double den = hr * hr + hi * hi;
+        if (reg < (T)0) { if (sqrt(den) < 1e-15) { atomicMin((unsigned long long *)bad_bin, (unsigned long long)k); den = 1; } }
+        else den += (double)reg;
+        rr[k] = (sr * hr + si * hi) / den; ri[k] = (si * hr - sr * hi) / den;
+    }
+    T *op = out + (long long)blockIdx.x * out_stride;
+    for (int i = 0; i < N && i < out_len; i++) {
+        double acc = 0;
+        for (int k = 0; k < N; k++) acc += rr[k] * cospi(2.0 * (double)((k * i) % N) / N) - ri[k] * sinpi(2.0 * (double)((k * i) % N) / N);
+        op[i] = (T)(acc / N);
+    }
 }
 
 #if ADSP_WIDE_TILES

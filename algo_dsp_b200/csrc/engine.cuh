@@ -144,6 +144,11 @@ adsp_status fft_correlate_pairs_device(adsp_ctx *ctx, const T *a, long long n, l
                                        long long b_stride, long long pairs, T *out, long long out_stride, bool *done);
 
 template <typename T>
+adsp_status fft_deconvolve_device(adsp_ctx *ctx, const T *sig, long long n, long long s_stride, const T *ker, long long m,
+                                  long long k_stride, long long batch, T *out, long long out_stride, long long out_len, T reg,
+                                  long long *d_bad);
+
+template <typename T>
 adsp_status direct_device(adsp_ctx *ctx, const T *d_a, long long n, long long a_stride, const T *d_b, long long m,
                           long long b_stride, long long batch, T *d_out, long long out_stride);
 

@@ -858,14 +858,14 @@ adsp_status fft_convolve_device(adsp_ctx *ctx, const T *d_x, long long n, long l
 template <typename T, int N1>
 static adsp_status launch_corr_cols_t(adsp_ctx *ctx, cudaStream_t st, const T *a, long long n, long long a_stride, const T *b,
                                       long long m, long long b_stride, cpx<T> *scratch, int N2, int lgN, const cpx<T> *tw,
-                                      const cpx<T> *hi, const cpx<T> *lo, long long pair0, int pairs) {
+                                      const cpx<T> *hi, const cpx<T> *lo, long long pair0, int pairs, int reverse_b = 1) {
     using CS = ColShape<N1>;
     const size_t smem = (FftShape<N1>::P > 0) ? ((size_t)CS::SMEM_ELEMS + FftShape<N1>::TW_ENTRIES) * sizeof(cpx<T>) : 16;
     static AttrOnce once;
     if (once.need(ctx->device)) ADSP_TRY(set_smem(corr_cols_fwd<T, N1>, smem));
     dim3 grid((unsigned)(N2 / CS::TC), (unsigned)pairs);
     LaunchTimer lt(ctx, st, KK_COLS_FWD);
-    corr_cols_fwd<T, N1><<<grid, CS::THREADS, smem, st>>>(a, n, a_stride, b, m, b_stride, scratch, N2, lgN, tw, hi, lo, pair0);
+    corr_cols_fwd<T, N1><<<grid, CS::THREADS, smem, st>>>(a, n, a_stride, b, m, b_stride, scratch, N2, lgN, tw, hi, lo, pair0, reverse_b);
     count_launch(ctx);
     ADSP_CUDA(cudaGetLastError());
     return ADSP_OK;
@@ -915,6 +915,78 @@ adsp_status fft_correlate_pairs_device(adsp_ctx *ctx, const T *a, long long n, l
     *done = true;
     return ADSP_OK;
 }
+// ------------------------------------------------------------------ deconvolution (deconvolve.go:72-412)
+// out[p][i], i < out_len = IFFT( S * conj(H) / (|H|^2 + reg) )[i] with N = nextPow2(n) (circular, exactly the reference's
+// transform length); reg < 0: naive division, *d_bad receives the smallest bin with |H| < 1e-15.  Device pointers.
+template <typename T, int L>
+static adsp_status launch_deconv_small(adsp_ctx *ctx, const T *sig, long long n, long long ss, const T *ker, long long m, long long ks,
+                                       long long batch, T *out, long long os, long long out_len, T reg, long long *d_bad) {
+    const cpx<T> *tw = nullptr;
+    ADSP_TRY(get_tw_table<T>(ctx, L, &tw));
+    const size_t smem = ((size_t)L + FftShape<L>::TW_ENTRIES) * sizeof(cpx<T>);
+    static AttrOnce once;
+    if (once.need(ctx->device)) ADSP_TRY(set_smem(deconv_small<T, L>, smem));
+    LaunchTimer lt(ctx, ctx->main, KK_OTHER);
+    deconv_small<T, L><<<(unsigned)batch, FftShape<L>::TPF, smem, ctx->main>>>(sig, n, ss, ker, m, ks, out, os, out_len, reg, tw, d_bad);
+    count_launch(ctx);
+    ADSP_CUDA(cudaGetLastError());
+    return ADSP_OK;
+}
+
+template <typename T>
+adsp_status fft_deconvolve_device(adsp_ctx *ctx, const T *sig, long long n, long long s_stride, const T *ker, long long m,
+                                  long long k_stride, long long batch, T *out, long long out_stride, long long out_len, T reg,
+                                  long long *d_bad) {
+    long long N = 1;
+    while (N < n) N *= 2;
+    if (m > N || N > (1LL << 22) || batch <= 0) { set_error("deconvolve: unsupported size"); return ADSP_ERR_INVALID_ARG; }
+    if (N < 16) {
+        LaunchTimer lt(ctx, ctx->main, KK_OTHER);
+        deconv_tiny<T><<<(unsigned)batch, 1, 0, ctx->main>>>(sig, n, s_stride, ker, m, k_stride, out, out_stride, out_len, (int)N, reg, d_bad);
+        count_launch(ctx);
+        ADSP_CUDA(cudaGetLastError());
+        return ADSP_OK;
+    }
+    switch (N) {
+#define ADSP_DS(l) case l: return launch_deconv_small<T, l>(ctx, sig, n, s_stride, ker, m, k_stride, batch, out, out_stride, out_len, reg, d_bad);
+        ADSP_DS(16) ADSP_DS(32) ADSP_DS(64) ADSP_DS(128) ADSP_DS(256) ADSP_DS(512) ADSP_DS(1024) ADSP_DS(2048) ADSP_DS(4096)
+#undef ADSP_DS
+    default: break;
+    }
+    FftChoice ch = make_choice(1, N);     // geometry only (N1, N2, lgN)
+    const cpx<T> *tw_rows, *tw_cols, *tw_hi, *tw_lo;
+    ADSP_TRY(get_tw_table<T>(ctx, ch.N2, &tw_rows));
+    ADSP_TRY(get_tw_table<T>(ctx, ch.N1, &tw_cols));
+    ADSP_TRY(get_tw4_tables<T>(ctx, ch.N, &tw_hi, &tw_lo));
+    ADSP_TRY(ctx->scratch.reserve((size_t)N * sizeof(cpx<T>)));
+    cpx<T> *Z = (cpx<T> *)ctx->scratch.p;
+    ConvGeom g{};
+    g.n = N; g.out_len = out_len; g.in_stride = 0; g.out_stride = out_stride; g.S = N; g.D = 0;
+    g.total_blocks = 1; g.in_shift = 0; g.out_shift = 0; g.nblk = 1; g.accumulate = 0;
+    cudaStream_t st = ctx->main;
+    const T scale = (T)(1.0L / (long double)N);
+    for (long long p = 0; p < batch; p++) {
+#define ADSP_DC_COLS(n1) case n1: ADSP_TRY((launch_corr_cols_t<T, n1>(ctx, st, sig, n, s_stride, ker, m, k_stride, Z, ch.N2, ch.lgN, tw_cols, tw_hi, tw_lo, p, 1, 0))); break;
+        switch (ch.N1) {
+            ADSP_DC_COLS(16) ADSP_DC_COLS(32) ADSP_DC_COLS(64) ADSP_DC_COLS(128) ADSP_DC_COLS(256) ADSP_DC_COLS(512) ADSP_DC_COLS(1024)
+        default: set_error("deconvolve: unsupported transform shape"); return ADSP_ERR_INVALID_ARG;
+        }
+#undef ADSP_DC_COLS
+        ADSP_TRY((launch_rows<T, 1>(ctx, st, ch.N2, Z, (const cpx<T> *)nullptr, Z, (T)1, ch.N1, tw_rows, 1)));
+        {
+            LaunchTimer lt(ctx, st, KK_OTHER);
+            deconv_pointwise<T><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(Z, ch.N1, ch.N2, scale, reg, d_bad);
+            count_launch(ctx);
+        }
+        ADSP_TRY((launch_rows<T, 2>(ctx, st, ch.N2, Z, (const cpx<T> *)nullptr, Z, (T)1, ch.N1, tw_rows, 1)));
+        ADSP_TRY(launch_cols<T>(ctx, st, ch.N1, true, g, (const T *)nullptr, out + p * out_stride, Z, ch.N2, ch.lgN, tw_cols, tw_hi, tw_lo, 0, 1));
+    }
+    ADSP_CUDA(cudaGetLastError());
+    return ADSP_OK;
+}
+template adsp_status fft_deconvolve_device<ADSP_REAL>(adsp_ctx *, const ADSP_REAL *, long long, long long, const ADSP_REAL *, long long, long long,
+                                                      long long, ADSP_REAL *, long long, long long, ADSP_REAL, long long *);
+
 template adsp_status fft_correlate_pairs_device<ADSP_REAL>(adsp_ctx *, const ADSP_REAL *, long long, long long, const ADSP_REAL *, long long,
                                                            long long, long long, ADSP_REAL *, long long, bool *);
 

@@ -42,7 +42,8 @@ typedef enum adsp_status {
     ADSP_ERR_STAGE_INDEX = 7,         /* conv.ErrStageIndexOutOfRange  dsp/conv/partitioned.go:14 */
     ADSP_ERR_INVALID_ARG = 8,         /* nil handle / negative size / bad enum */
     ADSP_ERR_CUDA = 9,                /* CUDA runtime error or no device (text in adsp_last_error) */
-    ADSP_ERR_OOM = 10                 /* device or pinned-host allocation failed */
+    ADSP_ERR_OOM = 10,                /* device or pinned-host allocation failed */
+    ADSP_ERR_DIVISION_BY_ZERO = 11    /* conv.ErrDivisionByZero        dsp/conv/deconvolve.go:14 */
 } adsp_status;
 
 /* conv.Mode, dsp/conv/conv.go:57-69 */
@@ -165,6 +166,23 @@ ADSP_API adsp_status adsp_plan_process_batch(adsp_plan *plan, const void *in, in
 ADSP_API adsp_status adsp_plan_process_device(adsp_plan *plan, const void *in_dev, int64_t n, int64_t channels,
                                               int64_t in_stride, void *out_dev, int64_t out_stride);
 ADSP_API adsp_status adsp_plan_sync(adsp_plan *plan);
+
+/* ---------------------------------------------------------------- deconvolution, float64 like the reference
+ * Deconvolve(signal, kernel, opts) deconvolve.go:72: circular spectral division at N = nextPow2(len(signal));
+ * method 0 = DeconvNaive (ErrDivisionByZero when a bin has |H| < 1e-15; the bin index is in adsp_last_error),
+ * 1 = DeconvRegularized (epsilon <= 0 -> 1e-6), 2 = DeconvWiener (variances <= 0 are estimated as the reference does),
+ * anything else = regularized with 1e-6.  out_len must equal adsp_deconv_out_len(n, m) (n - m + 1, or n if that is <= 0). */
+ADSP_API int64_t adsp_deconv_out_len(int64_t n, int64_t m);
+ADSP_API adsp_status adsp_deconvolve(adsp_ctx *, const double *signal, int64_t n, const double *kernel, int64_t m, int method,
+                                     double epsilon, double noise_variance, double signal_variance, double *out, int64_t out_len);
+/* InverseFilter(kernel, length, epsilon) deconvolve.go:359 */
+ADSP_API adsp_status adsp_inverse_filter(adsp_ctx *, const double *kernel, int64_t m, int64_t length, double epsilon, double *out);
+/* SNR(original, recovered) deconvolve.go:417 (host arithmetic; -Inf on length mismatch or empty input) */
+ADSP_API double adsp_snr(const double *original, int64_t n, const double *recovered, int64_t n2);
+/* `batch` independent problems, device pointers, strides in elements (k_stride 0 = one kernel for all); reg < 0 = naive. */
+ADSP_API adsp_status adsp_deconvolve_batch_device(adsp_ctx *, const double *signal_dev, int64_t n, int64_t s_stride,
+                                                  const double *kernel_dev, int64_t m, int64_t k_stride, int64_t batch,
+                                                  double reg, double *out_dev, int64_t out_stride);
 
 /* ---------------------------------------------------------------- partitioned (long IR, streaming)
  * NewPartitionedConvolution(kernel, minBlockOrder, maxBlockOrder) partitioned.go:212,335.

@@ -31,7 +31,8 @@ enum {
     ORC_ERR_INVALID_BLOCK_ORDER = 5,  /* partitioned.go:12 */
     ORC_ERR_EMPTY_IR = 6,             /* partitioned.go:13 */
     ORC_ERR_STAGE_INDEX = 7,          /* partitioned.go:14 */
-    ORC_ERR_INVALID_ARG = 8
+    ORC_ERR_INVALID_ARG = 8,
+    ORC_ERR_DIVISION_BY_ZERO = 9      /* deconvolve.go:14 ErrDivisionByZero */
 };
 
 /* nextPowerOf2, dsp/conv/conv.go:250-261. */
@@ -191,6 +192,97 @@ int orc_bench_ols_f64(const double *kernel, int64_t K, int64_t fftSize,
     fftplan_free_f64(plan);
     free(kfft);
     return ORC_OK;
+}
+
+/* ------------------------------- deconvolution (dsp/conv/deconvolve.go), float64 only like the reference */
+
+/* variance, deconvolve.go:332-353 (population variance) */
+double orc_variance(const double *x, int64_t n) {
+    if (n <= 0) return 0;
+    double mean = 0;
+    for (int64_t i = 0; i < n; i++) mean += x[i];
+    mean /= (double)n;
+    double sum = 0;
+    for (int64_t i = 0; i < n; i++) { double d = x[i] - mean; sum += d * d; }
+    return sum / (double)n;
+}
+
+int64_t orc_deconv_out_len(int64_t n, int64_t m) { int64_t o = n - m + 1; return o <= 0 ? n : o; }   /* :101-105 */
+
+/* Deconvolve, deconvolve.go:72-330.  method 0 naive (:98-168), 1 regularized (:172-240), 2 Wiener (:244-328).
+ * dst holds orc_deconv_out_len(n, m) samples.  *bad_bin = first bin with |H| < 1e-15 (naive only). */
+int orc_deconvolve(const double *signal, int64_t n, const double *kernel, int64_t m, int method, double epsilon,
+                   double noise_var, double signal_var, double *dst, int64_t *bad_bin) {
+    if (n <= 0) return ORC_ERR_EMPTY_INPUT;
+    if (m <= 0) return ORC_ERR_EMPTY_KERNEL;
+    double reg = 0;
+    if (method == 1) reg = epsilon <= 0 ? 1e-6 : epsilon;                                   /* :84-88 */
+    else if (method == 2) {                                                                  /* :254-270 */
+        if (signal_var <= 0) signal_var = orc_variance(signal, n);
+        if (noise_var <= 0) noise_var = signal_var * 0.01;
+        reg = noise_var / signal_var;
+        if (!(reg > 0)) reg = 1e-6;
+    } else if (method != 0) { method = 1; reg = 1e-6; }                                      /* :91-93 */
+    const int64_t out_len = orc_deconv_out_len(n, m);
+    const int64_t N = orc_next_pow2(n);                                                      /* :107 */
+    fftplan_f64 *plan = fftplan_new_f64((int)N);
+    cpx_f64 *fs = (cpx_f64 *)calloc((size_t)N, sizeof(cpx_f64));
+    cpx_f64 *fk = (cpx_f64 *)calloc((size_t)N, sizeof(cpx_f64));
+    for (int64_t i = 0; i < n; i++) fs[i].re = signal[i];
+    for (int64_t i = 0; i < m && i < N; i++) fk[i].re = kernel[i];   /* the Go loop would index past fftSize when m > N and panic */
+    fft_exec_f64(plan, fs, 0);
+    fft_exec_f64(plan, fk, 0);
+    int st = ORC_OK;
+    for (int64_t i = 0; i < N; i++) {
+        const double hr = fk[i].re, hi = fk[i].im;
+        if (method == 0) {                                                                   /* :143-151 */
+            if (hypot(hr, hi) < 1e-15) { st = ORC_ERR_DIVISION_BY_ZERO; if (bad_bin) *bad_bin = i; break; }
+            const double den = hr * hr + hi * hi;
+            const double re = (fs[i].re * hr + fs[i].im * hi) / den, im = (fs[i].im * hr - fs[i].re * hi) / den;
+            fs[i].re = re; fs[i].im = im;
+        } else {                                                                             /* :216-220, :304-308 */
+            const double den = hr * hr + hi * hi + reg;
+            const double re = (fs[i].re * hr + fs[i].im * hi) / den, im = (fs[i].im * hr - fs[i].re * hi) / den;
+            fs[i].re = re; fs[i].im = im;
+        }
+    }
+    if (st == ORC_OK) {
+        fft_exec_f64(plan, fs, 1);
+        for (int64_t i = 0; i < out_len; i++) dst[i] = fs[i].re;
+    }
+    fftplan_free_f64(plan);
+    free(fs); free(fk);
+    return st;
+}
+
+/* InverseFilter, deconvolve.go:359-412 */
+int orc_inverse_filter(const double *kernel, int64_t m, int64_t length, double epsilon, double *dst) {
+    if (m <= 0) return ORC_ERR_EMPTY_KERNEL;
+    if (length <= 0) return ORC_OK;
+    if (epsilon <= 0) epsilon = 1e-6;
+    const int64_t N = orc_next_pow2(length);
+    fftplan_f64 *plan = fftplan_new_f64((int)N);
+    cpx_f64 *fk = (cpx_f64 *)calloc((size_t)N, sizeof(cpx_f64));
+    for (int64_t i = 0; i < m && i < N; i++) fk[i].re = kernel[i];
+    fft_exec_f64(plan, fk, 0);
+    for (int64_t i = 0; i < N; i++) {
+        const double hr = fk[i].re, hi = fk[i].im, den = hr * hr + hi * hi + epsilon;
+        fk[i].re = hr / den; fk[i].im = -hi / den;
+    }
+    fft_exec_f64(plan, fk, 1);
+    for (int64_t i = 0; i < length; i++) dst[i] = fk[i].re;
+    fftplan_free_f64(plan);
+    free(fk);
+    return ORC_OK;
+}
+
+/* SNR, deconvolve.go:417-434 */
+double orc_snr(const double *original, int64_t n, const double *recovered, int64_t n2) {
+    if (n != n2 || n == 0) return -INFINITY;
+    double sp = 0, np_ = 0;
+    for (int64_t i = 0; i < n; i++) { sp += original[i] * original[i]; const double d = original[i] - recovered[i]; np_ += d * d; }
+    if (np_ == 0) return INFINITY;
+    return 10 * log10(sp / np_);
 }
 
 int orc_num_procs(void) { long n = sysconf(_SC_NPROCESSORS_ONLN); return n > 0 ? (int)n : 1; }

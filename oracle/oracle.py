@@ -16,11 +16,12 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "liboracle.so")
 
-OK, EMPTY_INPUT, EMPTY_KERNEL, LENGTH_MISMATCH, INVALID_BLOCK_SIZE, INVALID_BLOCK_ORDER, EMPTY_IR, STAGE_INDEX, INVALID_ARG = range(9)
+OK, EMPTY_INPUT, EMPTY_KERNEL, LENGTH_MISMATCH, INVALID_BLOCK_SIZE, INVALID_BLOCK_ORDER, EMPTY_IR, STAGE_INDEX, INVALID_ARG, DIVISION_BY_ZERO = range(10)
 _NAMES = {
     EMPTY_INPUT: "ErrEmptyInput", EMPTY_KERNEL: "ErrEmptyKernel", LENGTH_MISMATCH: "ErrLengthMismatch",
     INVALID_BLOCK_SIZE: "ErrInvalidBlockSize", INVALID_BLOCK_ORDER: "ErrInvalidBlockOrder",
     EMPTY_IR: "ErrEmptyImpulseResponse", STAGE_INDEX: "ErrStageIndexOutOfRange", INVALID_ARG: "ErrInvalidArgument",
+    DIVISION_BY_ZERO: "ErrDivisionByZero",
 }
 
 MODE_FULL, MODE_SAME, MODE_VALID = 0, 1, 2
@@ -285,6 +286,44 @@ class Partitioned:
         if getattr(self, "h", None):
             getattr(lib(), "orc_part_destroy" + self.sfx)(C.c_void_p(self.h))
             self.h = None
+
+
+DECONV_NAIVE, DECONV_REGULARIZED, DECONV_WIENER = 0, 1, 2
+
+
+def deconvolve(signal, kernel, method=DECONV_REGULARIZED, epsilon=1e-6, noise_variance=0.0, signal_variance=0.0):
+    """Deconvolve(signal, kernel, opts) -- deconvolve.go:72 (float64 only, like the reference)."""
+    x, k = _arr(signal, np.float64), _arr(kernel, np.float64)
+    L = lib()
+    L.orc_deconv_out_len.restype = C.c_int64
+    out = np.zeros(max(int(L.orc_deconv_out_len(C.c_int64(x.size), C.c_int64(k.size))), 1))
+    bad = C.c_int64(-1)
+    _check(L.orc_deconvolve(_p(x), C.c_int64(x.size), _p(k), C.c_int64(k.size), C.c_int(method), C.c_double(epsilon),
+                            C.c_double(noise_variance), C.c_double(signal_variance), _p(out), C.byref(bad)))
+    return out[: int(L.orc_deconv_out_len(C.c_int64(x.size), C.c_int64(k.size)))]
+
+
+def inverse_filter(kernel, length, epsilon):
+    """InverseFilter(kernel, length, epsilon) -- deconvolve.go:359."""
+    k = _arr(kernel, np.float64)
+    out = np.zeros(max(int(length), 1))
+    _check(lib().orc_inverse_filter(_p(k), C.c_int64(k.size), C.c_int64(length), C.c_double(epsilon), _p(out)))
+    return out[: int(length)]
+
+
+def snr(original, recovered):
+    """SNR(original, recovered) -- deconvolve.go:417."""
+    a, b = _arr(original, np.float64), _arr(recovered, np.float64)
+    f = lib().orc_snr
+    f.restype = C.c_double
+    return float(f(_p(a), C.c_int64(0 if len(original) == 0 else a.size), _p(b), C.c_int64(0 if len(recovered) == 0 else b.size)))
+
+
+def variance(x):
+    a = _arr(x, np.float64)
+    f = lib().orc_variance
+    f.restype = C.c_double
+    return float(f(_p(a), C.c_int64(a.size)))
 
 
 def bench_ols(kernel, signal2d, fft_size=0, threads=1):
