@@ -32,6 +32,7 @@ constexpr adsp_status ErrInvalidBlockSize = ADSP_ERR_INVALID_BLOCK_SIZE;
 constexpr adsp_status ErrInvalidBlockOrder = ADSP_ERR_INVALID_BLOCK_ORDER;
 constexpr adsp_status ErrEmptyImpulseResponse = ADSP_ERR_EMPTY_IR;
 constexpr adsp_status ErrStageIndexOutOfRange = ADSP_ERR_STAGE_INDEX;
+constexpr adsp_status ErrDivisionByZero = ADSP_ERR_DIVISION_BY_ZERO;       // deconvolve.go:14
 inline bool errors_is(const Error &e, adsp_status sentinel) { return e.status == sentinel; }
 
 inline void check(adsp_status st) {
@@ -161,6 +162,29 @@ public:
     }
 };
 inline PartitionedConvolution NewPartitionedConvolution(const Vec &k, int mn, int mx, Context &c = Context::Default()) { return PartitionedConvolution(k, mn, mx, c); }
+
+// Deconvolution -- deconvolve.go:20-434 (float64 like the reference)
+enum DeconvMethod { DeconvNaive = 0, DeconvRegularized = 1, DeconvWiener = 2 };                                   // :20-35
+struct DeconvOptions { DeconvMethod Method = DeconvRegularized; double Epsilon = 0, NoiseVariance = 0, SignalVariance = 0; };   // :37-54
+inline DeconvOptions DefaultDeconvOptions() { DeconvOptions o; o.Epsilon = 1e-6; return o; }                    // :56
+inline Vec Deconvolve(const Vec &signal, const Vec &kernel, const DeconvOptions &opts = DefaultDeconvOptions(),
+                      Context &c = Context::Default()) {                                                         // :72
+    if (signal.empty()) check(ADSP_ERR_EMPTY_INPUT);
+    if (kernel.empty()) check(ADSP_ERR_EMPTY_KERNEL);
+    Vec out((size_t)adsp_deconv_out_len((int64_t)signal.size(), (int64_t)kernel.size()));
+    check(adsp_deconvolve(c.handle(), signal.data(), (int64_t)signal.size(), kernel.data(), (int64_t)kernel.size(), (int)opts.Method,
+                          opts.Epsilon, opts.NoiseVariance, opts.SignalVariance, out.data(), (int64_t)out.size()));
+    return out;
+}
+inline Vec InverseFilter(const Vec &kernel, int64_t length, double epsilon, Context &c = Context::Default()) {   // :359
+    if (kernel.empty()) check(ADSP_ERR_EMPTY_KERNEL);
+    Vec out((size_t)(length > 0 ? length : 0));
+    if (length > 0) check(adsp_inverse_filter(c.handle(), kernel.data(), (int64_t)kernel.size(), length, epsilon, out.data()));
+    return out;
+}
+inline double SNR(const Vec &original, const Vec &recovered) {                                                  // :417
+    return adsp_snr(original.data(), (int64_t)original.size(), recovered.data(), (int64_t)recovered.size());
+}
 
 // ConvolutionReverb -- dsp/effects/reverb/convolution.go:17-101, extended to `channels` independent streams per call
 // (rows of a [channels][n] block with the given stride); channels = 1 is the reference's mono effect.

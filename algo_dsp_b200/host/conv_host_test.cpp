@@ -2,6 +2,7 @@
 // Build: g++ -std=c++17 conv_host_test.cpp -o conv_host_test -L.. -lalgodsp_cuda -Wl,-rpath,$PWD/..
 #include <cmath>
 #include <cstdio>
+#include <string>
 
 #include "conv.hpp"
 
@@ -45,6 +46,18 @@ int main() {
     {   // TestOverlapSaveInvalidFFTSize, conv_test.go:675-682
         try { conv::NewOverlapSave({0.25, 0.5, 0.25}, 100); EXPECT(false); }
         catch (const conv::Error &e) { EXPECT(conv::errors_is(e, conv::ErrInvalidBlockSize)); }
+    }
+    {   // ExampleDeconvolve, example_test.go:129-156: "Recovery SNR: 39.6 dB"
+        Vec original(50);
+        for (size_t i = 0; i < 50; i++) original[i] = std::sin(2 * M_PI * (double)i / 10);
+        Vec kernel{0.25, 0.5, 0.25};
+        auto opts = conv::DefaultDeconvOptions();
+        opts.Epsilon = 1e-3;
+        Vec recovered = conv::Deconvolve(conv::Direct(original, kernel), kernel, opts);
+        EXPECT(recovered.size() == 50);
+        char buf[32];
+        std::snprintf(buf, sizeof buf, "%.1f", conv::SNR(original, recovered));
+        EXPECT(std::string(buf) == "39.6");
     }
     {   // ConvolutionReverb: wet/dry in place equals dry*x + wet*(delayed convolution), convolution.go:60-83
         Vec kernel(3000);

@@ -233,6 +233,15 @@ def other_configs(torch, conv, G, ctx, stream):
     lags_ok = bool(np.array_equal(pi.cpu().numpy() - (n - 1), np.array(delays)))
     out["config4_correlate_peak"] = {"pairs": pairs, "pairs_per_s": pairs / ms * 1e3, "algorithmic_GBps": pairs * (4 * n - 1) * 8 / ms / 1e6,
                                      "lags_exact": lags_ok, "ms": ms}
+    # deconvolution: 16 problems x 2^20 samples, 4096-tap kernel, regularized spectral division, device resident
+    probs, n, m = 16, 1 << 20, 4096
+    sig = torch.rand((probs, n), device="cuda", dtype=torch.float64) * 2 - 1
+    ker = torch.tensor(G.decaying_ir(m) + (np.arange(m) == 0) * 2.0, device="cuda")
+    o = torch.empty((probs, n - m + 1), device="cuda", dtype=torch.float64)
+    ms = timeit(lambda: lib.adsp_deconvolve_batch_device(ctx.handle, sig.data_ptr(), n, n, ker.data_ptr(), m, 0, probs, C.c_double(1e-6),
+                                                         o.data_ptr(), n - m + 1), iters=3)
+    out["deconvolve_regularized"] = {"problems": probs, "samples": n, "kernel_taps": m, "problems_per_s": probs / ms * 1e3,
+                                     "algorithmic_GBps": probs * (2 * n - m + 1 + m) * 8 / ms / 1e6, "ms": ms}
     return out
 
 

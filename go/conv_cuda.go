@@ -22,6 +22,7 @@ import "C"
 import (
 	"errors"
 	"fmt"
+	"math"
 	"runtime"
 	"sync"
 	"unsafe"
@@ -213,6 +214,78 @@ func (os *OverlapSave) Process(input []float64) ([]float64, error) {
 // ProcessTo -- overlap_save.go:258.
 func (os *OverlapSave) ProcessTo(output, input []float64) error {
 	return statusErr(C.adsp_plan_process(os.plan, unsafe.Pointer(ptr(input)), C.int64_t(len(input)), unsafe.Pointer(ptr(output)), C.int64_t(len(output))))
+}
+
+// Deconvolution -- deconvolve.go:20-434.
+type DeconvMethod int
+
+const (
+	DeconvNaive DeconvMethod = iota
+	DeconvRegularized
+	DeconvWiener
+)
+
+type DeconvOptions struct {
+	Method         DeconvMethod
+	Epsilon        float64
+	NoiseVariance  float64
+	SignalVariance float64
+}
+
+var ErrDivisionByZero = errors.New("conv: division by zero in deconvolution")
+
+func DefaultDeconvOptions() DeconvOptions { return DeconvOptions{Method: DeconvRegularized, Epsilon: 1e-6} }
+
+// Deconvolve -- deconvolve.go:72.
+func Deconvolve(signal, kernel []float64, opts DeconvOptions) ([]float64, error) {
+	if len(signal) == 0 {
+		return nil, ErrEmptyInput
+	}
+	if len(kernel) == 0 {
+		return nil, ErrEmptyKernel
+	}
+	c, err := context()
+	if err != nil {
+		return nil, err
+	}
+	out := make([]float64, int(C.adsp_deconv_out_len(C.int64_t(len(signal)), C.int64_t(len(kernel)))))
+	st := C.adsp_deconvolve(c, ptr(signal), C.int64_t(len(signal)), ptr(kernel), C.int64_t(len(kernel)),
+		C.int(opts.Method), C.double(opts.Epsilon), C.double(opts.NoiseVariance), C.double(opts.SignalVariance),
+		ptr(out), C.int64_t(len(out)))
+	if st == C.ADSP_ERR_DIVISION_BY_ZERO {
+		return nil, fmt.Errorf("%w: %s", ErrDivisionByZero, lastError())
+	}
+	if st != C.ADSP_OK {
+		return nil, statusErr(st)
+	}
+	return out, nil
+}
+
+// InverseFilter -- deconvolve.go:359.
+func InverseFilter(kernel []float64, length int, epsilon float64) ([]float64, error) {
+	if len(kernel) == 0 {
+		return nil, ErrEmptyKernel
+	}
+	c, err := context()
+	if err != nil {
+		return nil, err
+	}
+	out := make([]float64, length)
+	if length > 0 {
+		if st := C.adsp_inverse_filter(c, ptr(kernel), C.int64_t(len(kernel)), C.int64_t(length), C.double(epsilon),
+			ptr(out)); st != C.ADSP_OK {
+			return nil, statusErr(st)
+		}
+	}
+	return out, nil
+}
+
+// SNR -- deconvolve.go:417.
+func SNR(original, recovered []float64) float64 {
+	if len(original) != len(recovered) || len(original) == 0 {
+		return math.Inf(-1)
+	}
+	return float64(C.adsp_snr(ptr(original), C.int64_t(len(original)), ptr(recovered), C.int64_t(len(recovered))))
 }
 
 // ConvolutionReverb backed by the device-resident frequency-domain delay line -- the reference type
