@@ -91,6 +91,7 @@ PROTOTYPES = {
     "adsp_partitioned_process_in_place_batch": (C.c_int, [c_vp, c_vp, c_i64, c_i64]),
     "adsp_partitioned_process_in_place_batch_device": (C.c_int, [c_vp, c_vp, c_i64, c_i64]),
     "adsp_partitioned_channels": (C.c_int, [c_vp]),
+    "adsp_partitioned_plan_layout": (C.c_int, [c_i64, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(c_i64), C.c_int]),
     "adsp_partitioned_internal_stage_count": (C.c_int, [c_vp]),
     "adsp_partitioned_internal_stage_info": (C.c_int, [c_vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(c_i64)]),
     "adsp_partitioned_latency": (C.c_int, [c_vp]),

@@ -1293,6 +1293,17 @@ adsp_status adsp_partitioned_process_in_place_batch(adsp_plan *p, void *block, i
 adsp_status adsp_partitioned_process_in_place_batch_device(adsp_plan *p, void *block, int64_t n, int64_t stride) {
     return part_batch(p, block, n, stride, block, stride, false, true);
 }
+// stage layout the delay-line engine would use for (K, minBlockOrder, maxBlockOrder); no GPU needed (host arithmetic)
+int adsp_partitioned_plan_layout(int64_t kernel_len, int min_order, int max_order, int *part_size, int *count, int64_t *ir_offset, int cap) {
+    if (kernel_len <= 0 || !fdl_supported(min_order) || max_order < min_order) return 0;
+    const std::vector<FdlStage> st = fdl_layout(kernel_len, min_order, max_order);
+    for (int i = 0; i < (int)st.size() && i < cap; i++) {
+        if (part_size) part_size[i] = st[(size_t)i].part_size;
+        if (count) count[i] = st[(size_t)i].count;
+        if (ir_offset) ir_offset[i] = st[(size_t)i].ir_offset;
+    }
+    return (int)st.size();
+}
 int adsp_partitioned_channels(const adsp_plan *p) { return (p && p->kind == PLAN_PART) ? p->channels : 0; }
 int adsp_partitioned_internal_stage_count(const adsp_plan *p) { return (p && p->fdl) ? fdl_stage_count(p->fdl) : 0; }
 adsp_status adsp_partitioned_internal_stage_info(const adsp_plan *p, int index, int *part_size, int *count, int64_t *ir_offset) {

@@ -154,7 +154,9 @@ adsp_status direct_device(adsp_ctx *ctx, const T *d_a, long long n, long long a_
 
 // Streaming partitioned convolution on a frequency-domain delay line, many channels per launch (fdl.cu)
 struct FdlEngine;
+struct FdlStage { int part_size; int count; long long ir_offset; };
 bool fdl_supported(int min_order);
+std::vector<FdlStage> fdl_layout(long long K, int min_order, int max_order);
 adsp_status fdl_create(adsp_ctx *ctx, const void *d_kernel, long long K, int min_order, int max_order, int channels,
                        adsp_precision prec, FdlEngine **out);
 void fdl_destroy(FdlEngine *e);

@@ -436,28 +436,38 @@ adsp_status fdl_process_t(FdlEngine *e, const T *in, long long n, long long in_s
 
 bool fdl_supported(int min_order) { return min_order >= 3 && min_order <= 24; }
 
+// Internal stage layout (pure host arithmetic): sizes L*2^s with one partition each, capped at min(2048, 2^maxOrder);
+// the last stage holds all remaining partitions.  Invariant: part_size <= ir_offset + L + 1 for every stage.
+std::vector<FdlStage> fdl_layout(long long K, int min_order, int max_order) {
+    std::vector<FdlStage> out;
+    const long long L = 1LL << min_order;
+    long long bmax = std::min<long long>(FDL_MAX_B, 1LL << std::min(max_order, 30));
+    if (bmax < 8) bmax = 8;
+    long long off = 0, B = std::min(L, bmax);
+    while (off < K) {
+        const bool last = (B >= bmax) || (off + B >= K);
+        const int count = last ? (int)((K - off + B - 1) / B) : 1;
+        out.push_back({(int)B, count, off});
+        off += (long long)count * B;
+        if (last) break;
+        B *= 2;
+    }
+    return out;
+}
+
 adsp_status fdl_create(adsp_ctx *ctx, const void *d_kernel, long long K, int min_order, int max_order, int channels,
                        adsp_precision prec, FdlEngine **out) {
     *out = nullptr;
     if (!fdl_supported(min_order) || channels <= 0) return ADSP_ERR_INVALID_ARG;
     FdlEngine *e = new FdlEngine();
     e->ctx = ctx; e->prec = prec; e->K = K; e->latency = 1 << min_order; e->channels = channels; e->pairs = (channels + 1) / 2;
-    const long long L = e->latency;
-    long long bmax = std::min<long long>(FDL_MAX_B, 1LL << std::min(max_order, 30));
-    if (bmax < 8) bmax = 8;
-    // stage layout (file header): sizes L*2^s capped at bmax; with L > bmax a single stage of bmax
-    long long off = 0, B = std::min(L, bmax);
-    while (off < K) {
+    for (const FdlStage &st : fdl_layout(K, min_order, max_order)) {
         StageGeom g{};
-        g.B = (int)B; g.off = off;
-        const bool last = (B >= bmax) || (off + B >= K);
-        g.count = last ? (int)((K - off + B - 1) / B) : 1;
-        g.ring = g.count + (int)(FDL_CHUNK / B) + 2;
+        g.B = st.part_size; g.count = st.count; g.off = st.ir_offset;
+        g.ring = g.count + (int)(FDL_CHUNK / g.B) + 2;
         e->stages.push_back(g);
-        off += (long long)g.count * B;
-        if (last) break;
-        B *= 2;
     }
+    const long long L = e->latency;
     const long long bl = e->stages.back().B;
     e->HX = 2 * bl;
     long long need = FDL_CHUNK + e->stages.back().off + 2 * bl + L + 64;

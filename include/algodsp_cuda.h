@@ -211,6 +211,8 @@ ADSP_API adsp_status adsp_partitioned_process_in_place_batch(adsp_plan *plan, vo
 ADSP_API adsp_status adsp_partitioned_process_in_place_batch_device(adsp_plan *plan, void *block_dev, int64_t n, int64_t stride);
 ADSP_API int adsp_partitioned_channels(const adsp_plan *plan);
 /* Internal stage layout of the delay-line engine (diagnostic; StageCount/StageInfo report the reference's layout). */
+ADSP_API int adsp_partitioned_plan_layout(int64_t kernel_len, int min_block_order, int max_block_order, int *part_size, int *count,
+                                          int64_t *ir_offset, int cap);   /* same layout, no plan and no GPU needed */
 ADSP_API int adsp_partitioned_internal_stage_count(const adsp_plan *plan);
 ADSP_API adsp_status adsp_partitioned_internal_stage_info(const adsp_plan *plan, int index, int *part_size, int *count,
                                                           int64_t *ir_offset);

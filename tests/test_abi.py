@@ -84,3 +84,26 @@ def test_product_package_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle" not in txt.lower() or f == "siggen.py", f"{f} mentions the oracle"
+
+
+def test_partitioned_delay_line_layout_invariants():
+    """Host arithmetic of the streaming engine's stage layout (csrc/fdl.cu fdl_layout), no GPU: partitions cover the IR,
+    are contiguous, and every stage can wait for whole blocks and still meet the latency (size <= offset + latency + 1)."""
+    import ctypes as C
+    from algo_dsp_b200 import _lib as L
+    lib = L.load()
+    for K in (1, 7, 128, 129, 5000, 96000, 288000, 1 << 20):
+        for mn in (3, 5, 7, 11, 12, 13):
+            for mx in (mn, mn + 2, 13, 20):
+                if mx < mn:
+                    continue
+                ps, cnt, off = (C.c_int * 32)(), (C.c_int * 32)(), (C.c_int64 * 32)()
+                k = lib.adsp_partitioned_plan_layout(K, mn, mx, ps, cnt, off, 32)
+                assert 1 <= k <= 32
+                lat, pos = 1 << mn, 0
+                for i in range(k):
+                    assert off[i] == pos and ps[i] <= off[i] + lat + 1 and ps[i] <= max(8, min(2048, 1 << mx))
+                    assert ps[i] & (ps[i] - 1) == 0 and cnt[i] >= 1
+                    pos += ps[i] * cnt[i]
+                assert pos >= K and pos - K < ps[k - 1]
+    assert lib.adsp_partitioned_plan_layout(100, 2, 5, None, None, None, 0) == 0      # minBlockOrder < 3: no delay-line engine
