@@ -90,7 +90,8 @@ FftChoice make_choice(long long Kp, long long N) {
     else {
         // rows of 2048 points run as 128-thread CTAs (4 per SM); 2^20-point transforms keep 4096-point
         // rows so that the column transforms stay at N1 = 256
-        long long n2 = env_ll("ADSP_FFT_N2", N >= (1LL << 20) ? 4096 : 2048);
+        // 2^16 = 256 x 256 needs only four radix-16 passes (measured +6 % over 32 x 2048)
+        long long n2 = env_ll("ADSP_FFT_N2", N >= (1LL << 20) ? 4096 : (N == (1LL << 16) ? 256 : 2048));
         if (n2 > N / 16) n2 = N / 16;
         if (n2 < 256) n2 = 256;
         while (N / n2 > 1024) n2 *= 2;
@@ -124,6 +125,9 @@ FftChoice choose_fft(long long K) {
         N = next_pow2_ll(8 * Kp);
         if (N < 256) N = 256;
         if (N > NMAX) N = NMAX;
+        // up to ~1600 taps the single-kernel 4096-point transform beats the smallest four-step ones although less of it
+        // is output (measured, 256 ch x 2^20: K=1000 150 vs 121, K=1500 130 vs 122, K=2000 107 vs 119 Gsamples/s)
+        if (N > 4096 && Kp <= 1600 && NMAX >= 4096) N = 4096;
     } else {
         parts = (int)((K + NBIG / 2 - 1) / (NBIG / 2));
         Kp = (K + parts - 1) / parts;
