@@ -368,7 +368,7 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         # dominant kernel = the one with the largest exclusive device time (agrees with the ncu launch list:
-        # profiles/r01_launches_bench_h_summary.txt)
+        # profiles/r01_launches_bench_k_summary.txt)
         kinds = ("rows", "cols_fwd", "cols_inv", "full", "fused")
         dom = max(kinds, key=lambda k: ktimes_excl[k][0])
         step_bytes = channels * OUT_LEN * ALGO_BYTES_PER_SAMPLE
