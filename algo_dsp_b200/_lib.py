@@ -78,6 +78,10 @@ PROTOTYPES = {
     "adsp_plan_process_device": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64]),
     "adsp_plan_sync": (C.c_int, [c_vp]),
     "adsp_partitioned_create": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, C.c_int, C.c_int, C.POINTER(c_vp)]),
+    "adsp_shard_channel_range": (None, [c_i64, C.c_int, C.c_int, C.POINTER(c_i64), C.POINTER(c_i64)]),
+    "adsp_shard_time": (None, [c_i64, c_i64, C.c_int, C.c_int] + [C.POINTER(c_i64)] * 5),
+    "adsp_plans_process_batch": (C.c_int, [C.POINTER(c_vp), C.c_int, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64]),
+    "adsp_plans_process_long": (C.c_int, [C.POINTER(c_vp), C.c_int, c_vp, c_i64, c_vp, c_i64]),
     "adsp_deconv_out_len": (c_i64, [c_i64, c_i64]),
     "adsp_deconvolve": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, C.c_int, C.c_double, C.c_double, C.c_double, c_vp, c_i64]),
     "adsp_inverse_filter": (C.c_int, [c_vp, c_vp, c_i64, c_i64, C.c_double, c_vp]),

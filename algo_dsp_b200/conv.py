@@ -500,6 +500,28 @@ def NewOverlapAdd(kernel, blockSize=0, ctx=None, dtype=np.float64):
     return OverlapAdd(kernel, blockSize, ctx, dtype)
 
 
+def ProcessBatchMulti(plans, x2d, out=None):
+    """One host call over several GPUs: `plans` are OverlapSave/OverlapAdd plans of the same kernel, one per Context
+    (device); channels (rows) are split contiguously across them, no collective (adsp_plans_process_batch)."""
+    p0 = plans[0]
+    x = np.ascontiguousarray(x2d, dtype=p0._dtype)
+    ol = x.shape[1] + p0.KernelLen() - 1
+    y = np.empty((x.shape[0], ol), dtype=p0._dtype) if out is None else out
+    arr = (C.c_void_p * len(plans))(*[p._h for p in plans])
+    _check(L.load().adsp_plans_process_batch(arr, len(plans), _p(x), x.shape[1], x.shape[0], x.shape[1], _p(y), y.shape[1]))
+    return y
+
+
+def ProcessLongMulti(plans, x):
+    """One long signal over several GPUs by time block with a (K-1) halo (adsp_plans_process_long)."""
+    p0 = plans[0]
+    xx = np.ascontiguousarray(x, dtype=p0._dtype)
+    y = np.empty(xx.size + p0.KernelLen() - 1, dtype=p0._dtype)
+    arr = (C.c_void_p * len(plans))(*[p._h for p in plans])
+    _check(L.load().adsp_plans_process_long(arr, len(plans), _p(xx), xx.size, _p(y), y.size))
+    return y
+
+
 class PartitionedConvolution(_Plan):
     """PartitionedConvolutionT -- partitioned.go:27 (f64: PartitionedConvolution, f32: PartitionedConvolution32).
     channels > 1: that many independent streams through one IR, one launch set per call (rows of 2-D blocks)."""

@@ -3,6 +3,7 @@
 // conv_kernels.cuh / aux_kernels.cuh.  There is no CPU fallback anywhere in this file.
 #include <algorithm>
 #include <cmath>
+#include <thread>
 
 #include "aux_kernels.cuh"
 #include "engine.cuh"
@@ -1129,6 +1130,91 @@ adsp_status adsp_plan_process(adsp_plan *p, const void *in, int64_t n, void *out
 }
 
 adsp_status adsp_plan_sync(adsp_plan *p) { return p ? adsp_ctx_sync(p->ctx) : ADSP_ERR_INVALID_ARG; }
+
+// ---------------------------------------------------------------- several GPUs from one host process
+// Shards are independent: contiguous channel ranges, or time blocks of one long signal with a (K-1) halo read from
+// the source (the rule of overlap_save.go:205-215 at shard granularity; the last shard also emits the K-1 tail,
+// :224-251).  No collective; one host thread per plan (= per GPU) drives that plan's own streams.
+void adsp_shard_channel_range(int64_t channels, int rank, int world, int64_t *lo, int64_t *hi) {
+    if (world < 1) world = 1;
+    const int64_t base = channels / world, rem = channels % world;
+    const int64_t l = rank * base + std::min<int64_t>(rank, rem);
+    if (lo) *lo = l;
+    if (hi) *hi = l + base + (rank < rem ? 1 : 0);
+}
+
+void adsp_shard_time(int64_t n, int64_t kernel_len, int rank, int world, int64_t *out_lo, int64_t *out_hi, int64_t *in_lo,
+                     int64_t *in_hi, int64_t *skip) {
+    if (world < 1) world = 1;
+    const int64_t out_len = n + kernel_len - 1;
+    int64_t S = (n + world - 1) / world;
+    S = (S + 31) / 32 * 32;                                                    // 256-byte aligned shard starts
+    const int64_t last_rank = std::min<int64_t>(world - 1, S > 0 ? (n + S - 1) / S - 1 : 0);   // owns the K-1 tail
+    int64_t olo = out_len, ohi = out_len, ilo = n, ihi = n, sk = 0;              // ranks past the signal own nothing
+    if (rank <= last_rank) {
+        const int64_t lo = std::min<int64_t>((int64_t)rank * S, n), hi = std::min<int64_t>((int64_t)(rank + 1) * S, n);
+        olo = lo;
+        ohi = (rank == last_rank) ? out_len : hi;
+        ilo = std::max<int64_t>(0, lo - (kernel_len - 1));
+        ihi = hi;
+        sk = lo - ilo;
+    }
+    if (out_lo) *out_lo = olo;
+    if (out_hi) *out_hi = ohi;
+    if (in_lo) *in_lo = ilo;
+    if (in_hi) *in_hi = ihi;
+    if (skip) *skip = sk;
+}
+
+adsp_status adsp_plans_process_batch(adsp_plan *const *plans, int nplans, const void *in, int64_t n, int64_t channels,
+                                     int64_t in_stride, void *out, int64_t out_stride) {
+    if (!plans || nplans < 1) return ADSP_ERR_INVALID_ARG;
+    for (int i = 0; i < nplans; i++)
+        if (!plans[i] || plans[i]->prec != plans[0]->prec || plans[i]->K != plans[0]->K) return ADSP_ERR_INVALID_ARG;
+    if (n <= 0) return ADSP_ERR_EMPTY_INPUT;
+    const size_t es = plans[0]->prec == ADSP_F64 ? 8 : 4;
+    std::vector<adsp_status> st((size_t)nplans, ADSP_OK);
+    std::vector<std::thread> th;
+    for (int r = 0; r < nplans; r++) {
+        int64_t lo, hi;
+        adsp_shard_channel_range(channels, r, nplans, &lo, &hi);
+        if (hi <= lo) continue;
+        th.emplace_back([=, &st] {
+            st[(size_t)r] = adsp_plan_process_batch(plans[r], (const char *)in + (size_t)lo * (size_t)in_stride * es, n, hi - lo, in_stride,
+                                                    (char *)out + (size_t)lo * (size_t)out_stride * es, out_stride);
+        });
+    }
+    for (auto &t : th) t.join();
+    for (adsp_status s : st) if (s != ADSP_OK) return s;
+    return ADSP_OK;
+}
+
+adsp_status adsp_plans_process_long(adsp_plan *const *plans, int nplans, const void *in, int64_t n, void *out, int64_t out_len) {
+    if (!plans || nplans < 1) return ADSP_ERR_INVALID_ARG;
+    for (int i = 0; i < nplans; i++)
+        if (!plans[i] || plans[i]->prec != plans[0]->prec || plans[i]->K != plans[0]->K) return ADSP_ERR_INVALID_ARG;
+    if (n <= 0) return ADSP_ERR_EMPTY_INPUT;
+    const int64_t K = plans[0]->K;
+    if (out_len != n + K - 1) { set_error("conv: buffer length mismatch"); return ADSP_ERR_LENGTH_MISMATCH; }
+    const size_t es = plans[0]->prec == ADSP_F64 ? 8 : 4;
+    std::vector<adsp_status> st((size_t)nplans, ADSP_OK);
+    std::vector<std::thread> th;
+    for (int r = 0; r < nplans; r++) {
+        int64_t olo, ohi, ilo, ihi, skip;
+        adsp_shard_time(n, K, r, nplans, &olo, &ohi, &ilo, &ihi, &skip);
+        if (ohi <= olo) continue;
+        th.emplace_back([=, &st] {
+            const int64_t seg = ihi - ilo;
+            std::vector<char> tmp((size_t)(seg + K - 1) * es);          // full convolution of the shard's segment (halo included)
+            adsp_status s = adsp_plan_process(plans[r], (const char *)in + (size_t)ilo * es, seg, tmp.data(), seg + K - 1);
+            if (s == ADSP_OK) memcpy((char *)out + (size_t)olo * es, tmp.data() + (size_t)skip * es, (size_t)(ohi - olo) * es);
+            st[(size_t)r] = s;
+        });
+    }
+    for (auto &t : th) t.join();
+    for (adsp_status s : st) if (s != ADSP_OK) return s;
+    return ADSP_OK;
+}
 
 }  // extern "C"
 

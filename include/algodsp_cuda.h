@@ -167,6 +167,20 @@ ADSP_API adsp_status adsp_plan_process_device(adsp_plan *plan, const void *in_de
                                               int64_t in_stride, void *out_dev, int64_t out_stride);
 ADSP_API adsp_status adsp_plan_sync(adsp_plan *plan);
 
+/* ---------------------------------------------------------------- several GPUs from one host process
+ * Shards are independent (no collective): contiguous channel ranges, or time blocks of one long signal with a
+ * (kernel_len - 1) halo read from the source -- the rule of overlap_save.go:205-215 at shard granularity, the last
+ * shard also emitting the tail (:224-251).  The two helpers are pure arithmetic (also what one-process-per-GPU
+ * launchers use: algo_dsp_b200/shard.py); the adsp_plans_* calls drive one plan per GPU from one host thread each. */
+ADSP_API void adsp_shard_channel_range(int64_t channels, int rank, int world, int64_t *lo, int64_t *hi);
+ADSP_API void adsp_shard_time(int64_t n, int64_t kernel_len, int rank, int world, int64_t *out_lo, int64_t *out_hi,
+                              int64_t *in_lo, int64_t *in_hi, int64_t *skip);
+/* plans[i]: OverlapSave/OverlapAdd plans of the SAME kernel and precision, one per context/device; host pointers */
+ADSP_API adsp_status adsp_plans_process_batch(adsp_plan *const *plans, int nplans, const void *in, int64_t n, int64_t channels,
+                                              int64_t in_stride, void *out, int64_t out_stride);
+ADSP_API adsp_status adsp_plans_process_long(adsp_plan *const *plans, int nplans, const void *in, int64_t n, void *out,
+                                             int64_t out_len);
+
 /* ---------------------------------------------------------------- deconvolution, float64 like the reference
  * Deconvolve(signal, kernel, opts) deconvolve.go:72: circular spectral division at N = nextPow2(len(signal));
  * method 0 = DeconvNaive (ErrDivisionByZero when a bin has |H| < 1e-15; the bin index is in adsp_last_error),

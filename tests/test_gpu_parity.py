@@ -358,3 +358,21 @@ def test_single_zero_padded_block_lengths(conv, oracle, K, n):
     yb = conv.NewOverlapSave(h, 0).ProcessBatch(xb)
     for c in range(3):
         assert rel(yb[c], oracle.overlap_save(h, 0, xb[c])) <= TOL64
+
+
+def test_one_process_many_plans_channel_and_time_sharding(conv, oracle):
+    """adsp_plans_process_batch / adsp_plans_process_long: one host call drives several plans (one per context; here
+    three contexts on the same device stand in for three GPUs).  Same results as a single plan, no collective."""
+    K, n, channels = 3000, 40000, 7
+    h = G.decaying_ir(K)
+    ctxs = [conv.Context(0) for _ in range(3)]
+    plans = [conv.OverlapSave(h, 0, ctx=c) for c in ctxs]
+    x = np.stack([G.white(n, seed=c) for c in range(channels)])
+    y = conv.ProcessBatchMulti(plans, x)
+    for c in range(channels):
+        assert rel(y[c], oracle.overlap_save(h, 0, x[c])) <= TOL64
+    xl = G.white(300000, seed=9)
+    yl = conv.ProcessLongMulti(plans, xl)
+    assert len(yl) == len(xl) + K - 1 and rel(yl, oracle.overlap_save(h, 0, xl)) <= TOL64
+    short = G.white(50, seed=1)                          # fewer samples than shards * alignment: trailing plans idle
+    assert rel(conv.ProcessLongMulti(plans, short), oracle.overlap_save(h, 0, short)) <= TOL64

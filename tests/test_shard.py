@@ -80,3 +80,22 @@ def test_world_size_2_gloo(oracle):
     assert G.rel_l2(full, oracle.overlap_save(h, 0, x)) <= 1e-13
     want = np.array([oracle.overlap_save(h, 0, G.white(2000, seed=100 + c)).sum() for c in range(channels)])
     assert np.allclose(sums, want, rtol=1e-12)
+
+
+def test_c_abi_shard_helpers_match_the_python_planner():
+    """adsp_shard_channel_range / adsp_shard_time (pure arithmetic in the C library, no GPU) == algo_dsp_b200/shard.py."""
+    import ctypes as C
+    from algo_dsp_b200 import _lib as L, shard
+    lib = L.load()
+    for channels, world in ((64, 8), (7, 3), (5, 8), (1024, 2), (0, 4)):
+        for r in range(world):
+            lo, hi = C.c_int64(), C.c_int64()
+            lib.adsp_shard_channel_range(channels, r, world, C.byref(lo), C.byref(hi))
+            assert (lo.value, hi.value) == shard.channel_range(channels, r, world)
+    for n, K, world in ((400000, 5000, 4), (1000, 300, 8), (100, 7, 8), (1 << 20, 1 << 14, 2), (33, 64, 3), (1 << 31, 1 << 20, 8), (1, 1, 5)):
+        ref = shard.time_shards(n, K, world)
+        for r in range(world):
+            v = [C.c_int64() for _ in range(5)]
+            lib.adsp_shard_time(n, K, r, world, *[C.byref(x) for x in v])
+            s = ref[r]
+            assert tuple(x.value for x in v) == (s.out_lo, s.out_hi, s.in_lo, s.in_hi, s.skip), (n, K, world, r)
