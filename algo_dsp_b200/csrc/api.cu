@@ -221,6 +221,26 @@ adsp_status direct_device(adsp_ctx *ctx, const T *d_a, long long n, long long a_
     const long long grid = tiles * batch;
     if (grid <= 0) return ADSP_OK;
     if (grid > 0x7fffffffLL) { set_error("direct: grid too large"); return ADSP_ERR_INVALID_ARG; }
+    // at most 64 taps shared by every channel (the auto-select case): taps as a kernel parameter (constant-bank operands)
+    static const bool ctaps = env_ll("ADSP_DIRECT_CTAPS", 1) != 0;
+    if (ctaps && m <= DIRECT_MC && (b_stride == 0 || batch == 1)) {
+        DirectTaps<T> taps;
+        for (int i = 0; i < DIRECT_MC; i++) taps.v[i] = (T)0;
+        ADSP_CUDA(cudaMemcpyAsync(taps.v, d_b, (size_t)m * sizeof(T), cudaMemcpyDeviceToHost, ctx->main));
+        ADSP_CUDA(cudaStreamSynchronize(ctx->main));
+        LaunchTimer lt(ctx, ctx->main, KK_DIRECT);
+        const unsigned g = (unsigned)grid;
+        if (m == DIRECT_MC) {
+            if (exact) direct_conv_ctaps_kernel<T, false, false><<<g, DIRECT_THREADS, 0, ctx->main>>>(d_a, n, a_stride, taps, (int)m, d_out, out_stride, tiles);
+            else direct_conv_ctaps_kernel<T, true, false><<<g, DIRECT_THREADS, 0, ctx->main>>>(d_a, n, a_stride, taps, (int)m, d_out, out_stride, tiles);
+        } else {
+            if (exact) direct_conv_ctaps_kernel<T, false, true><<<g, DIRECT_THREADS, 0, ctx->main>>>(d_a, n, a_stride, taps, (int)m, d_out, out_stride, tiles);
+            else direct_conv_ctaps_kernel<T, true, true><<<g, DIRECT_THREADS, 0, ctx->main>>>(d_a, n, a_stride, taps, (int)m, d_out, out_stride, tiles);
+        }
+        count_launch(ctx);
+        ADSP_CUDA(cudaGetLastError());
+        return ADSP_OK;
+    }
     LaunchTimer lt(ctx, ctx->main, KK_DIRECT);
     if (exact)
         direct_conv_kernel<T, false><<<(unsigned)grid, DIRECT_THREADS, 0, ctx->main>>>(d_a, n, a_stride, d_b, m, b_stride, d_out, out_stride, tiles);

@@ -97,6 +97,59 @@ direct_conv_kernel(const T *__restrict__ a, long long n, long long a_stride,
 #undef ADSP_SA
 }
 
+// Same kernel for the strategy auto-select case (conv.go:209-211: at most 64 taps, one kernel for every channel):
+// the taps travel as a kernel PARAMETER, so each tap is a constant-bank operand of the DFMA instead of a
+// shared-memory broadcast load -- one LSU wavefront less per 8 DFMA in a kernel whose LSU and FP64 pipes are
+// otherwise co-limited (2 + 1 wavefronts vs 4 FP64 issue cycles per tap).
+template <typename T> struct DirectTaps { T v[DIRECT_MC]; };
+
+template <typename T, bool FUSED, bool GUARD>
+__global__ void __launch_bounds__(DIRECT_THREADS)
+direct_conv_ctaps_kernel(const T *__restrict__ a, long long n, long long a_stride, const __grid_constant__ DirectTaps<T> taps, int m,
+                         T *__restrict__ out, long long out_stride, long long tiles_per_ch) {
+    __shared__ T sa[(DIRECT_TILE + DIRECT_MC) + ((DIRECT_TILE + DIRECT_MC) >> DIRECT_PAD_SHIFT) + 1];
+#define ADSP_SA(i) sa[(i) + ((i) >> DIRECT_PAD_SHIFT)]
+    const long long ch = blockIdx.x / tiles_per_ch;
+    const long long tile = blockIdx.x - ch * tiles_per_ch;
+    const long long k0 = tile * DIRECT_TILE;
+    const T *ac = a + ch * a_stride;
+    const long long out_len = n + m - 1;
+    const int t = threadIdx.x;
+    const long long abase = k0 - (DIRECT_MC - 1);
+    for (int i = t; i < DIRECT_TILE + DIRECT_MC - 1; i += DIRECT_THREADS) {
+        const long long ai = abase + i;
+        ADSP_SA(i) = (ai >= 0 && ai < n) ? ac[ai] : (T)0;
+    }
+    __syncthreads();
+    const int base = t * DIRECT_RO;
+    T acc[DIRECT_RO], w[DIRECT_RO];
+#pragma unroll
+    for (int r = 0; r < DIRECT_RO; r++) acc[r] = (T)0;
+#pragma unroll
+    for (int r = 0; r < DIRECT_RO - 1; r++) w[r + 1] = ADSP_SA(base + r);
+#pragma unroll
+    for (int jj = DIRECT_MC - 1; jj >= 0; jj--) {            // highest tap first: input index ascends (reference order)
+#pragma unroll
+        for (int r = 0; r < DIRECT_RO - 1; r++) w[r] = w[r + 1];
+        w[DIRECT_RO - 1] = ADSP_SA(base + DIRECT_RO - 1 + (DIRECT_MC - 1) - jj);
+        if (GUARD && jj >= m) continue;                        // padded taps are skipped, not multiplied by zero
+        const T bj = taps.v[jj];
+#pragma unroll
+        for (int r = 0; r < DIRECT_RO; r++) {
+            if (FUSED) acc[r] = fma(w[r], bj, acc[r]);
+            else if (sizeof(T) == 8) acc[r] = __dadd_rn((double)acc[r], __dmul_rn((double)w[r], (double)bj));
+            else acc[r] = __fadd_rn((float)acc[r], __fmul_rn((float)w[r], (float)bj));
+        }
+    }
+    T *oc = out + ch * out_stride;
+#pragma unroll
+    for (int r = 0; r < DIRECT_RO; r++) {
+        const long long k = k0 + (long long)t * DIRECT_RO + r;
+        if (k < out_len) oc[k] = acc[r];
+    }
+#undef ADSP_SA
+}
+
 // DirectCircular (dsp/conv/conv.go:176-189): dst[(i+j)%n] += a[i]*b[j]; per output the terms
 // arrive in order of ascending i.
 template <typename T>
