@@ -84,6 +84,12 @@ def test_product_package_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle" not in txt.lower() or f == "siggen.py", f"{f} mentions the oracle"
+    # development helpers outside tests/ must not use the checker either (those that do live in tests/tools/)
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "tools")):
+        for f in files:
+            if f.endswith((".py", ".sh", ".cu")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "from oracle" not in txt and "import oracle" not in txt, f"tools/{f} imports the oracle"
 
 
 def test_partitioned_delay_line_layout_invariants():

@@ -1,6 +1,6 @@
 """One timing of the bench workload under the current env (ADSP_LIB_PATH etc.): prints ms and Gs/s; checks one channel."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from algo_dsp_b200 import conv, siggen as G
 K = int(os.environ.get("BK", 96000)); n = int(os.environ.get("BN", 480000)); ch = int(os.environ.get("BCH", 256))

@@ -4,11 +4,11 @@ work of the 8-GPU decomposition, run back to back on one device. 
 windows against the CPU oracle (first 2^22 outputs, the last 2^22 including the tail, every shard
 boundary +- 2^20), fp64 and fp32.
 
-    python tools/config5_run.py [log2_n=31] [log2_K=20] [shards=8] [f64|f32|both]
+    python tests/tools/config5_run.py [log2_n=31] [log2_K=20] [shards=8] [f64|f32|both]
 Prints one JSON line per precision.
 """
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 from algo_dsp_b200 import conv, siggen as G

@@ -1,6 +1,6 @@
 """Timings of the other BASELINE configs (device-resident, reduced batch where noted)."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch, ctypes as C
 from algo_dsp_b200 import conv, siggen as G, _lib as L
 ctx = conv.default_context(); lib = L.load()

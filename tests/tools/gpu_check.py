@@ -1,6 +1,6 @@
 """Quick GPU sanity sweep: library vs oracle over many shapes; prints worst errors and timings."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from algo_dsp_b200 import conv
 from oracle import oracle as O

@@ -1,7 +1,7 @@
 """One host process, one plan per visible GPU: end-to-end (host buffers) throughput of the bench workload through
-adsp_plans_process_batch, and the time-block sharded long-signal call.  python tools/multi_gpu_one_process.py"""
+adsp_plans_process_batch, and the time-block sharded long-signal call.  python tests/tools/multi_gpu_one_process.py"""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from algo_dsp_b200 import conv, siggen as G
 from oracle import oracle as O

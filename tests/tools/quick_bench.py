@@ -1,6 +1,6 @@
 """Device-resident timing sweep of the OLS path (development aid; bench.py is the contract)."""
 import os, sys, time, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 from algo_dsp_b200 import conv
