@@ -44,7 +44,7 @@ __device__ __forceinline__ cpx<T> twiddle_any(const cpx<T> *__restrict__ tw_hi, 
 }
 
 template <typename T, int M>
-__global__ void __launch_bounds__(ColShapeMR<M>::THREADS, ColShapeMR<M>::MIN_CTAS)
+__global__ void __launch_bounds__(ColShapeMR<M>::THREADS, min_ctas_for<T>(ColShapeMR<M>::THREADS > 128 ? 128 : ColShapeMR<M>::THREADS, ColShapeMR<M>::MIN_CTAS))
 fftconv_cols_fwd_mr(ConvGeom g, const T *__restrict__ x, cpx<T> *__restrict__ scratch, int N2, unsigned N,
                     const cpx<T> *__restrict__ tw, const cpx<T> *__restrict__ tw_hi, const cpx<T> *__restrict__ tw_lo,
                     long long pair0, int ntiles) {
@@ -102,7 +102,7 @@ fftconv_cols_fwd_mr(ConvGeom g, const T *__restrict__ x, cpx<T> *__restrict__ sc
 }
 
 template <typename T, int M>
-__global__ void __launch_bounds__(ColShapeMR<M>::THREADS, ColShapeMR<M>::MIN_CTAS)
+__global__ void __launch_bounds__(ColShapeMR<M>::THREADS, min_ctas_for<T>(ColShapeMR<M>::THREADS > 128 ? 128 : ColShapeMR<M>::THREADS, ColShapeMR<M>::MIN_CTAS))
 fftconv_cols_inv_mr(ConvGeom g, const cpx<T> *__restrict__ scratch, const T *__restrict__ x, T *__restrict__ y, int N2, unsigned N,
                     const cpx<T> *__restrict__ tw, const cpx<T> *__restrict__ tw_hi, const cpx<T> *__restrict__ tw_lo,
                     long long pair0, int ntiles) {
