@@ -202,6 +202,12 @@ template <typename C> __device__ __forceinline__ void geometric16(C base, C rho,
     }
 }
 
+#ifndef ADSP_COLS_MIN_CTAS_128
+#define ADSP_COLS_MIN_CTAS_128 5     // column kernels: 5 resident CTAs (102 registers) measured +2 % on 2^20-point transforms
+#endif
+#ifndef ADSP_COLS_MIN_CTAS_256
+#define ADSP_COLS_MIN_CTAS_256 2
+#endif
 #ifndef ADSP_COLS_TC_512
 #define ADSP_COLS_TC_512 8      // 256-thread CTAs (3 per SM); 16 columns / 512 threads measured 9 % slower
 #endif
@@ -213,7 +219,7 @@ template <int N1> struct ColShape {
     static constexpr int TC = (N1 <= 256) ? (ADSP_COLS_CTA_THREADS / TPF) : ((N1 == 512) ? ADSP_COLS_TC_512 : ADSP_COLS_TC_1024);  // columns per tile
     static constexpr int THREADS = TPF * TC;
     static constexpr int SMEM_ELEMS = N1 * TC;
-    static constexpr int MIN_CTAS = (THREADS <= 128) ? ADSP_MIN_CTAS_128 : ((THREADS <= 256) ? 2 : 1);
+    static constexpr int MIN_CTAS = (THREADS <= 128) ? ADSP_COLS_MIN_CTAS_128 : ((THREADS <= 256) ? ADSP_COLS_MIN_CTAS_256 : 1);
 };
 
 // ------------------------------------------------------------------------------------------
