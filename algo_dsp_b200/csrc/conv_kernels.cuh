@@ -60,6 +60,31 @@ __device__ __forceinline__ BlockIO<T> block_io(const ConvGeom &g, const T *x, T 
 
 template <typename T> __device__ __forceinline__ T ld_stream(const T *p) { return __ldcs(p); }
 
+// The element index inside a block is < N <= 2^22, so the per-element bounds tests of a tile run in 32 bits:
+// inputs  valid  <=>  (unsigned)(i - lo) < span   with lo, span clamped into [0, N];
+// outputs valid  <=>  (unsigned)o < cnt           with o = i - D.
+template <typename T> struct TileIn {
+    const T *p;          // block base (element 0 of the block; may point before the channel start, only valid indices are read)
+    int lo;
+    unsigned span;
+};
+template <typename T> __device__ __forceinline__ TileIn<T> tile_in(const BlockIO<T> &b, long long N) {
+    TileIn<T> t;
+    long long lo = b.lo < 0 ? 0 : (b.lo > N ? N : b.lo);
+    long long hi = b.hi < lo ? lo : (b.hi > N ? N : b.hi);
+    t.p = b.in; t.lo = (int)lo; t.span = (unsigned)(hi - lo);
+    return t;
+}
+template <typename T> struct TileOut {
+    T *p;                // block output base (output sample 0 of the block)
+    unsigned cnt;
+};
+template <typename T> __device__ __forceinline__ TileOut<T> tile_out(const BlockIO<T> &b, long long N) {
+    TileOut<T> t;
+    t.p = b.out; t.cnt = (unsigned)(b.cnt < 0 ? 0 : (b.cnt > N ? N : b.cnt));
+    return t;
+}
+
 
 
 // CTA shapes (compile-time knobs; tools/ builds variants with -D to A/B them on the GPU).

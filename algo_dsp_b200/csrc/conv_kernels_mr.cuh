@@ -70,14 +70,15 @@ fftconv_cols_fwd_mr(ConvGeom g, const T *__restrict__ x, cpx<T> *__restrict__ sc
             tw_rho = twiddle_any<T>(tw_hi, tw_lo, ((unsigned)n2 * (unsigned)M) % N);
         }
         if (j < 16) {
-            const BlockIO<T> a = block_io<T>(g, x, (T *)nullptr, 2 * (pair0 + pl));
-            const BlockIO<T> b = block_io<T>(g, x, (T *)nullptr, 2 * (pair0 + pl) + 1);
+            const TileIn<T> a = tile_in<T>(block_io<T>(g, x, (T *)nullptr, 2 * (pair0 + pl)), (long long)N);
+            const TileIn<T> b = tile_in<T>(block_io<T>(g, x, (T *)nullptr, 2 * (pair0 + pl) + 1), (long long)N);
             C e[M];
+            const int idx0 = j * N2 + n2;
 #pragma unroll
             for (int i = 0; i < M; i++) {
-                const long long idx = (long long)(j + 16 * i) * N2 + n2;
-                e[i].x = (idx >= a.lo && idx < a.hi) ? ld_stream(a.in + idx) : (T)0;
-                e[i].y = (idx >= b.lo && idx < b.hi) ? ld_stream(b.in + idx) : (T)0;
+                const int idx = idx0 + i * 16 * N2;
+                e[i].x = ((unsigned)(idx - a.lo) < a.span) ? ld_stream(a.p + idx) : (T)0;
+                e[i].y = ((unsigned)(idx - b.lo) < b.span) ? ld_stream(b.p + idx) : (T)0;
             }
             small_dft<M, false>(e);
 #pragma unroll
@@ -143,20 +144,15 @@ fftconv_cols_inv_mr(ConvGeom g, const cpx<T> *__restrict__ scratch, const T *__r
 #pragma unroll
         for (int km = 1; km < M; km++) e[km] = cmul_tw<true>(e[km], stw[km * 16 + j]);
         small_dft<M, true>(e);
-        const BlockIO<T> a = block_io<T>(g, x, y, 2 * (pair0 + pl));
-        const BlockIO<T> b = block_io<T>(g, x, y, 2 * (pair0 + pl) + 1);
+        const TileOut<T> a = tile_out<T>(block_io<T>(g, x, y, 2 * (pair0 + pl)), (long long)N);
+        const TileOut<T> b = tile_out<T>(block_io<T>(g, x, y, 2 * (pair0 + pl) + 1), (long long)N);
+        const int o0 = j * N2 + n2 - (int)g.D;
+        const bool acc = g.accumulate != 0;
 #pragma unroll
         for (int i = 0; i < M; i++) {
-            const long long o = (long long)(j + 16 * i) * N2 + n2 - g.D;
-            if (o >= 0) {
-                if (g.accumulate) {
-                    if (o < a.cnt) a.out[o] += e[i].x;
-                    if (o < b.cnt) b.out[o] += e[i].y;
-                } else {
-                    if (o < a.cnt) __stcs(a.out + o, e[i].x);
-                    if (o < b.cnt) __stcs(b.out + o, e[i].y);
-                }
-            }
+            const int o = o0 + i * 16 * N2;                 // o < 0 wraps to a huge unsigned: one compare does both bounds
+            if ((unsigned)o < a.cnt) { if (acc) a.p[o] += e[i].x; else __stcs(a.p + o, e[i].x); }
+            if ((unsigned)o < b.cnt) { if (acc) b.p[o] += e[i].y; else __stcs(b.p + o, e[i].y); }
         }
     }
 }
