@@ -24,6 +24,11 @@ namespace adsp {
 #ifndef ADSP_MR_MIN_CTAS
 #define ADSP_MR_MIN_CTAS (ADSP_MR_TC == 8 ? 5 : 2)   // 5 x 128 threads per SM: 102 registers, measured +3.7 % over 4
 #endif
+// 1: read the column twiddles W_N1^(j*km) straight from global memory through L1 (4.6 KB, hot on every SM) instead of
+// staging them in shared memory behind a barrier at the start of every CTA (measured: 99.0 vs 101.2 Gsamples/s, so off)
+#ifndef ADSP_MR_TW_LDG
+#define ADSP_MR_TW_LDG 0
+#endif
 #ifndef ADSP_MR_WIDE_CTAS
 #define ADSP_MR_WIDE_CTAS 3
 #endif
@@ -54,7 +59,7 @@ fftconv_cols_fwd_mr(ConvGeom g, const T *__restrict__ x, cpx<T> *__restrict__ sc
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C *buf = reinterpret_cast<C *>(smem_raw);
     C *stw = buf + CS::SMEM_ELEMS;
-    for (int i = threadIdx.x; i < CS::TW_ENTRIES; i += CS::THREADS) stw[i] = tw[i];
+    if (!ADSP_MR_TW_LDG) { for (int i = threadIdx.x; i < CS::TW_ENTRIES; i += CS::THREADS) stw[i] = tw[i]; }
     const int c = threadIdx.x % TC;
     const int j = threadIdx.x / TC;
     const int tiles_per_pair = N2 / TC;
@@ -82,7 +87,7 @@ fftconv_cols_fwd_mr(ConvGeom g, const T *__restrict__ x, cpx<T> *__restrict__ sc
             }
             small_dft<M, false>(e);
 #pragma unroll
-            for (int km = 1; km < M; km++) e[km] = cmul_tw<false>(e[km], stw[km * 16 + j]);
+            for (int km = 1; km < M; km++) e[km] = cmul_tw<false>(e[km], ADSP_MR_TW_LDG ? __ldg(&tw[km * 16 + j]) : stw[km * 16 + j]);
             // (the barrier at the end of the previous tile guarantees its readers are done with buf)
 #pragma unroll
             for (int km = 0; km < M; km++) buf[(km * 16 + j) * TC + c] = e[km];
@@ -113,7 +118,7 @@ fftconv_cols_inv_mr(ConvGeom g, const cpx<T> *__restrict__ scratch, const T *__r
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C *buf = reinterpret_cast<C *>(smem_raw);
     C *stw = buf + CS::SMEM_ELEMS;
-    for (int i = threadIdx.x; i < CS::TW_ENTRIES; i += CS::THREADS) stw[i] = tw[i];
+    if (!ADSP_MR_TW_LDG) { for (int i = threadIdx.x; i < CS::TW_ENTRIES; i += CS::THREADS) stw[i] = tw[i]; }
     const int c = threadIdx.x % TC;
     const int j = threadIdx.x / TC;
     const int tiles_per_pair = N2 / TC;
@@ -142,7 +147,7 @@ fftconv_cols_inv_mr(ConvGeom g, const cpx<T> *__restrict__ scratch, const T *__r
 #pragma unroll
         for (int km = 0; km < M; km++) e[km] = buf[(km * 16 + j) * TC + c];
 #pragma unroll
-        for (int km = 1; km < M; km++) e[km] = cmul_tw<true>(e[km], stw[km * 16 + j]);
+        for (int km = 1; km < M; km++) e[km] = cmul_tw<true>(e[km], ADSP_MR_TW_LDG ? __ldg(&tw[km * 16 + j]) : stw[km * 16 + j]);
         small_dft<M, true>(e);
         const TileOut<T> a = tile_out<T>(block_io<T>(g, x, y, 2 * (pair0 + pl)), (long long)N);
         const TileOut<T> b = tile_out<T>(block_io<T>(g, x, y, 2 * (pair0 + pl) + 1), (long long)N);
