@@ -85,3 +85,21 @@ def test_inverse_filter_and_snr_reference_checks(conv):
     assert conv.errors_is(e.value, conv.ErrEmptyKernel)
     assert conv.SNR([1, 2, 3, 4, 5], [1, 2, 3, 4, 5]) == math.inf                                # conv_test.go:633-655
     assert conv.SNR([1, 2, 3, 4, 5], [1, 2, 3]) == -math.inf and conv.SNR([], []) == -math.inf
+
+
+def test_sweep_deconvolve_with_inverse_is_a_full_convolution(conv, oracle):
+    """measure/sweep.deconvolveWithInverse (sweep.go:182-239) pads to nextPow2(n + m - 1), multiplies the spectra and keeps
+    n + m - 1 samples: the full linear convolution of the response with the inverse filter, i.e. conv.Convolve.  A sweep
+    through a known two-tap system, deconvolved with the time-reversed sweep, peaks at the system's taps."""
+    n = 1 << 15
+    sweep = G.log_sweep(n)
+    system = np.zeros(400)
+    system[0], system[300] = 1.0, 0.5
+    response = conv.Convolve(sweep, system)
+    inv = sweep[::-1].copy()
+    ir = conv.Convolve(response, inv)
+    assert len(ir) == len(response) + len(inv) - 1
+    assert G.rel_l2(ir, oracle.convolve(response, inv)) <= 1e-12
+    idx, _ = conv.FindPeak(ir)
+    assert idx == n - 1                                          # main peak at len(inv) - 1 (sweep.go:231-232)
+    assert abs(ir[n - 1 + 300] / ir[n - 1] - 0.5) < 0.05         # the echo, 300 samples later at half the height
