@@ -614,8 +614,24 @@ __global__ void corr_pointwise(cpx<T> *ZA, const cpx<T> *ZB, int N1, int N2, T s
 //     S[k] = (Z[k] + conj(Z[N-k])) / 2,   H[k] = (Z[k] - conj(Z[N-k])) / (2i),
 //     R[k] = S[k] * conj(H[k]) / (|H[k]|^2 + reg)        (reg < 0: naive S/H, bins with |H| < 1e-15 reported in *bad_bin)
 // and R[N-k] = conj(R[k]) because the result is real.  One thread handles k and N-k.
+template <typename T> __device__ __forceinline__ cpx<T> deconv_bin(cpx<T> zk, cpx<T> zm, T scale, T reg, long long k, long long *bad_bin) {
+    const T sr = (zk.x + zm.x) * (T)0.5, si = (zk.y - zm.y) * (T)0.5;          // S = (zk + conj(zm))/2
+    const T hr = (zk.y + zm.y) * (T)0.5, hi = (zm.x - zk.x) * (T)0.5;          // H = (zk - conj(zm))/(2i)
+    T den = hr * hr + hi * hi;
+    if (reg < (T)0) {
+        if (sqrt((double)den) < 1e-15) { atomicMin((unsigned long long *)bad_bin, (unsigned long long)k); den = (T)1; }
+    } else den += reg;
+    cpx<T> r;
+    r.x = (sr * hr + si * hi) / den * scale;                                     // S * conj(H) / den
+    r.y = (si * hr - sr * hi) / den * scale;
+    return r;
+}
+
+// grid.y = q: problems 2q (spectrum Z[2q]) and 2q+1 (Z[2q+1], absent when nprob is odd) share one inverse transform:
+// Q[q] = R_A + i*R_B; both R are Hermitian (real results), so Q[N-k] = conj(R_A[k]) + i*conj(R_B[k]).
 template <typename T>
-__global__ void deconv_pointwise(cpx<T> *Z, int N1, int N2, T scale, T reg, long long *bad_bin) {
+__global__ void deconv_pointwise(const cpx<T> *__restrict__ Z, cpx<T> *__restrict__ Q, int nprob, int N1, int N2, T scale, T reg,
+                                 long long *bad_bin) {
     using C = cpx<T>;
     const long long N = (long long)N1 * N2;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -626,18 +642,20 @@ __global__ void deconv_pointwise(cpx<T> *Z, int N1, int N2, T scale, T reg, long
     if (k > km) return;
     const long long m1 = km & (N1 - 1), m2 = km / N1;
     const long long midx = m1 * N2 + m2;
-    const C zk = __ldcg(&Z[idx]), zm = __ldcg(&Z[midx]);
-    const T sr = (zk.x + zm.x) * (T)0.5, si = (zk.y - zm.y) * (T)0.5;          // S = (zk + conj(zm))/2
-    const T hr = (zk.y + zm.y) * (T)0.5, hi = (zm.x - zk.x) * (T)0.5;          // H = (zk - conj(zm))/(2i)
-    T den = hr * hr + hi * hi;
-    if (reg < (T)0) {
-        if (sqrt((double)den) < 1e-15) { atomicMin((unsigned long long *)bad_bin, (unsigned long long)k); den = (T)1; }
-    } else den += reg;
-    C r;
-    r.x = (sr * hr + si * hi) / den * scale;                                     // S * conj(H) / den
-    r.y = (si * hr - sr * hi) / den * scale;
-    __stcg(&Z[idx], r);
-    if (midx != idx) { C rc; rc.x = r.x; rc.y = -r.y; __stcg(&Z[midx], rc); }
+    const int q = blockIdx.y;
+    const C *ZA = Z + (size_t)(2 * q) * N;
+    const C ra = deconv_bin<T>(__ldcg(&ZA[idx]), __ldcg(&ZA[midx]), scale, reg, k, bad_bin);
+    C rb; rb.x = (T)0; rb.y = (T)0;
+    if (2 * q + 1 < nprob) {
+        const C *ZB = ZA + N;
+        rb = deconv_bin<T>(__ldcg(&ZB[idx]), __ldcg(&ZB[midx]), scale, reg, k, bad_bin);
+    }
+    C *Qq = Q + (size_t)q * N;
+    C qk, qm;
+    qk.x = ra.x - rb.y; qk.y = ra.y + rb.x;
+    qm.x = ra.x + rb.y; qm.y = -ra.y + rb.x;
+    __stcg(&Qq[idx], qk);
+    if (midx != idx) __stcg(&Qq[midx], qm);
 }
 
 // Deconvolution with a transform that fits one CTA (N = L <= 4096): load z = signal + i*kernel, FFT, division through a

@@ -958,28 +958,39 @@ adsp_status fft_deconvolve_device(adsp_ctx *ctx, const T *sig, long long n, long
     ADSP_TRY(get_tw_table<T>(ctx, ch.N2, &tw_rows));
     ADSP_TRY(get_tw_table<T>(ctx, ch.N1, &tw_cols));
     ADSP_TRY(get_tw4_tables<T>(ctx, ch.N, &tw_hi, &tw_lo));
-    ADSP_TRY(ctx->scratch.reserve((size_t)N * sizeof(cpx<T>)));
+    // groups of problems whose spectra (one slot each) and shared inverse transforms (one slot per two problems) fit the
+    // L2 scratch budget; two problems share an inverse transform (Q = R_A + i*R_B, results in re / im)
+    const size_t slot = (size_t)N * sizeof(cpx<T>);
+    long long G = (long long)(ctx->scratch_budget / slot) * 2 / 3;
+    G = std::max<long long>(2, G - (G & 1));
+    G = std::min<long long>(G, std::min<long long>(batch + (batch & 1), 4096));
+    const long long GQ = (G + 1) / 2;
+    ADSP_TRY(ctx->scratch.reserve((size_t)(G + GQ) * slot));
     cpx<T> *Z = (cpx<T> *)ctx->scratch.p;
+    cpx<T> *Q = Z + (size_t)G * N;
     ConvGeom g{};
     g.n = N; g.out_len = out_len; g.in_stride = 0; g.out_stride = out_stride; g.S = N; g.D = 0;
-    g.total_blocks = 1; g.in_shift = 0; g.out_shift = 0; g.nblk = 1; g.accumulate = 0;
+    g.total_blocks = batch; g.in_shift = 0; g.out_shift = 0; g.nblk = 1; g.accumulate = 0;
     cudaStream_t st = ctx->main;
     const T scale = (T)(1.0L / (long double)N);
-    for (long long p = 0; p < batch; p++) {
-#define ADSP_DC_COLS(n1) case n1: ADSP_TRY((launch_corr_cols_t<T, n1>(ctx, st, sig, n, s_stride, ker, m, k_stride, Z, ch.N2, ch.lgN, tw_cols, tw_hi, tw_lo, p, 1, 0))); break;
+    for (long long p0 = 0; p0 < batch; p0 += G) {
+        const int np = (int)std::min<long long>(G, batch - p0), nq = (np + 1) / 2;
+#define ADSP_DC_COLS(n1) case n1: ADSP_TRY((launch_corr_cols_t<T, n1>(ctx, st, sig, n, s_stride, ker, m, k_stride, Z, ch.N2, ch.lgN, tw_cols, tw_hi, tw_lo, p0, np, 0))); break;
         switch (ch.N1) {
             ADSP_DC_COLS(16) ADSP_DC_COLS(32) ADSP_DC_COLS(64) ADSP_DC_COLS(128) ADSP_DC_COLS(256) ADSP_DC_COLS(512) ADSP_DC_COLS(1024)
         default: set_error("deconvolve: unsupported transform shape"); return ADSP_ERR_INVALID_ARG;
         }
 #undef ADSP_DC_COLS
-        ADSP_TRY((launch_rows<T, 1>(ctx, st, ch.N2, Z, (const cpx<T> *)nullptr, Z, (T)1, ch.N1, tw_rows, 1)));
+        ADSP_TRY((launch_rows<T, 1>(ctx, st, ch.N2, Z, (const cpx<T> *)nullptr, Z, (T)1, ch.N1, tw_rows, np)));
         {
             LaunchTimer lt(ctx, st, KK_OTHER);
-            deconv_pointwise<T><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(Z, ch.N1, ch.N2, scale, reg, d_bad);
+            dim3 grid((unsigned)((N + 255) / 256), (unsigned)nq);
+            deconv_pointwise<T><<<grid, 256, 0, st>>>(Z, Q, np, ch.N1, ch.N2, scale, reg, d_bad);
             count_launch(ctx);
         }
-        ADSP_TRY((launch_rows<T, 2>(ctx, st, ch.N2, Z, (const cpx<T> *)nullptr, Z, (T)1, ch.N1, tw_rows, 1)));
-        ADSP_TRY(launch_cols<T>(ctx, st, ch.N1, true, g, (const T *)nullptr, out + p * out_stride, Z, ch.N2, ch.lgN, tw_cols, tw_hi, tw_lo, 0, 1));
+        ADSP_TRY((launch_rows<T, 2>(ctx, st, ch.N2, Q, (const cpx<T> *)nullptr, Q, (T)1, ch.N1, tw_rows, nq)));
+        // block 2*pair -> problem (re), 2*pair + 1 -> next problem (im): p0 is even, so pair0 = p0 / 2 lines the rows up
+        ADSP_TRY(launch_cols<T>(ctx, st, ch.N1, true, g, (const T *)nullptr, out, Q, ch.N2, ch.lgN, tw_cols, tw_hi, tw_lo, p0 / 2, nq));
     }
     ADSP_CUDA(cudaGetLastError());
     return ADSP_OK;

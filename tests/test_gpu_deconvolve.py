@@ -103,3 +103,26 @@ def test_sweep_deconvolve_with_inverse_is_a_full_convolution(conv, oracle):
     idx, _ = conv.FindPeak(ir)
     assert idx == n - 1                                          # main peak at len(inv) - 1 (sweep.go:231-232)
     assert abs(ir[n - 1 + 300] / ir[n - 1] - 0.5) < 0.05         # the echo, 300 samples later at half the height
+
+
+@pytest.mark.parametrize("n,m,batch,shared_kernel", [(20000, 500, 5, True), (20000, 500, 4, False), (300, 20, 7, True), (9000, 64, 1, True),
+                                                     (70000, 1000, 33, True)])
+def test_batch_device_deconvolution(conv, oracle, n, m, batch, shared_kernel):
+    """adsp_deconvolve_batch_device: `batch` problems per call; in the four-step range two problems share one inverse
+    transform and groups of problems share launches.  Every row must equal the single-problem result."""
+    import ctypes as C
+    import torch
+    from algo_dsp_b200 import _lib as L
+    ctx = conv.default_context()
+    x = np.stack([G.white(n, seed=10 + p) for p in range(batch)])
+    ks = np.stack([G.decaying_ir(m, seed=3 + (0 if shared_kernel else p)) + (np.arange(m) == 0) * 2.0 for p in range(batch)])
+    xd, kd = torch.tensor(x, device="cuda"), torch.tensor(ks, device="cuda")
+    ol = n - m + 1
+    od = torch.empty((batch, ol), device="cuda", dtype=torch.float64)
+    st = L.load().adsp_deconvolve_batch_device(ctx.handle, xd.data_ptr(), n, n, kd.data_ptr(), m, 0 if shared_kernel else m, batch,
+                                               C.c_double(1e-4), od.data_ptr(), ol)
+    assert st == 0
+    ctx.sync()
+    got = od.cpu().numpy()
+    for p in range(batch):
+        assert G.rel_l2(got[p], oracle.deconvolve(x[p], ks[p], oracle.DECONV_REGULARIZED, 1e-4)) <= TOL
