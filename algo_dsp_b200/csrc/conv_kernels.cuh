@@ -575,12 +575,17 @@ corr_cols_fwd(const T *__restrict__ a, long long n, long long a_stride, const T 
     for (int r = 0; r < 16; r++) __stcg(&dst[(size_t)(j + r * TPF) * N2], e[r]);
 }
 
-// Spectral product in four-step order, in place: ZA <- P_A + i*P_B (ZB may be null).  Element
-// (k1, k2) holds Z[k1 + N1*k2]; its mirror N-k sits at ((N1-k1)%N1, .).  One thread handles k and N-k.
+// Spectral product in four-step order.  grid.y = q: pairs 2q (spectrum Z[2q]) and 2q+1 (Z[2q+1], absent when npairs is
+// odd) share one inverse transform: Q[q] <- P_A + i*P_B.  Q may alias Z when the group holds at most two pairs (a thread
+// reads all four of its inputs before it writes).  Element (k1, k2) holds Z[k1 + N1*k2]; its mirror N-k sits at
+// ((N1-k1)%N1, .).  One thread handles k and N-k.
 template <typename T>
-__global__ void corr_pointwise(cpx<T> *ZA, const cpx<T> *ZB, int N1, int N2, T scale) {
+__global__ void corr_pointwise(const cpx<T> *Z, cpx<T> *Q, int npairs, int N1, int N2, T scale) {
     using C = cpx<T>;
     const long long N = (long long)N1 * N2;
+    const cpx<T> *ZA = Z + (size_t)(2 * blockIdx.y) * N;
+    const cpx<T> *ZB = (2 * (int)blockIdx.y + 1 < npairs) ? ZA + N : nullptr;
+    cpx<T> *Qq = Q + (size_t)blockIdx.y * N;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= N) return;
     const long long k1 = idx / N2, k2 = idx - k1 * N2;
@@ -605,8 +610,8 @@ __global__ void corr_pointwise(cpx<T> *ZA, const cpx<T> *ZB, int N1, int N2, T s
     C qk, qm;
     qk.x = pa.x - pb.y; qk.y = pa.y + pb.x;
     qm.x = pa.x + pb.y; qm.y = -pa.y + pb.x;
-    __stcg(&ZA[idx], qk);
-    if (midx != idx) __stcg(&ZA[midx], qm);
+    __stcg(&Qq[idx], qk);
+    if (midx != idx) __stcg(&Qq[midx], qm);
 }
 
 // Regularised / naive spectral division for deconvolution (deconvolve.go:143-151, 216-220, 304-308), in four-step order,
@@ -630,7 +635,7 @@ template <typename T> __device__ __forceinline__ cpx<T> deconv_bin(cpx<T> zk, cp
 // grid.y = q: problems 2q (spectrum Z[2q]) and 2q+1 (Z[2q+1], absent when nprob is odd) share one inverse transform:
 // Q[q] = R_A + i*R_B; both R are Hermitian (real results), so Q[N-k] = conj(R_A[k]) + i*conj(R_B[k]).
 template <typename T>
-__global__ void deconv_pointwise(const cpx<T> *__restrict__ Z, cpx<T> *__restrict__ Q, int nprob, int N1, int N2, T scale, T reg,
+__global__ void deconv_pointwise(const cpx<T> *Z, cpx<T> *Q, int nprob, int N1, int N2, T scale, T reg,
                                  long long *bad_bin) {
     using C = cpx<T>;
     const long long N = (long long)N1 * N2;

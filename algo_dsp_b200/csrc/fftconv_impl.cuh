@@ -886,30 +886,38 @@ adsp_status fft_correlate_pairs_device(adsp_ctx *ctx, const T *a, long long n, l
     ADSP_TRY(get_tw_table<T>(ctx, ch.N2, &tw_rows));
     ADSP_TRY(get_tw_table<T>(ctx, ch.N1, &tw_cols));
     ADSP_TRY(get_tw4_tables<T>(ctx, ch.N, &tw_hi, &tw_lo));
-    const size_t per_pair = (size_t)N * sizeof(cpx<T>);
-    ADSP_TRY(ctx->scratch.reserve(2 * per_pair));
-    cpx<T> *ZA = (cpx<T> *)ctx->scratch.p, *ZB = ZA + N;
+    // groups of pairs whose spectra (one slot each) and shared inverse transforms (one slot per two pairs) fit the L2
+    // scratch budget; a group of two pairs (the 2^21-point case of BASELINE config 4) keeps Q in place in slot 0
+    const size_t slot = (size_t)N * sizeof(cpx<T>);
+    long long G = (long long)(ctx->scratch_budget / slot) * 2 / 3;
+    G = std::max<long long>(2, G - (G & 1));
+    G = std::min<long long>(G, std::min<long long>(pairs + (pairs & 1), 4096));
+    const bool in_place = (G == 2);
+    ADSP_TRY(ctx->scratch.reserve((size_t)(in_place ? 2 : G + G / 2) * slot));
+    cpx<T> *Z = (cpx<T> *)ctx->scratch.p;
+    cpx<T> *Q = in_place ? Z : Z + (size_t)G * N;
     ConvGeom g{};                          // output side: block 2q -> pair 2q (re), block 2q+1 -> pair 2q+1 (im)
     g.n = N; g.out_len = out_len; g.in_stride = 0; g.out_stride = out_stride; g.S = N; g.D = 0;
     g.total_blocks = pairs; g.in_shift = 0; g.out_shift = 0; g.nblk = 1; g.accumulate = 0;
     cudaStream_t st = ctx->main;
     const T scale = (T)(1.0L / (long double)N);
-    for (long long p0 = 0; p0 < pairs; p0 += 2) {
-        const int np = (pairs - p0 >= 2) ? 2 : 1;
-#define ADSP_CORR_COLS(n1) case n1: ADSP_TRY((launch_corr_cols_t<T, n1>(ctx, st, a, n, a_stride, b, m, b_stride, ZA, ch.N2, ch.lgN, tw_cols, tw_hi, tw_lo, p0, np))); break;
+    for (long long p0 = 0; p0 < pairs; p0 += G) {
+        const int np = (int)std::min<long long>(G, pairs - p0), nq = (np + 1) / 2;
+#define ADSP_CORR_COLS(n1) case n1: ADSP_TRY((launch_corr_cols_t<T, n1>(ctx, st, a, n, a_stride, b, m, b_stride, Z, ch.N2, ch.lgN, tw_cols, tw_hi, tw_lo, p0, np))); break;
         switch (ch.N1) {
             ADSP_CORR_COLS(16) ADSP_CORR_COLS(32) ADSP_CORR_COLS(64) ADSP_CORR_COLS(128) ADSP_CORR_COLS(256) ADSP_CORR_COLS(512) ADSP_CORR_COLS(1024)
         default: set_error("correlate: unsupported transform shape"); return ADSP_ERR_INVALID_ARG;
         }
 #undef ADSP_CORR_COLS
-        ADSP_TRY((launch_rows<T, 1>(ctx, st, ch.N2, ZA, (const cpx<T> *)nullptr, ZA, (T)1, ch.N1, tw_rows, np)));   // forward rows, in place
+        ADSP_TRY((launch_rows<T, 1>(ctx, st, ch.N2, Z, (const cpx<T> *)nullptr, Z, (T)1, ch.N1, tw_rows, np)));   // forward rows, in place
         {
             LaunchTimer lt(ctx, st, KK_OTHER);
-            corr_pointwise<T><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(ZA, np == 2 ? ZB : (const cpx<T> *)nullptr, ch.N1, ch.N2, scale);
+            dim3 grid((unsigned)((N + 255) / 256), (unsigned)nq);
+            corr_pointwise<T><<<grid, 256, 0, st>>>(Z, Q, np, ch.N1, ch.N2, scale);
             count_launch(ctx);
         }
-        ADSP_TRY((launch_rows<T, 2>(ctx, st, ch.N2, ZA, (const cpx<T> *)nullptr, ZA, (T)1, ch.N1, tw_rows, 1)));     // inverse rows of Q
-        ADSP_TRY(launch_cols<T>(ctx, st, ch.N1, true, g, (const T *)nullptr, out, ZA, ch.N2, ch.lgN, tw_cols, tw_hi, tw_lo, p0 / 2, 1));
+        ADSP_TRY((launch_rows<T, 2>(ctx, st, ch.N2, Q, (const cpx<T> *)nullptr, Q, (T)1, ch.N1, tw_rows, nq)));     // inverse rows of Q
+        ADSP_TRY(launch_cols<T>(ctx, st, ch.N1, true, g, (const T *)nullptr, out, Q, ch.N2, ch.lgN, tw_cols, tw_hi, tw_lo, p0 / 2, nq));
     }
     ADSP_CUDA(cudaGetLastError());
     *done = true;
@@ -965,9 +973,10 @@ adsp_status fft_deconvolve_device(adsp_ctx *ctx, const T *sig, long long n, long
     G = std::max<long long>(2, G - (G & 1));
     G = std::min<long long>(G, std::min<long long>(batch + (batch & 1), 4096));
     const long long GQ = (G + 1) / 2;
-    ADSP_TRY(ctx->scratch.reserve((size_t)(G + GQ) * slot));
+    const bool in_place = (G == 2);        // one inverse per group: Q can live in slot 0 (a thread reads its inputs before it writes)
+    ADSP_TRY(ctx->scratch.reserve((size_t)(in_place ? 2 : G + GQ) * slot));
     cpx<T> *Z = (cpx<T> *)ctx->scratch.p;
-    cpx<T> *Q = Z + (size_t)G * N;
+    cpx<T> *Q = in_place ? Z : Z + (size_t)G * N;
     ConvGeom g{};
     g.n = N; g.out_len = out_len; g.in_stride = 0; g.out_stride = out_stride; g.S = N; g.D = 0;
     g.total_blocks = batch; g.in_shift = 0; g.out_shift = 0; g.nblk = 1; g.accumulate = 0;

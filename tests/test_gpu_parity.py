@@ -178,6 +178,19 @@ def test_correlate_batch_peak_lag_config4_shape(conv, oracle):
     assert np.array_equal(pi, pi2)
 
 
+@pytest.mark.parametrize("n,m,pairs", [(5000, 5000, 9), (3000, 700, 40), (40000, 40000, 5), (1 << 18, 1 << 18, 3)])
+def test_correlate_batch_groups_of_pairs(conv, oracle, n, m, pairs):
+    """Many pairs per call: groups of pairs share launches and two pairs share an inverse transform; odd counts leave
+    the last transform half empty.  Every pair must match the single-pair result."""
+    a = np.stack([G.white(n, seed=p) for p in range(pairs)])
+    b = np.stack([G.pink(m, seed=50 + p) for p in range(pairs)])
+    out, pi, pv = conv.CorrelateBatch(a, b)
+    for p in range(pairs):
+        ref = oracle.correlate(a[p], b[p])
+        assert rel(out[p], ref) <= TOL64
+        assert int(pi[p]) == oracle.find_peak(ref)[0]
+
+
 # ---------------------------------------------------------------- partitioned / streaming semantics
 @pytest.mark.parametrize("K,n,mn,mx,chunk", [(64, 512, 4, 10, 0), (1024, 4096, 6, 13, 0), (8192, 16384, 6, 13, 1000),
                                               (3000, 9000, 7, 13, 128), (96000, 200000, 7, 13, 48000)])
