@@ -33,6 +33,9 @@ static __constant__ int g_scratch_alias = 0;
 
 // 1: form the 15 twiddle powers of EVERY twiddled pass from the first power (14 complex products) instead of
 // reading all 15 from the shared-memory table in the short passes: trades 15 LDS.128 for 56 FP64 instructions
+#ifndef ADSP_TW_CHAIN
+#define ADSP_TW_CHAIN 0
+#endif
 #ifndef ADSP_TW_TREE_ALL
 #define ADSP_TW_TREE_ALL 0
 #endif
@@ -460,6 +463,13 @@ __device__ __forceinline__ void cta_fft(cpx<T> (&e)[16], cpx<T> *buf, const Addr
             const C *twp = stw + off + k;
 #pragma unroll
             for (int r = 1; r < 16; r++) e[r] = cmul_tw<INV>(e[r], twp[(r - 1) * ns]);
+        } else if (ADSP_TW_CHAIN) {
+            // powers by a running product: two twiddle values live instead of eight (register pressure), 15 dependent products
+            const C w1 = stw[off + k];
+            C w = w1;
+            e[1] = cmul_tw<INV>(e[1], w);
+#pragma unroll
+            for (int r = 2; r < 16; r++) { w = cmul(w, w1); e[r] = cmul_tw<INV>(e[r], w); }
         } else {
             const C w1 = stw[off + k];
             const C w2 = cmul(w1, w1), w4 = cmul(w2, w2), w8 = cmul(w4, w4);
