@@ -94,6 +94,9 @@ template <typename T> __device__ __forceinline__ TileOut<T> tile_out(const Block
 #ifndef ADSP_EXPERIMENTAL
 #define ADSP_EXPERIMENTAL 0
 #endif
+#ifndef ADSP_H_DIRECT
+#define ADSP_H_DIRECT 0
+#endif
 #ifndef ADSP_ROWS_SMALL_CTA
 #define ADSP_ROWS_SMALL_CTA (ADSP_EXPERIMENTAL ? 0 : 1)
 #endif
@@ -322,6 +325,18 @@ __device__ __forceinline__ void rows_tile(cpx<T> *__restrict__ scratch_pair, con
 #pragma unroll
         for (int q = 0; q < 16; q++) { e[q].x = (T)0; e[q].y = (T)0; }
     }
+#if ADSP_H_DIRECT
+    // spectrum straight from L2 into registers after the last forward pass (no shared-memory staging: two LSU passes less,
+    // one exposed L2 round trip more)
+    cta_fft<T, L, false, false, true>(e, buf, addr, stw, j, gate);
+    if (active && !ADSP_SKIP(2)) {
+        C hv[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) hv[q] = ld_scratch(&H[hoff + q * TPF], keep);
+#pragma unroll
+        for (int q = 0; q < 16; q++) e[q] = cmul(e[q], hv[q]);
+    }
+#else
     auto prefetch_h = [&](C *b) {
         if (active && !ADSP_SKIP(2)) {
 #pragma unroll
@@ -334,6 +349,7 @@ __device__ __forceinline__ void rows_tile(cpx<T> *__restrict__ scratch_pair, con
 #pragma unroll
         for (int q = 0; q < 16; q++) e[q] = cmul(e[q], buf[addr.at(j + q * TPF, Sh::P - 1)]);
     }
+#endif
     cta_fft<T, L, true, true, false>(e, buf, addr, stw, j, gate);                // ... through the inverse's first pass
     if (active && !ADSP_SKIP(1)) {
 #pragma unroll
