@@ -39,7 +39,7 @@ template <int M> struct ColShapeMR {
     static constexpr int THREADS = TPC * TC;
     static constexpr int SMEM_ELEMS = N1 * TC;
     static constexpr int TW_ENTRIES = 16 * M;    // W_N1^(j*km) at [km*16 + j]
-    static constexpr int MIN_CTAS = M > 16 ? (ADSP_MR_TC == 8 ? ADSP_MR_WIDE_CTAS : 2) : ADSP_MR_MIN_CTAS;
+    static constexpr int MIN_CTAS = M > 16 ? (ADSP_MR_TC <= 8 ? ADSP_MR_WIDE_CTAS : 2) : ADSP_MR_MIN_CTAS;
 };
 
 // W_N^m for any N that is a multiple of 1024: hi[m >> 10] * lo[m & 1023]
