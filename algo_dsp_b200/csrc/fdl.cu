@@ -238,7 +238,7 @@ struct FdlEngine {
     std::vector<void *> d_H, d_fdl;           // per stage: spectra [count][2B], delay line [pairs][ring][2B]
     std::vector<const void *> d_tw;           // per stage: twiddle table of the 2B-point transform
     long long HX = 0;                         // input history kept in front of each chunk (2*B_max)
-    DevBuf xbuf, xbuf_alt, acc, d_io_in, d_io_out, yscratch;   // xbuf / xbuf_alt: input rows [history | chunk], ping-pong
+    DevBuf xbuf, xbuf_alt, acc, d_io_out, yscratch;   // xbuf / xbuf_alt: input rows [history | chunk], ping-pong
     long long acc_len = 0;
     long long pos = 0;                        // samples consumed so far
     double wet = 1.0, dry = 1.0;
@@ -323,7 +323,8 @@ template <typename T> adsp_status fdl_build(FdlEngine *e, const T *d_kernel) {
         // first half, as overlap-save with outputs taken from [B, 2B) needs).
         const long long row_len = 2LL * g.count * g.B + 2 * g.B;
         const int ring_tmp = 2 * g.count + 2;
-        DevBuf row, spec;
+        struct Scoped { DevBuf b; ~Scoped() { b.release(); } } row_s, spec_s;   // freed on every exit path
+        DevBuf &row = row_s.b, &spec = spec_s.b;
         ADSP_TRY(row.reserve((size_t)row_len * sizeof(T)));
         ADSP_TRY(spec.reserve((size_t)ring_tmp * L2 * sizeof(cpx<T>)));
         ADSP_CUDA(cudaMemsetAsync(row.p, 0, (size_t)row_len * sizeof(T), ctx->main));
@@ -341,7 +342,6 @@ template <typename T> adsp_status fdl_build(FdlEngine *e, const T *d_kernel) {
         const long long tot = (long long)g.count * L2;
         if (st == ADSP_OK) fdl_scale<T><<<(unsigned)((tot + 255) / 256), 256, 0, ctx->main>>>((cpx<T> *)e->d_H[s], tot, (T)(1.0L / (long double)L2));
         cudaStreamSynchronize(ctx->main);
-        row.release(); spec.release();
         ADSP_TRY(st);
     }
     return ADSP_OK;
@@ -485,7 +485,7 @@ void fdl_destroy(FdlEngine *e) {
     if (!e) return;
     for (void *p : e->d_H) if (p) cudaFree(p);
     for (void *p : e->d_fdl) if (p) cudaFree(p);
-    e->xbuf.release(); e->xbuf_alt.release(); e->acc.release(); e->d_io_in.release(); e->d_io_out.release(); e->yscratch.release();
+    e->xbuf.release(); e->xbuf_alt.release(); e->acc.release(); e->d_io_out.release(); e->yscratch.release();
     delete e;
 }
 
