@@ -32,6 +32,10 @@ PROTOTYPES = {
     "adsp_ctx_stream": (c_vp, [c_vp]),
     "adsp_ctx_kernel_timing": (None, [c_vp, C.c_int]),
     "adsp_ctx_kernel_time": (C.c_int, [c_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]),
+    "adsp_ctx_host_profile": (None, [c_vp, C.c_int]),
+    "adsp_ctx_host_profile_get": (C.c_int, [c_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "adsp_host_ptr_is_pinned": (C.c_int, [c_vp]),
+    "adsp_ctx_stage_threads": (C.c_int, [c_vp]),
     "adsp_host_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(c_vp)]),
     "adsp_host_free_pinned": (None, [c_vp]),
     "adsp_device_alloc": (C.c_int, [c_vp, C.c_size_t, C.POINTER(c_vp)]),

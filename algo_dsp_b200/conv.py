@@ -115,6 +115,21 @@ class Context:
             _check(L.load().adsp_ctx_kernel_time(self._h, 0, None, None, 1))
         return out
 
+    def host_profile(self, enable: bool):
+        """Record a phase breakdown of the next small host-buffer call (adsp_ctx_host_profile)."""
+        L.load().adsp_ctx_host_profile(self._h, 1 if enable else 0)
+
+    def host_profile_get(self):
+        """{alloc_ms, upload_ms, kernels_ms, download_ms, total_ms, staged_in_bytes, staged_out_bytes} of the last profiled call."""
+        ms = (C.c_double * 6)()
+        bi, bo = C.c_uint64(), C.c_uint64()
+        _check(L.load().adsp_ctx_host_profile_get(self._h, ms, C.byref(bi), C.byref(bo)))
+        return {"alloc_ms": ms[0], "upload_ms": ms[1], "kernels_ms": ms[2], "download_ms": ms[3], "total_ms": ms[5],
+                "staged_in_bytes": int(bi.value), "staged_out_bytes": int(bo.value)}
+
+    def stage_threads(self) -> int:
+        return int(L.load().adsp_ctx_stage_threads(self._h))
+
     def close(self):
         if self._h:
             L.load().adsp_ctx_destroy(self._h)

@@ -2,6 +2,7 @@
 // functions.  Host-side bookkeeping only; all arithmetic runs in the sm_100a kernels of
 // conv_kernels.cuh / aux_kernels.cuh.  There is no CPU fallback anywhere in this file.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <thread>
 
@@ -22,8 +23,13 @@ adsp_status cuda_fail(cudaError_t e, const char *what, const char *file, int lin
     return (e == cudaErrorMemoryAllocation) ? ADSP_ERR_OOM : ADSP_ERR_CUDA;
 }
 
+// Bumped whenever a DevBuf is freed or re-allocated: captured CUDA graphs bake device pointers of the shared scratch
+// buffers in, so a graph captured under an older generation must not be replayed (adsp_plan_process_device).
+std::atomic<uint64_t> g_alloc_generation{1};
+
 adsp_status DevBuf::reserve(size_t bytes) {
     if (bytes <= cap) return ADSP_OK;
+    g_alloc_generation.fetch_add(1, std::memory_order_relaxed);
     if (p) { cudaFree(p); p = nullptr; cap = 0; }
     const size_t want = bytes + bytes / 8;
     cudaError_t e = cudaMalloc(&p, want);
@@ -31,7 +37,7 @@ adsp_status DevBuf::reserve(size_t bytes) {
     cap = want;
     return ADSP_OK;
 }
-void DevBuf::release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+void DevBuf::release() { if (p) { g_alloc_generation.fetch_add(1, std::memory_order_relaxed); cudaFree(p); } p = nullptr; cap = 0; }
 
 adsp_status PinnedBuf::reserve(size_t bytes) {
     if (bytes <= cap) return ADSP_OK;
@@ -264,29 +270,15 @@ static adsp_status peak_device(adsp_ctx *ctx, const T *d_x, long long len, long 
     ADSP_TRY(ctx->d_small.reserve(need + 64));
     long long *pi = (long long *)ctx->d_small.p;
     T *pv = (T *)((char *)ctx->d_small.p + (size_t)batch * nparts * sizeof(long long));
-    dim3 g1((unsigned)nparts, (unsigned)batch);
-    peak_partial_kernel<T><<<g1, 256, 0, ctx->main>>>(d_x, len, stride, pv, pi);
+    for (long long b0 = 0; b0 < batch; b0 += 65535) {   // grid.y is limited to 65535 rows per launch
+        const long long nb = std::min<long long>(65535, batch - b0);
+        dim3 g1((unsigned)nparts, (unsigned)nb);
+        peak_partial_kernel<T><<<g1, 256, 0, ctx->main>>>(d_x + b0 * stride, len, stride, pv + b0 * nparts, pi + b0 * nparts);
+        count_launch(ctx);
+    }
     peak_final_kernel<T><<<(unsigned)batch, 32, 0, ctx->main>>>(d_x, stride, pv, pi, nparts, batch, d_v, d_i);
-    count_launch(ctx, 2);
+    count_launch(ctx);
     ADSP_CUDA(cudaGetLastError());
-    return ADSP_OK;
-}
-
-// ---------------------------------------------------------------- host <-> device transfer helpers
-static bool is_pinned_host(const void *p) {
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return a.type == cudaMemoryTypeHost;
-}
-
-// copy rows of `width` elements between host (stride hs) and device (stride ds)
-static adsp_status copy2d(adsp_ctx *ctx, void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes,
-                          size_t rows, cudaMemcpyKind kind) {
-    if (rows == 0 || width_bytes == 0) return ADSP_OK;
-    if (rows == 1 || (dpitch == width_bytes && spitch == width_bytes))
-        ADSP_CUDA(cudaMemcpyAsync(dst, src, width_bytes * rows, kind, ctx->main));
-    else
-        ADSP_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, rows, kind, ctx->main));
     return ADSP_OK;
 }
 
@@ -324,6 +316,7 @@ struct adsp_plan {
     struct GraphEntry {
         const void *in; void *out; long long n, channels, in_stride, out_stride;
         cudaGraphExec_t exec; uint64_t launches; int seen;
+        uint64_t alloc_gen;   // g_alloc_generation at capture: any later (re)allocation of a shared buffer invalidates the graph
     };
     std::vector<GraphEntry> graphs;
 };
@@ -338,7 +331,7 @@ template <> std::map<long long, FftConv<float>> &plan_extra<float>(adsp_plan *p)
 template <typename T> static adsp_status plan_build(adsp_plan *p, const T *host_kernel) {
     adsp_ctx *ctx = p->ctx;
     ADSP_TRY(p->d_kernel.reserve((size_t)p->K * sizeof(T)));
-    ADSP_CUDA(cudaMemcpyAsync(p->d_kernel.p, host_kernel, (size_t)p->K * sizeof(T), cudaMemcpyHostToDevice, ctx->main));
+    ADSP_TRY(upload(ctx, p->d_kernel.p, host_kernel, (size_t)p->K * sizeof(T)));
     p->ch = choose_fft(p->K);
     auto &v = plan_fc<T>(p);
     v.resize((size_t)p->ch.parts);
@@ -381,9 +374,12 @@ static adsp_status plan_run_device(adsp_plan *p, const T *d_in, long long n, lon
     return ADSP_OK;
 }
 
-// host-pointer batch.  Small calls: one H2D, compute, one D2H.  Large multi-channel calls: channel
-// chunks flow through a three-stage pipeline (H2D on copy_in | kernels on main+workers | D2H on
-// copy_out) with two device slots per direction, so both PCIe directions and the SMs overlap.
+// host-pointer batch.  Small calls: upload, compute, download (pageable memory staged through the pinned slots by the
+// copy-thread pool, staging.cu).  Large multi-channel calls: channel chunks flow through a five-stage pipeline
+//   stage-in (pool: caller memory -> pinned slot) | H2D (copy_in) | kernels (main + workers) | D2H (copy_out) |
+//   stage-out (pool: pinned slot -> caller memory)
+// with kPipeSlots slots per direction, so both PCIe directions, the SMs and the host copy threads all overlap.  The two
+// staging stages disappear for pinned/registered caller memory (adsp_host_alloc_pinned), which is DMA'd in place.
 template <typename T>
 static adsp_status plan_run_host(adsp_plan *p, const T *in, long long n, long long channels, long long in_stride,
                                  T *out, long long out_stride) {
@@ -392,44 +388,101 @@ static adsp_status plan_run_host(adsp_plan *p, const T *in, long long n, long lo
     // device layout: dense rows padded to 32 elements so every channel starts 256-byte aligned
     const long long dis = ((n + 31) / 32) * 32, dos = ((out_len + 31) / 32) * 32;
     const size_t row_bytes = (size_t)(dis + dos) * sizeof(T);
-    const long long chunk_target = env_ll("ADSP_PIPE_CHUNK_MB", 96) << 20;
+    const bool stage_in = !host_ptr_is_pinned(in), stage_out = !host_ptr_is_pinned(out);
+    const bool staged = stage_in || stage_out;
+    // chunk size: 96 MB measured best for DMA straight from pinned caller memory (tools/e2e_sweep.py); staged chunks are
+    // smaller so that the five stages fill sooner and the pinned slots stay modest (kPipeSlots x 2 x chunk)
+    const long long chunk_target = (staged ? env_ll("ADSP_STAGE_PIPE_CHUNK_MB", 32) : env_ll("ADSP_PIPE_CHUNK_MB", 96)) << 20;
     long long cc = (long long)(chunk_target / (long long)row_bytes);
-    if (cc < 2) cc = 2;
+    if (cc < 1) cc = 1;
     if (channels < 4 || (size_t)channels * row_bytes < (size_t)(32u << 20) || cc >= channels) {
+        using clk = std::chrono::steady_clock;
+        const bool prof = ctx->host_profile;
+        auto t0 = clk::now();
+        auto lap = [&](int slot) {   // profile mode serialises the phases (one extra stream sync each)
+            if (!prof) return;
+            cudaStreamSynchronize(ctx->main);
+            const auto t1 = clk::now();
+            ctx->host_prof_ms[slot] = std::chrono::duration<double, std::milli>(t1 - t0).count();
+            t0 = t1;
+        };
+        const auto tstart = t0;
         ADSP_TRY(ctx->d_in.reserve((size_t)dis * channels * sizeof(T)));
         ADSP_TRY(ctx->d_out.reserve((size_t)dos * channels * sizeof(T)));
-        ADSP_TRY(copy2d(ctx, ctx->d_in.p, (size_t)dis * sizeof(T), in, (size_t)in_stride * sizeof(T), (size_t)n * sizeof(T),
-                        (size_t)channels, cudaMemcpyHostToDevice));
+        lap(0);   // allocation (zero after the first call of a shape)
+        ADSP_TRY(upload2d(ctx, ctx->d_in.p, (size_t)dis * sizeof(T), in, (size_t)in_stride * sizeof(T), (size_t)n * sizeof(T), (size_t)channels));
+        lap(1);   // stage-in + H2D
         ADSP_TRY(plan_run_device<T>(p, (const T *)ctx->d_in.p, n, channels, dis, (T *)ctx->d_out.p, dos));
-        ADSP_TRY(copy2d(ctx, out, (size_t)out_stride * sizeof(T), ctx->d_out.p, (size_t)dos * sizeof(T),
-                        (size_t)out_len * sizeof(T), (size_t)channels, cudaMemcpyDeviceToHost));
+        lap(2);   // kernels
+        ADSP_TRY(download2d(ctx, out, (size_t)out_stride * sizeof(T), ctx->d_out.p, (size_t)dos * sizeof(T), (size_t)out_len * sizeof(T),
+                            (size_t)channels));
         ADSP_CUDA(cudaStreamSynchronize(ctx->main));
+        lap(3);   // D2H + stage-out
+        if (prof) ctx->host_prof_ms[5] = std::chrono::duration<double, std::milli>(clk::now() - tstart).count();
         return ADSP_OK;
     }
-    for (int s = 0; s < 2; s++) {
+    constexpr int NS = kPipeSlots;
+    StagePool *pool = staged ? stage_pool(ctx) : nullptr;
+    for (int s = 0; s < NS; s++) {
         ADSP_TRY(ctx->pipe_in[s].reserve((size_t)dis * cc * sizeof(T)));
         ADSP_TRY(ctx->pipe_out[s].reserve((size_t)dos * cc * sizeof(T)));
+        if (stage_in) ADSP_TRY(ctx->h_in[s].reserve((size_t)n * cc * sizeof(T)));
+        if (stage_out) ADSP_TRY(ctx->h_out[s].reserve((size_t)out_len * cc * sizeof(T)));
     }
-    long long idx = 0;
-    for (long long c0 = 0; c0 < channels; c0 += cc, idx++) {
-        const long long nc = std::min(cc, channels - c0);
-        const int s = (int)(idx & 1);
-        // stage 1: H2D (slot free once the compute that last used it is done)
-        if (idx >= 2) ADSP_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_comp[s], 0));
-        ADSP_CUDA(cudaMemcpy2DAsync(ctx->pipe_in[s].p, (size_t)dis * sizeof(T), in + c0 * in_stride, (size_t)in_stride * sizeof(T),
-                                    (size_t)n * sizeof(T), (size_t)nc, cudaMemcpyHostToDevice, ctx->copy_in));
-        ADSP_CUDA(cudaEventRecord(ctx->ev_in[s], ctx->copy_in));
-        // stage 2: kernels (output slot free once its previous D2H is done)
-        ADSP_CUDA(cudaStreamWaitEvent(ctx->main, ctx->ev_in[s], 0));
-        if (idx >= 2) ADSP_CUDA(cudaStreamWaitEvent(ctx->main, ctx->ev_out[s], 0));
-        ADSP_TRY(plan_run_device<T>(p, (const T *)ctx->pipe_in[s].p, n, nc, dis, (T *)ctx->pipe_out[s].p, dos));
-        ADSP_CUDA(cudaEventRecord(ctx->ev_comp[s], ctx->main));
-        // stage 3: D2H
-        ADSP_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_comp[s], 0));
-        ADSP_CUDA(cudaMemcpy2DAsync(out + c0 * out_stride, (size_t)out_stride * sizeof(T), ctx->pipe_out[s].p, (size_t)dos * sizeof(T),
-                                    (size_t)out_len * sizeof(T), (size_t)nc, cudaMemcpyDeviceToHost, ctx->copy_out));
-        ADSP_CUDA(cudaEventRecord(ctx->ev_out[s], ctx->copy_out));
+    if (stage_in) ctx->staged_bytes_in += (uint64_t)channels * n * sizeof(T);
+    if (stage_out) ctx->staged_bytes_out += (uint64_t)channels * out_len * sizeof(T);
+    const long long nchunks = (channels + cc - 1) / cc;
+    auto chunk_c0 = [&](long long i) { return i * cc; };
+    auto chunk_nc = [&](long long i) { return std::min(cc, channels - i * cc); };
+    StagePool::Ticket tk_in[NS], tk_out[NS];
+    // iteration i: stage-in of chunk i | enqueue H2D + kernels + D2H of chunk i-1 | stage-out of chunk i-2
+    for (long long i = 0; i < nchunks + 2; i++) {
+        if (i < nchunks && stage_in) {
+            const int s = (int)(i % NS);
+            ADSP_CUDA(cudaEventSynchronize(ctx->ev_in[s]));              // the H2D that last read this pinned slot is done
+            tk_in[s] = pool->copy2d_async(ctx->h_in[s].p, (size_t)n * sizeof(T), in + chunk_c0(i) * in_stride, (size_t)in_stride * sizeof(T),
+                                          (size_t)n * sizeof(T), (size_t)chunk_nc(i));
+        }
+        if (i >= 1 && i - 1 < nchunks) {
+            const long long j = i - 1, c0 = chunk_c0(j), nc = chunk_nc(j);
+            const int s = (int)(j % NS);
+            // H2D (device slot free once the kernels that last read it are done)
+            if (j >= NS) ADSP_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_comp[s], 0));
+            if (stage_in) {
+                StagePool::wait(tk_in[s]);
+                ADSP_CUDA(cudaMemcpy2DAsync(ctx->pipe_in[s].p, (size_t)dis * sizeof(T), ctx->h_in[s].p, (size_t)n * sizeof(T), (size_t)n * sizeof(T),
+                                            (size_t)nc, cudaMemcpyHostToDevice, ctx->copy_in));
+            } else {
+                ADSP_CUDA(cudaMemcpy2DAsync(ctx->pipe_in[s].p, (size_t)dis * sizeof(T), in + c0 * in_stride, (size_t)in_stride * sizeof(T),
+                                            (size_t)n * sizeof(T), (size_t)nc, cudaMemcpyHostToDevice, ctx->copy_in));
+            }
+            ADSP_CUDA(cudaEventRecord(ctx->ev_in[s], ctx->copy_in));
+            // kernels (output slot free once its previous D2H is done)
+            ADSP_CUDA(cudaStreamWaitEvent(ctx->main, ctx->ev_in[s], 0));
+            if (j >= NS) ADSP_CUDA(cudaStreamWaitEvent(ctx->main, ctx->ev_out[s], 0));
+            ADSP_TRY(plan_run_device<T>(p, (const T *)ctx->pipe_in[s].p, n, nc, dis, (T *)ctx->pipe_out[s].p, dos));
+            ADSP_CUDA(cudaEventRecord(ctx->ev_comp[s], ctx->main));
+            // D2H (pinned slot free once the pool has copied its previous contents out)
+            ADSP_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_comp[s], 0));
+            if (stage_out) {
+                StagePool::wait(tk_out[s]);
+                ADSP_CUDA(cudaMemcpy2DAsync(ctx->h_out[s].p, (size_t)out_len * sizeof(T), ctx->pipe_out[s].p, (size_t)dos * sizeof(T),
+                                            (size_t)out_len * sizeof(T), (size_t)nc, cudaMemcpyDeviceToHost, ctx->copy_out));
+            } else {
+                ADSP_CUDA(cudaMemcpy2DAsync(out + c0 * out_stride, (size_t)out_stride * sizeof(T), ctx->pipe_out[s].p, (size_t)dos * sizeof(T),
+                                            (size_t)out_len * sizeof(T), (size_t)nc, cudaMemcpyDeviceToHost, ctx->copy_out));
+            }
+            ADSP_CUDA(cudaEventRecord(ctx->ev_out[s], ctx->copy_out));
+        }
+        if (i >= 2 && stage_out) {
+            const long long j = i - 2;
+            const int s = (int)(j % NS);
+            ADSP_CUDA(cudaEventSynchronize(ctx->ev_out[s]));
+            tk_out[s] = pool->copy2d_async(out + chunk_c0(j) * out_stride, (size_t)out_stride * sizeof(T), ctx->h_out[s].p, (size_t)out_len * sizeof(T),
+                                           (size_t)out_len * sizeof(T), (size_t)chunk_nc(j));
+        }
     }
+    for (int s = 0; s < NS; s++) StagePool::wait(tk_out[s]);
     ADSP_CUDA(cudaStreamSynchronize(ctx->copy_out));
     ADSP_CUDA(cudaStreamSynchronize(ctx->main));
     return ADSP_OK;
@@ -506,7 +559,7 @@ adsp_status adsp_ctx_create(int device, adsp_ctx **out) {
     }
     ADSP_CUDA(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
     ADSP_CUDA(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < kPipeSlots; i++) {
         ADSP_CUDA(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
         ADSP_CUDA(cudaEventCreateWithFlags(&c->ev_comp[i], cudaEventDisableTiming));
         ADSP_CUDA(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
@@ -522,14 +575,14 @@ void adsp_ctx_destroy(adsp_ctx *c) {
     for (auto &kv : c->tw_tables) cudaFree(kv.second);
     for (auto &kv : c->tw4_tables) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
     c->scratch.release(); c->d_in.release(); c->d_out.release(); c->d_k.release(); c->d_tmp.release(); c->d_small.release(); c->d_counters.release();
-    for (int i = 0; i < 2; i++) {
+    c->pool.reset();
+    for (int i = 0; i < kPipeSlots; i++) {
         c->h_in[i].release(); c->h_out[i].release(); c->pipe_in[i].release(); c->pipe_out[i].release();
         cudaEventDestroy(c->ev_in[i]); cudaEventDestroy(c->ev_comp[i]); cudaEventDestroy(c->ev_out[i]);
     }
     for (auto &t : c->timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
     for (auto e : c->event_pool) cudaEventDestroy(e);
     cudaStreamDestroy(c->copy_in); cudaStreamDestroy(c->copy_out);
-    c->h_small.release();
     for (int i = 0; i < kWorkerStreams; i++) { cudaStreamDestroy(c->worker[i]); cudaEventDestroy(c->ev_join[i]); }
     cudaEventDestroy(c->ev_fork);
     cudaStreamDestroy(c->main);
@@ -566,6 +619,27 @@ adsp_status adsp_ctx_kernel_time(adsp_ctx *c, int kind, double *total_ms, uint64
     return ADSP_OK;
 }
 void *adsp_ctx_stream(adsp_ctx *c) { return c ? (void *)c->main : nullptr; }
+
+void adsp_ctx_host_profile(adsp_ctx *c, int enable) {
+    if (!c) return;
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->host_profile = enable != 0;
+    for (double &v : c->host_prof_ms) v = 0;
+}
+adsp_status adsp_ctx_host_profile_get(adsp_ctx *c, double *ms6, uint64_t *staged_in_bytes, uint64_t *staged_out_bytes) {
+    if (!c) return ADSP_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (ms6) for (int i = 0; i < 6; i++) ms6[i] = c->host_prof_ms[i];
+    if (staged_in_bytes) *staged_in_bytes = c->staged_bytes_in;
+    if (staged_out_bytes) *staged_out_bytes = c->staged_bytes_out;
+    return ADSP_OK;
+}
+int adsp_host_ptr_is_pinned(const void *p) { return host_ptr_is_pinned(p) ? 1 : 0; }
+int adsp_ctx_stage_threads(adsp_ctx *c) {
+    if (!c) return 0;
+    std::lock_guard<std::mutex> lk(c->mu);
+    return stage_pool(c)->threads();
+}
 
 adsp_status adsp_host_alloc_pinned(size_t bytes, void **out) {
     if (!out) return ADSP_ERR_INVALID_ARG;
@@ -661,8 +735,8 @@ adsp_status oneshot(adsp_ctx *ctx, OneShot op, const T *a, int64_t n, const T *b
     ADSP_TRY(ctx->d_tmp.reserve((size_t)m * sizeof(T) * 2));
     ADSP_TRY(ctx->d_out.reserve((size_t)out_len * sizeof(T)));
     T *da = (T *)ctx->d_in.p, *db = (T *)ctx->d_tmp.p, *dbr = db + m, *dout = (T *)ctx->d_out.p;
-    ADSP_CUDA(cudaMemcpyAsync(da, a, (size_t)n * sizeof(T), cudaMemcpyHostToDevice, ctx->main));
-    ADSP_CUDA(cudaMemcpyAsync(db, b, (size_t)m * sizeof(T), cudaMemcpyHostToDevice, ctx->main));
+    ADSP_TRY(upload(ctx, da, a, (size_t)n * sizeof(T)));
+    ADSP_TRY(upload(ctx, db, b, (size_t)m * sizeof(T)));
     const T *dk = db;
     if (corr) {  // reverse b: correlate.go:22-25
         reverse_kernel<T><<<(unsigned)((m + 255) / 256), 256, 0, ctx->main>>>(db, m, m, dbr, m, 1);
@@ -690,7 +764,7 @@ adsp_status oneshot(adsp_ctx *ctx, OneShot op, const T *a, int64_t n, const T *b
         scale_by_inverse_kernel<T><<<(unsigned)((out_len + 255) / 256), 256, 0, ctx->main>>>(dout, out_len, dden);
         count_launch(ctx);
     }
-    ADSP_CUDA(cudaMemcpyAsync(out, dout, (size_t)out_len * sizeof(T), cudaMemcpyDeviceToHost, ctx->main));
+    ADSP_TRY(download(ctx, out, dout, (size_t)out_len * sizeof(T)));
     ADSP_CUDA(cudaStreamSynchronize(ctx->main));
     return ADSP_OK;
 }
@@ -782,10 +856,10 @@ adsp_status adsp_deconvolve(adsp_ctx *ctx, const double *signal, int64_t n, cons
     ADSP_TRY(ctx->d_in.reserve((size_t)n * sizeof(double)));
     ADSP_TRY(ctx->d_tmp.reserve((size_t)m * sizeof(double)));
     ADSP_TRY(ctx->d_out.reserve((size_t)out_len * sizeof(double)));
-    ADSP_CUDA(cudaMemcpyAsync(ctx->d_in.p, signal, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->main));
-    ADSP_CUDA(cudaMemcpyAsync(ctx->d_tmp.p, kernel, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, ctx->main));
+    ADSP_TRY(upload(ctx, ctx->d_in.p, signal, (size_t)n * sizeof(double)));
+    ADSP_TRY(upload(ctx, ctx->d_tmp.p, kernel, (size_t)m * sizeof(double)));
     ADSP_TRY(deconv_run(ctx, (const double *)ctx->d_in.p, n, n, (const double *)ctx->d_tmp.p, m, m, 1, reg, (double *)ctx->d_out.p, out_len, out_len));
-    ADSP_CUDA(cudaMemcpyAsync(out, ctx->d_out.p, (size_t)out_len * sizeof(double), cudaMemcpyDeviceToHost, ctx->main));
+    ADSP_TRY(download(ctx, out, ctx->d_out.p, (size_t)out_len * sizeof(double)));
     ADSP_CUDA(cudaStreamSynchronize(ctx->main));
     return ADSP_OK;
 }
@@ -866,7 +940,7 @@ adsp_status adsp_find_peak(adsp_ctx *ctx, const double *corr, int64_t len, int64
     ADSP_CUDA(cudaSetDevice(ctx->device));
     ADSP_TRY(ctx->d_in.reserve((size_t)len * sizeof(double)));
     ADSP_TRY(ctx->d_tmp.reserve(64));
-    ADSP_CUDA(cudaMemcpyAsync(ctx->d_in.p, corr, (size_t)len * sizeof(double), cudaMemcpyHostToDevice, ctx->main));
+    ADSP_TRY(upload(ctx, ctx->d_in.p, corr, (size_t)len * sizeof(double)));
     double *dv = (double *)ctx->d_tmp.p;
     long long *di = (long long *)(dv + 1);
     ADSP_TRY(peak_device<double>(ctx, (const double *)ctx->d_in.p, len, len, 1, dv, di));
@@ -885,6 +959,7 @@ adsp_status adsp_direct_batch_device(adsp_ctx *ctx, const void *a, int64_t n, in
     if (n <= 0) return ADSP_ERR_EMPTY_INPUT;
     if (m <= 0) return ADSP_ERR_EMPTY_KERNEL;
     if (batch <= 0) return ADSP_OK;
+    std::lock_guard<std::mutex> lk(ctx->mu);
     ADSP_CUDA(cudaSetDevice(ctx->device));
     if (prec == ADSP_F64) return direct_device<double>(ctx, (const double *)a, n, a_stride, (const double *)b, m, b_stride, batch, (double *)out, out_stride);
     return direct_device<float>(ctx, (const float *)a, n, a_stride, (const float *)b, m, b_stride, batch, (float *)out, out_stride);
@@ -903,11 +978,11 @@ adsp_status adsp_direct_batch(adsp_ctx *ctx, const double *a, int64_t n, int64_t
     ADSP_TRY(ctx->d_in.reserve((size_t)n * batch * sizeof(double)));
     ADSP_TRY(ctx->d_tmp.reserve((size_t)m * nb * sizeof(double)));
     ADSP_TRY(ctx->d_out.reserve((size_t)out_len * batch * sizeof(double)));
-    ADSP_TRY(copy2d(ctx, ctx->d_in.p, (size_t)n * 8, a, (size_t)a_stride * 8, (size_t)n * 8, (size_t)batch, cudaMemcpyHostToDevice));
-    ADSP_TRY(copy2d(ctx, ctx->d_tmp.p, (size_t)m * 8, b, (size_t)(b_stride ? b_stride : m) * 8, (size_t)m * 8, (size_t)nb, cudaMemcpyHostToDevice));
+    ADSP_TRY(upload2d(ctx, ctx->d_in.p, (size_t)n * 8, a, (size_t)a_stride * 8, (size_t)n * 8, (size_t)batch));
+    ADSP_TRY(upload2d(ctx, ctx->d_tmp.p, (size_t)m * 8, b, (size_t)(b_stride ? b_stride : m) * 8, (size_t)m * 8, (size_t)nb));
     ADSP_TRY(direct_device<double>(ctx, (const double *)ctx->d_in.p, n, n, (const double *)ctx->d_tmp.p, m, b_stride ? m : 0, batch,
                                    (double *)ctx->d_out.p, out_len));
-    ADSP_TRY(copy2d(ctx, out, (size_t)out_stride * 8, ctx->d_out.p, (size_t)out_len * 8, (size_t)out_len * 8, (size_t)batch, cudaMemcpyDeviceToHost));
+    ADSP_TRY(download2d(ctx, out, (size_t)out_stride * 8, ctx->d_out.p, (size_t)out_len * 8, (size_t)out_len * 8, (size_t)batch));
     ADSP_CUDA(cudaStreamSynchronize(ctx->main));
     return ADSP_OK;
 }
@@ -991,6 +1066,7 @@ adsp_status adsp_correlate_batch(adsp_ctx *ctx, const double *a, int64_t n, int6
     const int64_t out_len = n + m - 1;
     void *da = nullptr, *db = nullptr, *dout = nullptr, *dpi = nullptr, *dpv = nullptr;
     adsp_status st = ADSP_OK;
+    std::lock_guard<std::mutex> lk(ctx->mu);   // the staged transfers use the context's pinned slots
     ADSP_CUDA(cudaSetDevice(ctx->device));
     do {
         if ((st = adsp_device_alloc(ctx, (size_t)n * pairs * 8, &da)) != ADSP_OK) break;
@@ -998,12 +1074,12 @@ adsp_status adsp_correlate_batch(adsp_ctx *ctx, const double *a, int64_t n, int6
         if (out && (st = adsp_device_alloc(ctx, (size_t)out_len * pairs * 8, &dout)) != ADSP_OK) break;
         if ((st = adsp_device_alloc(ctx, (size_t)pairs * 8, &dpi)) != ADSP_OK) break;
         if ((st = adsp_device_alloc(ctx, (size_t)pairs * 8, &dpv)) != ADSP_OK) break;
-        if ((st = copy2d(ctx, da, (size_t)n * 8, a, (size_t)a_stride * 8, (size_t)n * 8, (size_t)pairs, cudaMemcpyHostToDevice)) != ADSP_OK) break;
-        if ((st = copy2d(ctx, db, (size_t)m * 8, b, (size_t)b_stride * 8, (size_t)m * 8, (size_t)pairs, cudaMemcpyHostToDevice)) != ADSP_OK) break;
-        st = adsp_correlate_batch_device(ctx, da, n, n, db, m, m, pairs, dout, out_len, (peak_index && peak_value) ? dpi : nullptr,
-                                         (peak_index && peak_value) ? dpv : nullptr, ADSP_F64);
+        if ((st = upload2d(ctx, da, (size_t)n * 8, a, (size_t)a_stride * 8, (size_t)n * 8, (size_t)pairs)) != ADSP_OK) break;
+        if ((st = upload2d(ctx, db, (size_t)m * 8, b, (size_t)b_stride * 8, (size_t)m * 8, (size_t)pairs)) != ADSP_OK) break;
+        st = correlate_batch_dev<double>(ctx, (const double *)da, n, n, (const double *)db, m, m, pairs, (double *)dout, out_len,
+                                         (peak_index && peak_value) ? (long long *)dpi : nullptr, (peak_index && peak_value) ? (double *)dpv : nullptr);
         if (st != ADSP_OK) break;
-        if (out && (st = copy2d(ctx, out, (size_t)out_stride * 8, dout, (size_t)out_len * 8, (size_t)out_len * 8, (size_t)pairs, cudaMemcpyDeviceToHost)) != ADSP_OK) break;
+        if (out && (st = download2d(ctx, out, (size_t)out_stride * 8, dout, (size_t)out_len * 8, (size_t)out_len * 8, (size_t)pairs)) != ADSP_OK) break;
         if (peak_index && peak_value) {
             cudaMemcpyAsync(peak_index, dpi, (size_t)pairs * 8, cudaMemcpyDeviceToHost, ctx->main);
             cudaMemcpyAsync(peak_value, dpv, (size_t)pairs * 8, cudaMemcpyDeviceToHost, ctx->main);
@@ -1080,6 +1156,9 @@ adsp_status adsp_plan_process_device(adsp_plan *p, const void *in, int64_t n, in
     if (channels <= 0) return ADSP_OK;
     if (!in || !out) return ADSP_ERR_INVALID_ARG;
     adsp_ctx *ctx = p->ctx;
+    // enqueue under the context lock: the launch sequence mutates ctx->scratch, the table maps, the fork/join events
+    // and p->graphs, all shared with the host-pointer entry points (the lock is NOT held across any device wait)
+    std::lock_guard<std::mutex> lk(ctx->mu);
     ADSP_CUDA(cudaSetDevice(ctx->device));
     // A repeated call (same buffers and sizes) replays a captured CUDA graph of the whole launch
     // sequence (kernels on the worker streams, fork/join events): ~200 launches become one submission.
@@ -1089,6 +1168,13 @@ adsp_status adsp_plan_process_device(adsp_plan *p, const void *in, int64_t n, in
     adsp_plan::GraphEntry *ent = nullptr;
     for (auto &g : p->graphs)
         if (g.in == in && g.out == out && g.n == n && g.channels == channels && g.in_stride == in_stride && g.out_stride == out_stride) { ent = &g; break; }
+    if (ent && ent->exec && ent->alloc_gen != g_alloc_generation.load(std::memory_order_relaxed)) {
+        // a shared device buffer (scratch, staging) was re-allocated since the capture: the graph's baked-in pointers may
+        // be stale.  Drop it; this call runs eagerly (and re-reserves what it needs), the next one captures again.
+        cudaGraphExecDestroy(ent->exec);
+        p->graphs.erase(p->graphs.begin() + (ent - p->graphs.data()));
+        ent = nullptr;
+    }
     if (ent && ent->exec) {
         ADSP_CUDA(cudaGraphLaunch(ent->exec, ctx->main));
         count_launch(ctx, (int)ent->launches);
@@ -1099,20 +1185,21 @@ adsp_status adsp_plan_process_device(adsp_plan *p, const void *in, int64_t n, in
             if (p->graphs.front().exec) cudaGraphExecDestroy(p->graphs.front().exec);
             p->graphs.erase(p->graphs.begin());
         }
-        p->graphs.push_back({in, out, n, channels, in_stride, out_stride, nullptr, 0, 1});
+        p->graphs.push_back({in, out, n, channels, in_stride, out_stride, nullptr, 0, 1, 0});
         return plan_run_device_any(p, in, n, channels, in_stride, out, out_stride);
     }
     // second sighting: capture
     const uint64_t l0 = ctx->launches.load();
+    const uint64_t gen0 = g_alloc_generation.load(std::memory_order_relaxed);
     cudaGraph_t graph = nullptr;
     ADSP_CUDA(cudaStreamBeginCapture(ctx->main, cudaStreamCaptureModeThreadLocal));
     adsp_status st = plan_run_device_any(p, in, n, channels, in_stride, out, out_stride);
     cudaError_t ce = cudaStreamEndCapture(ctx->main, &graph);
-    if (st != ADSP_OK || ce != cudaSuccess || !graph) {
+    // an allocation during the capture (a buffer grew) means pointers recorded before it are stale: do not keep the graph
+    const bool moved = g_alloc_generation.load(std::memory_order_relaxed) != gen0;
+    if (st != ADSP_OK || ce != cudaSuccess || !graph || moved) {
         cudaGetLastError();
         if (graph) cudaGraphDestroy(graph);
-        ent->seen = 1 << 30;   // do not try again for this shape
-        ent->exec = nullptr;
         p->graphs.erase(p->graphs.begin() + (ent - p->graphs.data()));
         return plan_run_device_any(p, in, n, channels, in_stride, out, out_stride);
     }
@@ -1121,6 +1208,7 @@ adsp_status adsp_plan_process_device(adsp_plan *p, const void *in, int64_t n, in
     cudaGraphDestroy(graph);
     if (ce != cudaSuccess) { cudaGetLastError(); return plan_run_device_any(p, in, n, channels, in_stride, out, out_stride); }
     ent->exec = exec;
+    ent->alloc_gen = gen0;
     ent->launches = ctx->launches.load() - l0;
     ctx->launches.store(l0);
     ADSP_CUDA(cudaGraphLaunch(ent->exec, ctx->main));
@@ -1311,6 +1399,7 @@ adsp_status part_create(adsp_ctx *ctx, const T *kernel, int64_t K, int min_order
     if (max_order < min_order) { set_error("conv: invalid block order: maxBlockOrder must be >= minBlockOrder"); return ADSP_ERR_INVALID_BLOCK_ORDER; }
     if (min_order > 24) { set_error("conv: invalid block order: too large"); return ADSP_ERR_INVALID_BLOCK_ORDER; }
     if (channels < 1) { set_error("partitioned: channels must be >= 1"); return ADSP_ERR_INVALID_ARG; }
+    if (channels > 131070) { set_error("partitioned: at most 131070 channels per plan (65535 channel pairs per launch); split the batch over several plans"); return ADSP_ERR_INVALID_ARG; }
     std::lock_guard<std::mutex> lk(ctx->mu);
     ADSP_CUDA(cudaSetDevice(ctx->device));
     adsp_plan *p = new adsp_plan();
@@ -1426,6 +1515,7 @@ adsp_status adsp_partitioned_internal_stage_info(const adsp_plan *p, int index, 
 
 void adsp_plan_reset(adsp_plan *p) {
     if (!p) return;
+    std::lock_guard<std::mutex> lk(p->ctx->mu);
     if (p->fdl) { cudaSetDevice(p->ctx->device); fdl_reset(p->fdl); return; }   // partitioned.go:399-407
     if (p->kind == PLAN_PART || p->kind == PLAN_STREAM) {                    // partitioned.go:399-407, streaming_overlap_save.go:167-169
         cudaSetDevice(p->ctx->device);

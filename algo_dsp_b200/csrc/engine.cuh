@@ -3,13 +3,17 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -54,6 +58,37 @@ struct PinnedBuf {
     void release();
 };
 
+// ------------------------------------------------------------------ pinned host staging (staging.cu)
+// A Go []float64 (overlap_save.go:132-133) -- like any malloc'ed buffer -- is PAGEABLE: the DMA engines cannot read it, and
+// the CUDA runtime's own pageable path is a synchronous single-threaded bounce copy.  The library therefore stages
+// pageable caller memory through its own pinned buffers with a small pool of copy threads, overlapped with the
+// H2D | kernels | D2H pipeline.  Pinned or registered caller memory (adsp_host_alloc_pinned) is DMA'd in place.
+constexpr int kPipeSlots = 3;       // device / pinned slots per direction of the host-buffer pipeline
+
+class StagePool {
+public:
+    struct Job { std::atomic<long long> remaining{0}; std::mutex m; std::condition_variable cv; };
+    using Ticket = std::shared_ptr<Job>;
+    explicit StagePool(int nthreads);
+    ~StagePool();
+    int threads() const { return (int)workers_.size(); }
+    // copies `rows` rows of `width` bytes (row pitches in bytes), split into slices run by the pool; returns at once
+    Ticket copy2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows);
+    static void wait(const Ticket &t);
+    void copy2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows) { wait(copy2d_async(dst, dpitch, src, spitch, width, rows)); }
+private:
+    struct Slice { char *dst; const char *src; size_t dpitch, spitch, width, rows; Ticket job; };
+    void run();
+    std::vector<std::thread> workers_;
+    std::deque<Slice> q_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    bool stop_ = false;
+};
+
+// true when the DMA engines can access `p` directly (cudaMallocHost / cudaHostRegister / managed memory)
+bool host_ptr_is_pinned(const void *p);
+
 // Internal transform geometry chosen for a kernel length (free to differ from the reference's
 // FFTSize()/StepSize(), which are reported from the reference formulas).
 struct FftChoice {
@@ -86,13 +121,18 @@ struct adsp_ctx {
     std::map<std::pair<int, int>, std::pair<void *, void *>> tw4_tables;  // (lgN, prec) -> (hi, lo)
     adsp::DevBuf scratch;              // four-step intermediates (L2 resident by construction)
     adsp::DevBuf d_in, d_out, d_k, d_tmp, d_small, d_counters;
-    adsp::PinnedBuf h_in[2], h_out[2], h_small;
+    adsp::PinnedBuf h_in[adsp::kPipeSlots], h_out[adsp::kPipeSlots];   // pinned staging of pageable caller memory
+    std::unique_ptr<adsp::StagePool> pool;                               // copy threads (created on the first pageable call)
+    // host-path profile (adsp_ctx_host_profile): ms of {stage-in, H2D, kernels, D2H, stage-out, total} of the last small call
+    bool host_profile = false;
+    double host_prof_ms[6] = {0, 0, 0, 0, 0, 0};
+    uint64_t staged_bytes_in = 0, staged_bytes_out = 0;                  // bytes that went through pinned staging (diagnostic)
     std::atomic<uint64_t> launches{0};
     size_t scratch_budget = 0;  // bytes of scratch allowed in flight (fits L2)
     // host-staged pipeline (H2D | compute | D2H overlapped over channel chunks)
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
-    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
-    adsp::DevBuf pipe_in[2], pipe_out[2];
+    cudaEvent_t ev_in[adsp::kPipeSlots] = {}, ev_comp[adsp::kPipeSlots] = {}, ev_out[adsp::kPipeSlots] = {};
+    adsp::DevBuf pipe_in[adsp::kPipeSlots], pipe_out[adsp::kPipeSlots];
     // optional per-kernel timing (bench roofline): event pairs around every launch of a kind
     bool timing = false;
     struct TimedLaunch { int kind; cudaEvent_t e0, e1; };
@@ -168,6 +208,15 @@ void fdl_stage_info(const FdlEngine *e, int i, int *part, int *count, long long 
 // in/out: `channels` rows of n samples (strides in elements), host or device pointers; mix: out = dry*in + wet*y
 adsp_status fdl_process(FdlEngine *e, const void *in, long long n, long long in_stride, void *out, long long out_stride, bool host_ptrs,
                         bool mix);
+
+// host <-> device transfers that stage pageable memory through the context's pinned buffers (staging.cu).
+// upload: returns once `src` has been consumed (the device copy may still be in flight on ctx->main);
+// download: enqueues after everything already on ctx->main, returns when `dst` holds the data.
+StagePool *stage_pool(adsp_ctx *ctx);
+adsp_status upload(adsp_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+adsp_status download(adsp_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+adsp_status upload2d(adsp_ctx *ctx, void *dst_dev, size_t dpitch, const void *src_host, size_t spitch, size_t width, size_t rows);
+adsp_status download2d(adsp_ctx *ctx, void *dst_host, size_t dpitch, const void *src_dev, size_t spitch, size_t width, size_t rows);
 
 inline void count_launch(adsp_ctx *ctx, int n = 1) { ctx->launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 

@@ -188,10 +188,15 @@ fdl_mac_bins(const cpx<T> *__restrict__ fdl, const cpx<T> *__restrict__ H, int c
         for (int f = 0; f < FT - 1; f++) hw[f] = hw[f + 1];
         if (ptop < count) hw[FT - 1] = __ldg(&hb[(size_t)ptop * L2]); else { hw[FT - 1].x = (T)0; hw[FT - 1].y = (T)0; }
         const C x = __ldcg(&ring_base[(size_t)slot * L2]);
+        // firing f meets partition ptop - (FT-1-f) at this slot; outside [0, count) the slot does not belong to that
+        // firing (newer than it, or older than the IR) and is skipped rather than multiplied by a zero tap, so a
+        // non-finite or stale delay-line value cannot leak into outputs the reference leaves untouched (0 * NaN)
 #pragma unroll
         for (int f = 0; f < FT; f++) {
-            acc[f].x += x.x * hw[f].x - x.y * hw[f].y;
-            acc[f].y += x.x * hw[f].y + x.y * hw[f].x;
+            if ((unsigned)(ptop - (FT - 1 - f)) < (unsigned)count) {
+                acc[f].x += x.x * hw[f].x - x.y * hw[f].y;
+                acc[f].y += x.x * hw[f].y + x.y * hw[f].x;
+            }
         }
         ptop++;
         slot = (slot == 0) ? ring - 1 : slot - 1;
@@ -393,10 +398,14 @@ adsp_status fdl_chunk(FdlEngine *e, long long n, const T *d_in, long long in_str
             ADSP_TRY(fdl_mac_any<T>(ctx, 2 * g.B, ma));
         }
     }
-    dim3 grid((unsigned)((n + 255) / 256), (unsigned)e->channels);
-    fdl_emit<T><<<grid, 256, 0, ctx->main>>>((T *)e->acc.p, e->acc_len, e->acc_len - 1, e->pos - e->latency, n, d_in, in_stride, d_out,
-                                             out_stride, mix ? 1 : 0, (T)e->wet, (T)e->dry);
-    count_launch(ctx);
+    for (int c0 = 0; c0 < e->channels; c0 += 65535) {   // grid.y is limited to 65535 rows per launch
+        const int nc = std::min(65535, e->channels - c0);
+        dim3 grid((unsigned)((n + 255) / 256), (unsigned)nc);
+        fdl_emit<T><<<grid, 256, 0, ctx->main>>>((T *)e->acc.p + (long long)c0 * e->acc_len, e->acc_len, e->acc_len - 1, e->pos - e->latency, n,
+                                                 d_in + (long long)c0 * in_stride, in_stride, d_out + (long long)c0 * out_stride, out_stride,
+                                                 mix ? 1 : 0, (T)e->wet, (T)e->dry);
+        count_launch(ctx);
+    }
     // keep the last HX input samples as the history of the next chunk: one strided copy into the other buffer
     T *xb = (T *)e->xbuf.p;
     ADSP_CUDA(cudaMemcpy2DAsync(e->xbuf_alt.p, (size_t)xstride * sizeof(T), xb + n, (size_t)xstride * sizeof(T), (size_t)e->HX * sizeof(T),

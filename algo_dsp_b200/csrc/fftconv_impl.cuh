@@ -947,7 +947,13 @@ adsp_status fft_deconvolve_device(adsp_ctx *ctx, const T *sig, long long n, long
                                   long long *d_bad) {
     long long N = 1;
     while (N < n) N *= 2;
-    if (m > N || N > (1LL << 22) || batch <= 0) { set_error("deconvolve: unsupported size"); return ADSP_ERR_INVALID_ARG; }
+    if (batch <= 0) { set_error("deconvolve: empty batch"); return ADSP_ERR_INVALID_ARG; }
+    if (N > (1LL << 22)) {
+        set_error("deconvolve: signals longer than 2^22 = 4194304 samples are not supported (the reference's transform length nextPow2(n) = " +
+                  std::to_string(N) + " exceeds the largest single transform of this library)");
+        return ADSP_ERR_INVALID_ARG;
+    }
+    if (m > N) { set_error("deconvolve: kernel (" + std::to_string(m) + " taps) longer than the transform length nextPow2(n) = " + std::to_string(N)); return ADSP_ERR_INVALID_ARG; }
     if (N < 16) {
         LaunchTimer lt(ctx, ctx->main, KK_OTHER);
         deconv_tiny<T><<<(unsigned)batch, 1, 0, ctx->main>>>(sig, n, s_stride, ker, m, k_stride, out, out_stride, out_len, (int)N, reg, d_bad);

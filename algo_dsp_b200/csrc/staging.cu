@@ -1,0 +1,198 @@
+// staging.cu -- pinned host staging for pageable caller memory (north star: "pinned host staging").
+//
+// The Go API hands the library plain []float64 slices (overlap_save.go:132-133 allocates the result with make); such
+// memory is pageable, so cudaMemcpyAsync on it degrades to the runtime's synchronous bounce copy and nothing overlaps.
+// Here pageable buffers are copied to/from the context's own pinned slots by a small pool of host threads (a single
+// memcpy thread moves ~10 GB/s, PCIe Gen5 x16 needs ~50 GB/s per direction) while the DMA engines and the SMs work on
+// the neighbouring chunks.  Memory that is already pinned/registered is DMA'd in place.
+#include <algorithm>
+
+#include "engine.cuh"
+
+namespace adsp {
+
+// ------------------------------------------------------------------ copy-thread pool
+StagePool::StagePool(int nthreads) {
+    if (nthreads < 1) nthreads = 1;
+    for (int i = 0; i < nthreads; i++) workers_.emplace_back([this] { run(); });
+}
+
+StagePool::~StagePool() {
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto &t : workers_) t.join();
+}
+
+void StagePool::run() {
+    for (;;) {
+        Slice s;
+        {
+            std::unique_lock<std::mutex> lk(m_);
+            cv_.wait(lk, [this] { return stop_ || !q_.empty(); });
+            if (q_.empty()) return;   // stop requested and nothing left
+            s = std::move(q_.front());
+            q_.pop_front();
+        }
+        if (s.dpitch == s.width && s.spitch == s.width) memcpy(s.dst, s.src, s.width * s.rows);
+        else for (size_t r = 0; r < s.rows; r++) memcpy(s.dst + r * s.dpitch, s.src + r * s.spitch, s.width);
+        if (s.job->remaining.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+            std::lock_guard<std::mutex> lk(s.job->m);
+            s.job->cv.notify_all();
+        }
+    }
+}
+
+StagePool::Ticket StagePool::copy2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows) {
+    Ticket job = std::make_shared<Job>();
+    if (rows == 0 || width == 0) return job;
+    // slices of about 1 MiB (never more than 4 per worker per job, so that tiny copies do not pay for the queue)
+    const size_t total = width * rows;
+    size_t nsl = std::min<size_t>((total + (1u << 20) - 1) >> 20, (size_t)workers_.size() * 4);
+    if (nsl < 1) nsl = 1;
+    std::vector<Slice> sl;
+    if (rows >= nsl) {                       // split by rows
+        const size_t per = (rows + nsl - 1) / nsl;
+        for (size_t r0 = 0; r0 < rows; r0 += per)
+            sl.push_back({(char *)dst + r0 * dpitch, (const char *)src + r0 * spitch, dpitch, spitch, width, std::min(per, rows - r0), job});
+    } else {                                 // few long rows: split every row by columns (64-byte aligned cuts)
+        const size_t per_row = (nsl + rows - 1) / rows;
+        size_t seg = (width + per_row - 1) / per_row;
+        seg = (seg + 63) & ~(size_t)63;
+        for (size_t r = 0; r < rows; r++)
+            for (size_t c0 = 0; c0 < width; c0 += seg)
+                sl.push_back({(char *)dst + r * dpitch + c0, (const char *)src + r * spitch + c0, 0, 0, std::min(seg, width - c0), 1, job});
+        for (auto &s : sl) { s.dpitch = s.width; s.spitch = s.width; }
+    }
+    job->remaining.store((long long)sl.size(), std::memory_order_release);
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        for (auto &s : sl) q_.push_back(std::move(s));
+    }
+    cv_.notify_all();
+    return job;
+}
+
+void StagePool::wait(const Ticket &t) {
+    if (!t) return;
+    std::unique_lock<std::mutex> lk(t->m);
+    t->cv.wait(lk, [&] { return t->remaining.load(std::memory_order_acquire) <= 0; });
+}
+
+bool host_ptr_is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type != cudaMemoryTypeUnregistered;
+}
+
+StagePool *stage_pool(adsp_ctx *ctx) {
+    if (!ctx->pool) {
+        const unsigned hw = std::thread::hardware_concurrency();
+        long long n = env_ll("ADSP_STAGE_THREADS", 0);
+        if (n <= 0) n = std::max(1u, std::min(8u, hw ? hw / 2 : 4u));
+        ctx->pool.reset(new StagePool((int)n));
+    }
+    return ctx->pool.get();
+}
+
+// ------------------------------------------------------------------ staged transfers on ctx->main
+// Pageable transfers below this size go through the runtime's own bounce path (one call, no pool wake-up).
+static constexpr size_t kStageMin = 256u << 10;
+
+static size_t stage_chunk_bytes() {
+    long long mb = env_ll("ADSP_STAGE_CHUNK_MB", 8);
+    if (mb < 1) mb = 1;
+    return (size_t)mb << 20;
+}
+
+adsp_status upload2d(adsp_ctx *ctx, void *dst_dev, size_t dpitch, const void *src_host, size_t spitch, size_t width, size_t rows) {
+    if (rows == 0 || width == 0) return ADSP_OK;
+    const bool dense = (rows == 1) || (dpitch == width && spitch == width);
+    if (host_ptr_is_pinned(src_host) || width * rows < kStageMin) {
+        if (dense) ADSP_CUDA(cudaMemcpyAsync(dst_dev, src_host, width * rows, cudaMemcpyHostToDevice, ctx->main));
+        else ADSP_CUDA(cudaMemcpy2DAsync(dst_dev, dpitch, src_host, spitch, width, rows, cudaMemcpyHostToDevice, ctx->main));
+        return ADSP_OK;
+    }
+    StagePool *pool = stage_pool(ctx);
+    const size_t chunk = stage_chunk_bytes();
+    for (int s = 0; s < kPipeSlots; s++) ADSP_TRY(ctx->h_in[s].reserve(chunk));
+    ctx->staged_bytes_in += width * rows;
+    int i = 0;
+    auto send = [&](char *d, const char *h, size_t dp, size_t sp, size_t w, size_t r) -> adsp_status {
+        const int s = i++ % kPipeSlots;
+        ADSP_CUDA(cudaEventSynchronize(ctx->ev_in[s]));                  // the DMA that last read this slot is done
+        pool->copy2d(ctx->h_in[s].p, w, h, sp, w, r);                    // user memory -> pinned slot (dense rows)
+        if (r == 1) ADSP_CUDA(cudaMemcpyAsync(d, ctx->h_in[s].p, w, cudaMemcpyHostToDevice, ctx->main));
+        else ADSP_CUDA(cudaMemcpy2DAsync(d, dp, ctx->h_in[s].p, w, w, r, cudaMemcpyHostToDevice, ctx->main));
+        ADSP_CUDA(cudaEventRecord(ctx->ev_in[s], ctx->main));
+        return ADSP_OK;
+    };
+    if (width >= chunk || rows == 1) {
+        for (size_t r = 0; r < rows; r++)
+            for (size_t c0 = 0; c0 < width; c0 += chunk)
+                ADSP_TRY(send((char *)dst_dev + r * dpitch + c0, (const char *)src_host + r * spitch + c0, 0, 0, std::min(chunk, width - c0), 1));
+    } else {
+        const size_t per = std::max<size_t>(1, chunk / width);
+        for (size_t r0 = 0; r0 < rows; r0 += per)
+            ADSP_TRY(send((char *)dst_dev + r0 * dpitch, (const char *)src_host + r0 * spitch, dpitch, spitch, width, std::min(per, rows - r0)));
+    }
+    return ADSP_OK;
+}
+
+adsp_status download2d(adsp_ctx *ctx, void *dst_host, size_t dpitch, const void *src_dev, size_t spitch, size_t width, size_t rows) {
+    if (rows == 0 || width == 0) return ADSP_OK;
+    const bool dense = (rows == 1) || (dpitch == width && spitch == width);
+    if (host_ptr_is_pinned(dst_host) || width * rows < kStageMin) {
+        if (dense) ADSP_CUDA(cudaMemcpyAsync(dst_host, src_dev, width * rows, cudaMemcpyDeviceToHost, ctx->main));
+        else ADSP_CUDA(cudaMemcpy2DAsync(dst_host, dpitch, src_dev, spitch, width, rows, cudaMemcpyDeviceToHost, ctx->main));
+        ADSP_CUDA(cudaStreamSynchronize(ctx->main));
+        return ADSP_OK;
+    }
+    StagePool *pool = stage_pool(ctx);
+    const size_t chunk = stage_chunk_bytes();
+    for (int s = 0; s < kPipeSlots; s++) ADSP_TRY(ctx->h_out[s].reserve(chunk));
+    ctx->staged_bytes_out += width * rows;
+    struct Piece { char *h; const char *d; size_t hp, dp, w, r; };
+    std::vector<Piece> pieces;
+    if (width >= chunk || rows == 1) {
+        for (size_t r = 0; r < rows; r++)
+            for (size_t c0 = 0; c0 < width; c0 += chunk)
+                pieces.push_back({(char *)dst_host + r * dpitch + c0, (const char *)src_dev + r * spitch + c0, 0, 0, std::min(chunk, width - c0), 1});
+    } else {
+        const size_t per = std::max<size_t>(1, chunk / width);
+        for (size_t r0 = 0; r0 < rows; r0 += per)
+            pieces.push_back({(char *)dst_host + r0 * dpitch, (const char *)src_dev + r0 * spitch, dpitch, spitch, width, std::min(per, rows - r0)});
+    }
+    StagePool::Ticket tk[kPipeSlots];
+    const size_t np = pieces.size();
+    for (size_t i = 0; i <= np; i++) {
+        if (i < np) {
+            const int s = (int)(i % kPipeSlots);
+            StagePool::wait(tk[s]);                                      // the host copy that last read this slot is done
+            const Piece &pc = pieces[i];
+            if (pc.r == 1) ADSP_CUDA(cudaMemcpyAsync(ctx->h_out[s].p, pc.d, pc.w, cudaMemcpyDeviceToHost, ctx->main));
+            else ADSP_CUDA(cudaMemcpy2DAsync(ctx->h_out[s].p, pc.w, pc.d, pc.dp, pc.w, pc.r, cudaMemcpyDeviceToHost, ctx->main));
+            ADSP_CUDA(cudaEventRecord(ctx->ev_out[s], ctx->main));
+        }
+        if (i >= 1) {
+            const size_t j = i - 1;
+            const int s = (int)(j % kPipeSlots);
+            ADSP_CUDA(cudaEventSynchronize(ctx->ev_out[s]));
+            const Piece &pc = pieces[j];
+            tk[s] = pool->copy2d_async(pc.h, pc.r == 1 ? pc.w : pc.hp, ctx->h_out[s].p, pc.w, pc.w, pc.r);
+        }
+    }
+    for (int s = 0; s < kPipeSlots; s++) StagePool::wait(tk[s]);
+    return ADSP_OK;
+}
+
+adsp_status upload(adsp_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes) {
+    return upload2d(ctx, dst_dev, bytes, src_host, bytes, bytes, 1);
+}
+adsp_status download(adsp_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes) {
+    return download2d(ctx, dst_host, bytes, src_dev, bytes, bytes, 1);
+}
+
+}  // namespace adsp

@@ -75,7 +75,19 @@ ADSP_API adsp_status adsp_ctx_kernel_time(adsp_ctx *ctx, int kind, double *total
 /* Raw cudaStream_t of the context's main stream (for event timing by a harness). */
 ADSP_API void *adsp_ctx_stream(adsp_ctx *ctx);
 
-/* Pinned host staging for callers that want zero-copy DMA (Go side: C.malloc replacement). */
+/* Host-buffer calls and pageable memory.  Every entry point that takes HOST pointers accepts ordinary pageable memory
+ * (a Go []float64, malloc, numpy): the library stages it through its own pinned buffers with a pool of copy threads
+ * (ADSP_STAGE_THREADS, default min(8, cores/2)), overlapped with H2D | kernels | D2H (csrc/staging.cu).  Memory from
+ * adsp_host_alloc_pinned (or cudaHostRegister'ed by the caller) is DMA'd in place, which saves the two host copies.
+ * adsp_ctx_host_profile(ctx, 1) makes the small-call path (one upload, kernels, one download) record a breakdown of the
+ * last call: ms6 = {device allocation, upload (stage-in + H2D), kernels, download (D2H + stage-out), 0, total}; the
+ * phases are serialised by a stream sync each while profiling is on.  staged_*_bytes count what went through staging. */
+ADSP_API void adsp_ctx_host_profile(adsp_ctx *ctx, int enable);
+ADSP_API adsp_status adsp_ctx_host_profile_get(adsp_ctx *ctx, double *ms6, uint64_t *staged_in_bytes, uint64_t *staged_out_bytes);
+ADSP_API int adsp_host_ptr_is_pinned(const void *p);     /* 1: DMA-able in place, 0: pageable (will be staged) */
+ADSP_API int adsp_ctx_stage_threads(adsp_ctx *ctx);      /* size of the context's copy-thread pool (creates it) */
+
+/* Pinned host memory for callers that want zero-copy DMA (Go side: C.malloc replacement). */
 ADSP_API adsp_status adsp_host_alloc_pinned(size_t bytes, void **out);
 ADSP_API void adsp_host_free_pinned(void *p);
 ADSP_API adsp_status adsp_device_alloc(adsp_ctx *ctx, size_t bytes, void **out);

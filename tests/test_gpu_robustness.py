@@ -93,3 +93,108 @@ def test_nan_and_inf_propagate_like_ieee(conv):
     x[40] = np.nan
     y = conv.Direct(x, [1.0, 2.0, 3.0])
     assert np.isnan(y[40:43]).all() and not np.isnan(np.delete(y, [40, 41, 42])).any()
+
+
+def test_graph_replay_survives_scratch_reallocation(conv, oracle):
+    """a captured graph bakes the shared scratch pointer in.  Small call x3 (eager, capture, replay),
+    then a larger call on the same context grows the scratch (cudaFree + cudaMalloc), then the small call again: the
+    stale graph must be dropped, not replayed against freed memory."""
+    torch = pytest.importorskip("torch")
+    ctx = conv.Context(0)
+    K = 20000
+    h = G.decaying_ir(K)
+    plan = conv.OverlapSave(h, 0, ctx=ctx)
+    n, ch = 100000, 2
+    x = torch.tensor(np.stack([G.white(n, seed=c) for c in range(ch)]), device="cuda")
+    ol = n + K - 1
+    y = torch.zeros((ch, ol), device="cuda", dtype=torch.float64)
+    ref = oracle.overlap_save(h, 0, x[1].cpu().numpy())
+
+    def small():
+        y.zero_()
+        plan.process_device(x.data_ptr(), n, ch, n, y.data_ptr(), ol)
+        plan.sync()
+        assert G.rel_l2(y[1].cpu().numpy(), ref) <= 1e-12
+
+    for _ in range(3):
+        small()
+    # grow the context's scratch: many more channels of a longer transform through another plan of the same context
+    big = conv.OverlapSave(G.decaying_ir(90000), 0, ctx=ctx)
+    nb, chb = 400000, 48
+    xb = torch.rand((chb, nb), device="cuda", dtype=torch.float64)
+    yb = torch.zeros((chb, nb + 90000 - 1), device="cuda", dtype=torch.float64)
+    big.process_device(xb.data_ptr(), nb, chb, nb, yb.data_ptr(), nb + 90000 - 1)
+    big.sync()
+    for _ in range(3):
+        small()
+    # and a one-shot correlate (another user of the shared scratch) between replays
+    conv.Correlate(G.white(300000, seed=5), G.white(200000, seed=6), ctx=ctx)
+    small()
+    big.Close()
+    plan.Close()
+
+
+@pytest.mark.parametrize("in_pinned,out_pinned", [(False, False), (True, False), (False, True), (True, True)])
+def test_pageable_and_pinned_host_buffers_through_the_pipeline(conv, oracle, monkeypatch, in_pinned, out_pinned):
+    """The chunked host pipeline (stage-in | H2D | kernels | D2H | stage-out) with pageable and pinned caller memory in
+    every combination; chunk size forced small so that several chunks and slot reuse happen at a test-sized batch."""
+    monkeypatch.setenv("ADSP_STAGE_PIPE_CHUNK_MB", "1")
+    monkeypatch.setenv("ADSP_PIPE_CHUNK_MB", "1")
+    K, n, ch = 3000, 40000, 112         # (n + out_len) * 8 B * ch = 74 MB > the 32 MB small-call limit; 1 MB chunks -> 1 row per chunk... many chunks
+    h = G.decaying_ir(K)
+    ol = n + K - 1
+    xs = conv.pinned_empty((ch, n)) if in_pinned else np.empty((ch, n))
+    for c in range(ch):
+        xs[c] = G.white(n, seed=c)
+    out = conv.pinned_empty((ch, ol)) if out_pinned else np.empty((ch, ol))
+    out[:] = -7.0
+    assert bool(L.load().adsp_host_ptr_is_pinned(C.c_void_p(xs.ctypes.data))) == in_pinned
+    assert bool(L.load().adsp_host_ptr_is_pinned(C.c_void_p(out.ctypes.data))) == out_pinned
+    ctx = conv.Context(0)
+    plan = conv.OverlapSave(h, 0, ctx=ctx)
+    for _ in range(2):                  # second pass reuses the pinned slots and events
+        st = L.load().adsp_plan_process_batch(plan._h, xs.ctypes.data_as(C.c_void_p), n, ch, n, out.ctypes.data_as(C.c_void_p), ol)
+        assert st == L.OK
+    for c in (0, 1, 2, 55, ch - 2, ch - 1):
+        assert G.rel_l2(out[c], oracle.overlap_save(h, 0, xs[c])) <= 1e-12
+    prof = ctx.host_profile_get()
+    assert (prof["staged_in_bytes"] > 0) == (not in_pinned) and (prof["staged_out_bytes"] > 0) == (not out_pinned)
+    plan.Close()
+
+
+def test_small_call_profile_and_staged_one_shot(conv, oracle):
+    """Config-1-sized mono call from pageable memory: staged through the pinned slots, phase breakdown recorded."""
+    ctx = conv.Context(0)
+    h, x = G.decaying_ir(96000), G.white(480000, seed=1)
+    plan = conv.OverlapSave(h, 0, ctx=ctx)
+    plan.Process(x)
+    ctx.host_profile(True)
+    y = plan.Process(x)
+    prof = ctx.host_profile_get()
+    ctx.host_profile(False)
+    assert G.rel_l2(y, oracle.overlap_save(h, 0, x)) <= 1e-12
+    assert prof["total_ms"] > 0 and prof["kernels_ms"] > 0 and prof["upload_ms"] > 0 and prof["download_ms"] > 0
+    assert prof["staged_in_bytes"] >= x.nbytes and ctx.stage_threads() >= 1
+    # one-shot entry points take the same staged path
+    a, b = G.white(700000, seed=2), G.decaying_ir(5000)
+    assert G.rel_l2(conv.Convolve(a, b, ctx=ctx), oracle.convolve(a, b)) <= 1e-12
+    plan.Close()
+
+
+def test_partitioned_nan_stays_local(conv):
+    """a non-finite input sample must not leak through delay-line slots that do not belong to a firing
+    (0 * NaN through a padded tap).  Block transforms spread a NaN over the blocks that contain it (the reference's
+    per-partition FFTs do the same, partitioned.go:139-186), so the poisoned band is block granular: it must cover
+    [i0 + L, i0 + L + K) and stay within a few of the largest internal blocks (2048 samples) around it."""
+    K, L_ord = 40000, 7
+    h = G.decaying_ir(K)
+    n = 120000
+    x = G.white(n, seed=4)
+    i0 = 30000
+    x[i0] = np.nan
+    p = conv.NewPartitionedConvolution(h, L_ord, 13)
+    y = np.concatenate([p.ProcessBlock(x[a:a + 8192]) for a in range(0, n, 8192)])
+    lat = 1 << L_ord
+    bad = np.isnan(y)
+    assert bad[i0 + lat: i0 + lat + K].all()
+    assert not bad[: i0 + lat - 4096].any() and not bad[i0 + lat + K + 8192:].any()
