@@ -36,6 +36,24 @@ PROTOTYPES = {
     "adsp_ctx_host_profile_get": (C.c_int, [c_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "adsp_host_ptr_is_pinned": (C.c_int, [c_vp]),
     "adsp_ctx_stage_threads": (C.c_int, [c_vp]),
+    "adsp_ctx_measure_pipes": (C.c_int, [c_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "adsp_ctx_copy_ceiling": (C.c_int, [c_vp, C.c_size_t, C.c_size_t, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "adsp_gen_uniform_device": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, C.c_int]),
+    "adsp_gen_white_device": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, C.c_double, c_i64, c_i64, c_i64, C.c_int]),
+    "adsp_gen_pink_device": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, C.c_double, c_i64, c_i64, c_i64, C.c_int]),
+    "adsp_gen_decaying_ir_device": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, C.c_double, c_i64, c_i64, C.c_int]),
+    "adsp_gen_linear_sweep_device": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]),
+    "adsp_gen_log_sweep_device": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]),
+    "adsp_gen_delay_mix_device": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, C.c_double, c_i64, c_i64, c_i64, c_i64, c_vp, C.c_int]),
+    "adsp_normalize_device": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, C.c_double, c_vp, c_i64, C.c_int]),
+    "adsp_remove_dc_device": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, C.c_int]),
+    "adsp_gen_uniform_host": (None, [c_vp, c_i64, c_i64, c_i64]),
+    "adsp_gen_white_host": (None, [c_vp, c_i64, C.c_double, c_i64, c_i64]),
+    "adsp_gen_pink_host": (None, [c_vp, c_i64, C.c_double, c_i64, c_i64]),
+    "adsp_gen_decaying_ir_host": (None, [c_vp, c_i64, C.c_double, c_i64]),
+    "adsp_gen_linear_sweep_host": (None, [c_vp, c_i64, c_i64, c_i64, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "adsp_gen_log_sweep_host": (None, [c_vp, c_i64, c_i64, c_i64, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "adsp_gen_delay_host": (c_i64, [c_i64, c_i64, c_i64]),
     "adsp_host_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(c_vp)]),
     "adsp_host_free_pinned": (None, [c_vp]),
     "adsp_device_alloc": (C.c_int, [c_vp, C.c_size_t, C.POINTER(c_vp)]),

@@ -72,6 +72,14 @@ ADSP_API uint64_t adsp_ctx_launch_count(adsp_ctx *ctx);
  * time and launch count of `kind`, and clears the accumulators when reset != 0. */
 ADSP_API void adsp_ctx_kernel_timing(adsp_ctx *ctx, int enable);
 ADSP_API adsp_status adsp_ctx_kernel_time(adsp_ctx *ctx, int kind, double *total_ms, uint64_t *launches, int reset);
+/* Run-time peaks the bench reports its rooflines against (csrc/diag.cu; not part of the data path): FP64 FMA
+ * thread-instructions per second and shared-memory bytes per second (128-bit stores + loads) over the whole GPU at the
+ * current clock -- the two per-SM resources that bound the fp64 FFT kernels before HBM does. */
+ADSP_API adsp_status adsp_ctx_measure_pipes(adsp_ctx *ctx, double *dfma_per_s, double *smem_bytes_per_s);
+/* Raw host-link ceiling: `reps` rounds of one H2D copy (h2d_bytes) and one D2H copy (d2h_bytes) from/to pinned memory,
+ * concurrently on two streams (ms_per_round), and each direction alone.  Bounds every host-buffer (end-to-end) figure. */
+ADSP_API adsp_status adsp_ctx_copy_ceiling(adsp_ctx *ctx, size_t h2d_bytes, size_t d2h_bytes, int reps, double *ms_per_round,
+                                           double *h2d_alone_ms, double *d2h_alone_ms);
 /* Raw cudaStream_t of the context's main stream (for event timing by a harness). */
 ADSP_API void *adsp_ctx_stream(adsp_ctx *ctx);
 
@@ -209,6 +217,49 @@ ADSP_API double adsp_snr(const double *original, int64_t n, const double *recove
 ADSP_API adsp_status adsp_deconvolve_batch_device(adsp_ctx *, const double *signal_dev, int64_t n, int64_t s_stride,
                                                   const double *kernel_dev, int64_t m, int64_t k_stride, int64_t batch,
                                                   double reg, double *out_dev, int64_t out_stride);
+
+/* ---------------------------------------------------------------- dsp/signal generators on the device
+ * The step BEFORE the path: inputs are generated in HBM (csrc/siggen.cu).  Formulas of dsp/signal/generate.go --
+ * WhiteNoise :188, PinkNoise :210 (Voss-McCartney, tables :220-221), LinearSweep :134, LogSweep :157, Normalize :253,
+ * RemoveDC :306 -- on uniforms from a STATELESS hash of (seed, stream, index) instead of Go's math/rand (whose seeding
+ * table is not in the tree): sample i depends only on (seed, i), so any shard of a stream can be produced anywhere
+ * (index0 = first stream index of this call).  Row r of a batch uses seed0 + r * seed_step.  out: DEVICE pointer, `rows`
+ * rows of n samples, stride in elements; asynchronous on the context stream.  The *_host twins run the same arithmetic
+ * (csrc/siggen_core.h) on the CPU and are bit-identical to the fp64 device output -- for feeding a CPU reference the
+ * very same signal.  Errors mirror the reference's argument checks (ADSP_ERR_INVALID_ARG + text). */
+ADSP_API adsp_status adsp_gen_uniform_device(adsp_ctx *, void *out, int64_t n, int64_t rows, int64_t stride, int64_t seed0,
+                                             int64_t seed_step, int64_t index0, adsp_precision prec);
+ADSP_API adsp_status adsp_gen_white_device(adsp_ctx *, void *out, int64_t n, int64_t rows, int64_t stride, double amplitude,
+                                           int64_t seed0, int64_t seed_step, int64_t index0, adsp_precision prec);
+ADSP_API adsp_status adsp_gen_pink_device(adsp_ctx *, void *out, int64_t n, int64_t rows, int64_t stride, double amplitude,
+                                          int64_t seed0, int64_t seed_step, int64_t index0, adsp_precision prec);
+/* synthetic decaying IR of SURVEY 8d: h[i] = (u_i*2-1) * 10^(-decades*i/taps)  (decades = 3: -60 dB at the last tap) */
+ADSP_API adsp_status adsp_gen_decaying_ir_device(adsp_ctx *, void *out, int64_t taps, int64_t rows, int64_t stride, double decades,
+                                                 int64_t seed0, int64_t seed_step, adsp_precision prec);
+/* samples [index0, index0+n) of a sweep that is total_samples long */
+ADSP_API adsp_status adsp_gen_linear_sweep_device(adsp_ctx *, void *out, int64_t n, int64_t index0, int64_t total_samples,
+                                                  double start_hz, double end_hz, double amplitude, double sample_rate, adsp_precision prec);
+ADSP_API adsp_status adsp_gen_log_sweep_device(adsp_ctx *, void *out, int64_t n, int64_t index0, int64_t total_samples,
+                                               double start_hz, double end_hz, double amplitude, double sample_rate, adsp_precision prec);
+/* config 4 responses: out[r][i] = (i >= d_r ? src[i-d_r] : 0) + white(seed0 + r*seed_step)[i] * noise_amplitude,
+ * d_r = adsp_gen_delay_host(delay_seed, r, delay_mod); delays_dev (nullable) receives d_r as int64. rows <= 65535. */
+ADSP_API adsp_status adsp_gen_delay_mix_device(adsp_ctx *, void *out, int64_t n, int64_t rows, int64_t stride, const void *src_dev,
+                                               double noise_amplitude, int64_t seed0, int64_t seed_step, int64_t delay_seed,
+                                               int64_t delay_mod, int64_t *delays_dev, adsp_precision prec);
+/* Normalize(data, targetPeak) generate.go:253 / RemoveDC(data) :306, row-wise on device data (rows <= 65535). */
+ADSP_API adsp_status adsp_normalize_device(adsp_ctx *, const void *in_dev, int64_t n, int64_t rows, int64_t in_stride, double target_peak,
+                                           void *out_dev, int64_t out_stride, adsp_precision prec);
+ADSP_API adsp_status adsp_remove_dc_device(adsp_ctx *, const void *in_dev, int64_t n, int64_t rows, int64_t in_stride, void *out_dev,
+                                           int64_t out_stride, adsp_precision prec);
+ADSP_API void adsp_gen_uniform_host(double *out, int64_t n, int64_t seed, int64_t index0);
+ADSP_API void adsp_gen_white_host(double *out, int64_t n, double amplitude, int64_t seed, int64_t index0);
+ADSP_API void adsp_gen_pink_host(double *out, int64_t n, double amplitude, int64_t seed, int64_t index0);
+ADSP_API void adsp_gen_decaying_ir_host(double *out, int64_t taps, double decades, int64_t seed);
+ADSP_API void adsp_gen_linear_sweep_host(double *out, int64_t n, int64_t index0, int64_t total_samples, double start_hz, double end_hz,
+                                         double amplitude, double sample_rate);
+ADSP_API void adsp_gen_log_sweep_host(double *out, int64_t n, int64_t index0, int64_t total_samples, double start_hz, double end_hz,
+                                      double amplitude, double sample_rate);
+ADSP_API int64_t adsp_gen_delay_host(int64_t delay_seed, int64_t row, int64_t delay_mod);
 
 /* ---------------------------------------------------------------- partitioned (long IR, streaming)
  * NewPartitionedConvolution(kernel, minBlockOrder, maxBlockOrder) partitioned.go:212,335.
