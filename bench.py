@@ -13,7 +13,11 @@ with no collective (weak scaling: 256 channels per GPU).
 
 Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM, CUDA-event timed on the
 library's stream.  `e2e`: the same metric through the host-buffer C-ABI call
-(adsp_plan_process_batch) with pinned host buffers, H2D and D2H inside the timed region.
+(adsp_plan_process_batch) with pinned host buffers, H2D and D2H inside the timed region; `e2e.pageable` is the same call
+on ordinary pageable numpy memory (what a Go []float64 caller passes: staged through the library's pinned slots), and
+`e2e.copy_ceiling` the raw concurrent H2D+D2H cudaMemcpyAsync time of the same byte counts.  `sustained` repeats the
+timed loop for >= 2 s with the clock/power sampler on.  `roofline.fp64` / `roofline.lsu` put the step against the FP64
+and shared-memory pipe peaks measured in the same run (adsp_ctx_measure_pipes).
 `--impl reference` times the CPU restatement of the reference (oracle/, all host threads) on a
 bounded sample of the same workload.
 """
@@ -56,6 +60,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index = index
         self.samples = []
+        self.power = []
         self.reasons = set()
         self.max_mhz = None
         self._stop = threading.Event()
@@ -63,7 +68,7 @@ class ClockSampler(threading.Thread):
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -80,6 +85,7 @@ class ClockSampler(threading.Thread):
                 for nm, v in zip(names, parts[2:6]):
                     if v.lower().startswith("active"):
                         self.reasons.add(nm)
+                self.power.append(float(parts[6]))
             except Exception:
                 pass
 
@@ -88,9 +94,15 @@ class ClockSampler(threading.Thread):
         if self.proc:
             self.proc.terminate()
 
-    def summary(self):
-        s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+    def mark(self):
+        """index of the next sample (to summarise a window of the run)"""
+        return len(self.samples), len(self.power)
+
+    def summary(self, since=(0, 0)):
+        s = sorted(self.samples[since[0]:])
+        pw = self.power[since[1]:]
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s),
+                "power_w_max": max(pw) if pw else None}
 
 
 def dist_env():
@@ -168,23 +180,41 @@ def other_configs(torch, conv, G, ctx, stream):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / iters
 
+    def gen_white(rows, n, seed0):
+        t = torch.empty((rows, n), device="cuda", dtype=torch.float64)
+        G.white_device(ctx, t.data_ptr(), n, rows, n, amp=1.0, seed0=seed0, seed_step=1)
+        ctx.sync()                       # the generator runs on the library's stream, torch on its own
+        return t
+
     out = {}
     # config 1: mono 10 s @48 kHz, 96k taps -- latency of one Process (device resident, and through the host API)
     h = G.decaying_ir(K_TAPS)
     plan = conv.OverlapSave(h, 0, ctx=ctx)
-    x1 = torch.rand((1, N_SAMPLES), device="cuda", dtype=torch.float64) * 2 - 1
+    x1 = gen_white(1, N_SAMPLES, 1)
     y1 = torch.empty((1, OUT_LEN + 31), device="cuda", dtype=torch.float64)
     ms = timeit(lambda: plan.process_device(x1.data_ptr(), N_SAMPLES, 1, N_SAMPLES, y1.data_ptr(), OUT_LEN + 31), iters=20)
-    xh = x1[0].cpu().numpy()
-    t0 = time.perf_counter()
-    for _ in range(5):
+    xh = x1[0].cpu().numpy()            # pageable, like a Go []float64
+    for _ in range(3):
+        plan.Process(xh)                 # warm the host path: device buffers, pinned slots, copy threads
+    lat = []
+    for _ in range(15):
+        t0 = time.perf_counter()
         plan.Process(xh)
-    host_ms = (time.perf_counter() - t0) / 5 * 1e3
-    out["config1_mono_ols_96k"] = {"device_latency_ms": ms, "host_api_latency_ms": host_ms, "samples_per_s_device": OUT_LEN / ms * 1e3}
+        lat.append((time.perf_counter() - t0) * 1e3)
+    lat.sort()
+    ctx.host_profile(True)
+    plan.Process(xh)
+    breakdown = ctx.host_profile_get()
+    ctx.host_profile(False)
+    out["config1_mono_ols_96k"] = {"device_latency_ms": ms, "host_api_latency_ms": lat[len(lat) // 2], "host_api_latency_ms_min": lat[0],
+                                   "host_api_latency_ms_max": lat[-1], "host_api_calls": len(lat),
+                                   "host_api_breakdown_ms": {k: round(v, 4) for k, v in breakdown.items() if k.endswith("_ms")},
+                                   "host_api_note": "pageable numpy buffers through adsp_plan_process (Python wrapper included); breakdown phases are serialised by a sync each",
+                                   "samples_per_s_device": OUT_LEN / ms * 1e3}
     plan.Close()
     # config 2: direct 64-tap FIR (Convolve auto-select -> direct), 256 of the 1024 channels x 2^20
     ch, n, m = 256, 1 << 20, 64
-    x = torch.rand((ch, n), device="cuda", dtype=torch.float64) * 2 - 1
+    x = gen_white(ch, n, 1)
     k = torch.tensor(G.test_kernel(m), device="cuda")
     y = torch.empty((ch, n + m - 1), device="cuda", dtype=torch.float64)
     ms = timeit(lambda: lib.adsp_direct_batch_device(ctx.handle, x.data_ptr(), n, n, k.data_ptr(), m, 0, ch, y.data_ptr(), n + m - 1, 0))
@@ -193,7 +223,9 @@ def other_configs(torch, conv, G, ctx, stream):
     del x, y
     # config 3: long-IR reverb shape, 8 of the 64 channels x 14.4 M samples, 288k taps
     ch, n, K = 8, 14_400_000, 288_000
-    x = torch.rand((ch, n), device="cuda", dtype=torch.float64) * 2 - 1
+    x = torch.empty((ch, n), device="cuda", dtype=torch.float64)
+    G.pink_device(ctx, x.data_ptr(), n, ch, n, amp=1.0, seed0=100, seed_step=1)     # pink, seed 100 + channel
+    ctx.sync()
     ol = n + K - 1
     ostr = (ol + 31) // 32 * 32
     y = torch.empty((ch, ostr), device="cuda", dtype=torch.float64)
@@ -210,21 +242,21 @@ def other_configs(torch, conv, G, ctx, stream):
     rv.SetWetDry(0.3, 0.7)
     stream_res = {"channels": 64, "latency_samples": rv.Latency(), "internal_stages": rv.internal_stages()}
     for nblk in (8192, 128):
-        xb = torch.rand((64, nblk), device="cuda", dtype=torch.float64) * 2 - 1
+        xb = gen_white(64, nblk, 1)
         ms = timeit(lambda: lib.adsp_partitioned_process_in_place_batch_device(rv._h, C.c_void_p(xb.data_ptr()), nblk, nblk), iters=50)
         stream_res[f"block_{nblk}"] = {"ms_per_call": ms, "samples_per_s": 64 * nblk / ms * 1e3, "x_realtime_48k": nblk / 48000.0 / (ms * 1e-3)}
     out["config3_streaming_reverb_288k"] = stream_res
     rv.Close()
     # config 4: sweep/response correlation + peak lag, 16 of the 1024 pairs x 2^20
     pairs, n = 16, 1 << 20
-    sweep = G.log_sweep(n)
-    a = np.zeros((pairs, n))
-    delays = [(p * 131) % 4096 for p in range(pairs)]
-    for p in range(pairs):
-        a[p, delays[p]:] = sweep[: n - delays[p]]
-    a += np.random.default_rng(0).standard_normal(a.shape) * 0.01
-    A = torch.tensor(a, device="cuda")
-    B = torch.tensor(np.tile(sweep, (pairs, 1)), device="cuda")
+    # b_p = log sweep; a_p = b_p delayed by d_p = hash(p) mod 4096 + white at -40 dB (seed 1000 + p); all built in HBM
+    B1 = torch.empty((1, n), device="cuda", dtype=torch.float64)
+    G.log_sweep_device(ctx, B1.data_ptr(), n)
+    A = torch.empty((pairs, n), device="cuda", dtype=torch.float64)
+    G.delay_mix_device(ctx, A.data_ptr(), n, pairs, n, B1.data_ptr(), noise_amp=0.01, seed0=1000, delay_seed=0, delay_mod=4096)
+    ctx.sync()
+    delays = [G.delay_of(p) for p in range(pairs)]
+    B = B1.expand(pairs, n).contiguous()
     o = torch.empty((pairs, 2 * n - 1), device="cuda", dtype=torch.float64)
     pi = torch.empty(pairs, device="cuda", dtype=torch.int64)
     pv = torch.empty(pairs, device="cuda", dtype=torch.float64)
@@ -235,7 +267,7 @@ def other_configs(torch, conv, G, ctx, stream):
                                      "lags_exact": lags_ok, "ms": ms}
     # deconvolution: 16 problems x 2^20 samples, 4096-tap kernel, regularized spectral division, device resident
     probs, n, m = 16, 1 << 20, 4096
-    sig = torch.rand((probs, n), device="cuda", dtype=torch.float64) * 2 - 1
+    sig = gen_white(probs, n, 1)
     ker = torch.tensor(G.decaying_ir(m) + (np.arange(m) == 0) * 2.0, device="cuda")
     o = torch.empty((probs, n - m + 1), device="cuda", dtype=torch.float64)
     ms = timeit(lambda: lib.adsp_deconvolve_batch_device(ctx.handle, sig.data_ptr(), n, n, ker.data_ptr(), m, 0, probs, C.c_double(1e-6),
@@ -246,6 +278,7 @@ def other_configs(torch, conv, G, ctx, stream):
 
 
 def run_ours(args):
+    import ctypes as C
     import torch
     rank, local_rank, world = dist_env()
     if world > 1:
@@ -254,7 +287,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     else:
         dist = None
-    from algo_dsp_b200 import conv, siggen as G
+    from algo_dsp_b200 import _lib as L, conv, siggen as G
+    lib = L.load()
 
     dev = local_rank if world > 1 else 0
     torch.cuda.set_device(dev)
@@ -265,11 +299,11 @@ def run_ours(args):
     geom = plan.internal_geometry()
     geom["cover"] = plan.describe_cover(N_SAMPLES)   # the transforms one Process() actually runs
 
-    # synthetic white noise, (u*2-1), distinct per rank/channel; generated on the device for the
-    # HBM-resident leg, copied once to pinned host memory for the end-to-end leg
-    gen = torch.Generator(device="cuda")
-    gen.manual_seed(1 + rank)
-    x = torch.rand((channels, N_SAMPLES), device="cuda", dtype=torch.float64, generator=gen) * 2 - 1
+    # synthetic white noise (u*2-1), dsp/signal WhiteNoise on the library's hash PRNG, seed = 1 + global channel number,
+    # generated straight into HBM by the device generator (adsp_gen_white_device)
+    x = torch.empty((channels, N_SAMPLES), device="cuda", dtype=torch.float64)
+    G.white_device(ctx, x.data_ptr(), N_SAMPLES, channels, N_SAMPLES, amp=1.0, seed0=1 + rank * channels, seed_step=1)
+    ctx.sync()
     ostride = (OUT_LEN + 31) // 32 * 32
     y = torch.empty((channels, ostride), device="cuda", dtype=torch.float64)
     stream = torch.cuda.ExternalStream(ctx.stream())
@@ -304,6 +338,31 @@ def run_ours(args):
     barrier()
     ms_total = e0.elapsed_time(e1)
     launches = ctx.launch_count() - launches0
+    clocks_timed = sampler.summary() if sampler else None
+
+    # ---- sustained leg: the same step back to back for >= sustain_s seconds (clock / power sampler running)
+    sustained = None
+    if args.sustain_s > 0:
+        est = max(ms_total / args.steps, 1e-3)
+        chunk = max(int(100.0 / est), 1)               # ~0.1 s of steps between host checks
+        mark = sampler.mark() if sampler else (0, 0)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        nsteps, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < args.sustain_s:
+            for _ in range(chunk):
+                step()
+            nsteps += chunk
+            plan.sync()
+        s1.record(stream)
+        plan.sync()
+        barrier()
+        sus_ms = s0.elapsed_time(s1)
+        sustained = {"steps": nsteps, "seconds": sus_ms * 1e-3, "ms_per_step": sus_ms / nsteps}
+        if sampler:
+            cs = sampler.summary(mark)
+            sustained.update({"sm_mhz_median": cs["sm_mhz"], "power_w_max": cs["power_w_max"], "reasons": cs["reasons"]})
 
     # ---- per-kernel device time of the dominant kernel (same K steps, event pair per launch)
     ctx.kernel_timing(True)
@@ -329,19 +388,38 @@ def run_ours(args):
     os.environ.pop("ADSP_GROUP_PAIRS")
     ctx.kernel_timing(False)
 
-    # ---- end-to-end through the host-buffer C-ABI call, pinned host memory
+    # ---- pipe peaks of this GPU at this clock (FP64 FMA issue, shared-memory bandwidth)
+    dfma, smem = C.c_double(), C.c_double()
+    lib.adsp_ctx_measure_pipes(ctx.handle, C.byref(dfma), C.byref(smem))
+
+    # ---- end-to-end through the host-buffer C-ABI call: (a) pinned caller buffers, DMA in place; (b) pageable numpy
+    # buffers (a Go []float64), staged through the library's pinned slots by its copy threads
     e2e_channels = channels
+    h2d_bytes, d2h_bytes = e2e_channels * N_SAMPLES * 8, e2e_channels * OUT_LEN * 8
     xh = conv.pinned_empty((e2e_channels, N_SAMPLES))
     yh = conv.pinned_empty((e2e_channels, OUT_LEN))
     xh[:] = x[:e2e_channels].cpu().numpy()
-    for _ in range(2):
-        plan.ProcessBatch(xh, out=yh)
+
+    def e2e_leg(xin, yout):
+        for _ in range(2):
+            plan.ProcessBatch(xin, out=yout)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            plan.ProcessBatch(xin, out=yout)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / args.steps
+
+    e2e_s = e2e_leg(xh, yh)
+    xp = np.array(xh)                      # ordinary pageable memory
+    yp = np.empty((e2e_channels, OUT_LEN))
+    e2e_page_s = e2e_leg(xp, yp)
+    page_ok = bool(np.array_equal(yp[0], yh[0]) and np.array_equal(yp[-1], yh[-1]))
+    # raw ceiling of the host link for exactly these byte counts (all ranks at the same time)
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        plan.ProcessBatch(xh, out=yh)
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / args.steps
+    c_both, c_in, c_out = C.c_double(), C.c_double(), C.c_double()
+    lib.adsp_ctx_copy_ceiling(ctx.handle, h2d_bytes, d2h_bytes, 3, C.byref(c_both), C.byref(c_in), C.byref(c_out))
+    barrier()
     if sampler:
         sampler.stop()
 
@@ -357,18 +435,18 @@ def run_ours(args):
     chk = float(np.max(np.abs(y[0, :OUT_LEN].cpu().numpy() - yh[0])))
 
     ms_step = ms_total / args.steps
-    t = torch.tensor([ms_step, e2e_s * 1e3], device="cuda", dtype=torch.float64)
+    vals = [ms_step, e2e_s * 1e3, e2e_page_s * 1e3, c_both.value, c_in.value, c_out.value, sustained["ms_per_step"] if sustained else 0.0]
+    t = torch.tensor(vals, device="cuda", dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step, e2e_ms = float(t[0]), float(t[1])
+    ms_step, e2e_ms, e2e_page_ms, ceil_ms, ceil_in_ms, ceil_out_ms, sus_ms_step = (float(v) for v in t)
     total_samples = world * channels * OUT_LEN
     value = total_samples / (ms_step * 1e-3)
     e2e_value = world * e2e_channels * OUT_LEN / (e2e_ms * 1e-3)
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        # dominant kernel = the one with the largest exclusive device time (agrees with the ncu launch list:
-        # profiles/r01_launches_bench_k_summary.txt)
+        # dominant kernel = the one with the largest exclusive device time (agrees with the ncu launch list)
         kinds = ("rows", "cols_fwd", "cols_inv", "full", "fused")
         dom = max(kinds, key=lambda k: ktimes_excl[k][0])
         step_bytes = channels * OUT_LEN * ALGO_BYTES_PER_SAMPLE
@@ -383,23 +461,42 @@ def run_ours(args):
         ex_total = sum(v[0] for v in ktimes_excl.values())
         path_achieved = step_bytes / (ms_step * 1e-3) / 1e9
         kshare = {k: round(v[0], 3) for k, v in ktimes.items() if v[1]}
-        traffic, traffic_note = None, None
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            traffic = tr["fftconv_" + dom]["dram_bytes_per_launch"]
-            traffic_note = tr["source"]
-        except Exception:
-            pass
+        # DRAM traffic and instruction counts per step come from committed ncu captures of this same command (profiles/),
+        # not from this run: labelled as such
+        prof = {}
+        for name in ("r02_traffic.json", "r01_traffic.json"):
+            try:
+                prof = json.load(open(os.path.join(ROOT, "profiles", name)))
+                prof["file"] = "profiles/" + name
+                break
+            except Exception:
+                pass
+        traffic = (prof.get("fftconv_" + dom) or {}).get("dram_bytes_per_launch")
+        per_step_traffic = prof.get("per_step_total_bytes")
+        traffic_note = ("static: from the committed ncu capture " + prof.get("file", "") + " (" + str(prof.get("source", "")) + "), not measured in this run") if prof else None
         # The unit of work is a GROUP: one block pair through all three kernels (every output sample passes all of them, and
         # SURVEY 8d's 16 B per output sample -- one input read, one output written -- belongs to the whole path: the row kernel
         # itself touches only L2-resident scratch).  So the roofline line is the pipeline's: algorithmic bytes per step / step
         # time; the dominant member kernel is reported underneath, both exclusively timed and as launched in the schedule.
         groups_per_step = max(ktimes["rows"][1] // max(args.steps, 1), 1)
-        per_step_traffic = None
-        try:
-            per_step_traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["per_step_total_bytes"]
-        except Exception:
-            pass
+        # FP64 / LSU pipe rooflines: work per output sample (~150 FP64 instructions and ~3.5 shared-memory/LSU
+        # wavefronts of 128 B per complex point; a pair of channels shares N complex points per block) over the peaks
+        # measured a moment ago on this GPU
+        pts_per_sample = (geom["fft_n"] / 2.0) / OUT_LEN if geom.get("fft_n") else None
+        dp_per_pt = float(prof.get("fp64_instr_per_complex_point", 150.0))
+        wf_per_pt = float(prof.get("lsu_wavefronts_per_complex_point", 3.5))
+        fp64_roof = lsu_roof = None
+        if pts_per_sample and len(geom.get("cover", [])) == 1:
+            ips = dp_per_pt * pts_per_sample
+            fp64_roof = {"peak_dfma_per_s": dfma.value, "instr_per_sample": ips, "achieved_instr_per_s": ips * value / world,
+                         "frac": ips * value / world / dfma.value if dfma.value else None,
+                         "samples_per_s_at_peak": dfma.value / ips if ips else None,
+                         "source": "peak: adsp_ctx_measure_pipes in this run; instructions per point: " + ("ncu, " + prof["file"] if "fp64_instr_per_complex_point" in prof else "instruction count of the kernels (DESIGN.md 3)")}
+            bps = wf_per_pt * 128.0 * pts_per_sample
+            lsu_roof = {"peak_smem_bytes_per_s": smem.value, "wavefront_bytes_per_sample": bps, "achieved_bytes_per_s": bps * value / world,
+                        "frac": bps * value / world / smem.value if smem.value else None,
+                        "samples_per_s_at_peak": smem.value / bps if bps else None,
+                        "source": "peak: adsp_ctx_measure_pipes in this run (128-bit shared-memory stores + loads); wavefronts per point: " + ("ncu, " + prof["file"] if "lsu_wavefronts_per_complex_point" in prof else "DESIGN.md 3")}
         roof = {
             "bound": "hbm",
             "kernel": "fftconv four-step pipeline: cols_fwd -> rows -> cols_inv (one launch of each per group of block pairs); dominant member fftconv_" + dom,
@@ -409,6 +506,7 @@ def run_ours(args):
             "avg_launch_ms": ms_step / groups_per_step, "launches": int(groups_per_step * args.steps),
             "algorithmic_bytes_per_launch": step_bytes / groups_per_step,
             "note": "launch = one group (three kernels); groups of four streams overlap, so avg_launch_ms is step time / groups per step",
+            "fp64": fp64_roof, "lsu": lsu_roof,
             "dominant_kernel": {
                 "name": "fftconv_" + dom,
                 "exclusive": {"avg_launch_ms": ex_avg_ms, "launches": ex_n, "algorithmic_bytes_per_launch": ex_bytes,
@@ -422,32 +520,58 @@ def run_ours(args):
                                 "note": "event-bracketed launches of four concurrent groups share the GPU, so these durations overlap"},
             },
             "path_achieved": path_achieved, "path_frac": path_achieved / peak,
-            "co_bound": "shared-memory (LSU) pipe and fp64 pipe (DESIGN.md 3: 3.5 LSU wavefronts and ~150 DP instr per complex point); "
-                        "ncu steady state: LSU 69 % / fp64 pipe 49 % in fftconv_rows, 57-60 % / 40 % in the column kernels",
+            "co_bound": "shared-memory (LSU) pipe and fp64 pipe: see roofline.fp64 / roofline.lsu (peaks measured in this run)",
         }
+        if sustained:
+            sustained["value"] = world * channels * OUT_LEN / (sus_ms_step * 1e-3)
+            sustained["ms_per_step"] = sus_ms_step
+            sustained["frac_of_hbm_roofline"] = sustained["value"] / world * ALGO_BYTES_PER_SAMPLE / 1e9 / peak
         cpu_threads = os.cpu_count() or 1
         cpu_ch = max(4 * cpu_threads, 8)
-        cpu_v, cpu_t, cpu_passes = cpu_baseline(cpu_ch, cpu_threads) if world == 1 else (None, None, None)
+        cpu_v = cpu_1 = None
+        oracle_err = None
+        if world == 1:
+            cpu_v, cpu_t, cpu_passes = cpu_baseline(cpu_ch, cpu_threads)
+            cpu_1, cpu_1t, cpu_1p = cpu_baseline(2, 1, budget_s=6.0)
+            # the timed output against the CPU restatement of the reference (checker only): channel 0 of this rank
+            from oracle import oracle as O
+            ref0 = O.overlap_save(h, 0, xh[0])
+            oracle_err = float(np.linalg.norm(y[0, :OUT_LEN].cpu().numpy() - ref0) / np.linalg.norm(ref0))
+        ceil_value = world * e2e_channels * OUT_LEN / (ceil_ms * 1e-3) if ceil_ms > 0 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "ols96k_batch", "kernel_taps": K_TAPS, "signal_samples": N_SAMPLES, "channels_per_gpu": channels,
                        "output_samples_per_channel": OUT_LEN, "sharding": f"channel x{world}, no collective",
                        "internal_fft": geom, "l2_policy": "inputs (0.98 GB/GPU/step) exceed L2; no flush needed",
+                       "inputs": "dsp/signal WhiteNoise on the hash PRNG, generated on the device (adsp_gen_white_device), seed 1 + channel",
                        "reference_getters": {"FFTSize": plan.FFTSize(), "StepSize": plan.StepSize()}},
             "roofline": roof,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_channels * N_SAMPLES * 8,
-                    "d2h_bytes_per_step": e2e_channels * OUT_LEN * 8, "ms_per_step": e2e_ms,
-                    "api": "adsp_plan_process_batch (pinned host buffers, chunked H2D|compute|D2H pipeline)"},
+            "sustained": sustained,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms,
+                    "api": "adsp_plan_process_batch (pinned host buffers, chunked H2D|compute|D2H pipeline)",
+                    "pageable": {"value": world * e2e_channels * OUT_LEN / (e2e_page_ms * 1e-3), "ms_per_step": e2e_page_ms,
+                                 "frac_of_pinned": e2e_ms / e2e_page_ms, "outputs_equal_pinned_leg": page_ok, "stage_threads": ctx.stage_threads(),
+                                 "api": "same call on pageable numpy buffers (a Go []float64): stage-in | H2D | kernels | D2H | stage-out, "
+                                        "pinned slots and copy threads inside the library"},
+                    "copy_ceiling": {"ms_per_step": ceil_ms, "value": ceil_value, "h2d_alone_ms": ceil_in_ms, "d2h_alone_ms": ceil_out_ms,
+                                     "h2d_GBps_alone": h2d_bytes / ceil_in_ms / 1e6 if ceil_in_ms else None,
+                                     "d2h_GBps_alone": d2h_bytes / ceil_out_ms / 1e6 if ceil_out_ms else None,
+                                     "e2e_frac_of_ceiling": ceil_ms / e2e_ms if e2e_ms else None,
+                                     "what": "one cudaMemcpyAsync H2D + one D2H of the step's byte counts from/to pinned memory, concurrently, "
+                                             "every rank at the same time, max over ranks"}},
             "gpu_launches": launches,
-            "clocks": sampler.summary() if sampler else None,
+            "clocks": clocks_timed,
             "other_configs": other,
             "check_max_abs_diff_device_vs_host_path": chk,
+            "check_rel_l2_vs_cpu_oracle_channel0": oracle_err,
         }
         if cpu_v is not None:
             line["cpu_baseline"] = {"value": cpu_v, "unit": UNIT, "cores": cpu_threads, "kind": "port",
                                     "sample": f"{cpu_passes} passes over {cpu_ch} channels x {N_SAMPLES} samples x {K_TAPS} taps "
                                               f"({cpu_t:.1f} s wall in total, mean rate)",
+                                    "single_thread": {"value": cpu_1, "cores": 1,
+                                                      "sample": f"{cpu_1p} passes over 2 channels ({cpu_1t:.1f} s wall): the reference itself never spawns goroutines"},
                                     "note": "C restatement of the Go reference OverlapSave.Process (N=262144 complex FFT per block); "
                                             "the Go toolchain and algo-fft are absent here"}
         print(json.dumps(line), flush=True)
@@ -465,6 +589,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--channels", type=int, default=CHANNELS_PER_GPU)
     ap.add_argument("--skip-other", action="store_true", help="skip the auxiliary measurements of BASELINE configs 1-4")
+    ap.add_argument("--sustain-s", type=float, default=2.5, help="seconds of back-to-back steps for the `sustained` leg (0: skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
