@@ -33,7 +33,7 @@ PROTOTYPES = {
     "adsp_ctx_kernel_timing": (None, [c_vp, C.c_int]),
     "adsp_ctx_kernel_time": (C.c_int, [c_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]),
     "adsp_ctx_host_profile": (None, [c_vp, C.c_int]),
-    "adsp_ctx_host_profile_get": (C.c_int, [c_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "adsp_ctx_host_profile_get": (C.c_int, [c_vp, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "adsp_host_ptr_is_pinned": (C.c_int, [c_vp]),
     "adsp_ctx_stage_threads": (C.c_int, [c_vp]),
     "adsp_ctx_measure_pipes": (C.c_int, [c_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

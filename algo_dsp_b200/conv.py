@@ -121,10 +121,11 @@ class Context:
 
     def host_profile_get(self):
         """{alloc_ms, upload_ms, kernels_ms, download_ms, total_ms, staged_in_bytes, staged_out_bytes} of the last profiled call."""
-        ms = (C.c_double * 6)()
+        ms = (C.c_double * 12)()
         bi, bo = C.c_uint64(), C.c_uint64()
-        _check(L.load().adsp_ctx_host_profile_get(self._h, ms, C.byref(bi), C.byref(bo)))
+        _check(L.load().adsp_ctx_host_profile_get(self._h, ms, 12, C.byref(bi), C.byref(bo)))
         return {"alloc_ms": ms[0], "upload_ms": ms[1], "kernels_ms": ms[2], "download_ms": ms[3], "total_ms": ms[5],
+                "stage_in_copy_ms": ms[6], "d2h_wait_ms": ms[7], "stage_out_copy_ms": ms[8], "pointer_query_ms": ms[9],
                 "staged_in_bytes": int(bi.value), "staged_out_bytes": int(bo.value)}
 
     def stage_threads(self) -> int:

@@ -388,7 +388,12 @@ static adsp_status plan_run_host(adsp_plan *p, const T *in, long long n, long lo
     // device layout: dense rows padded to 32 elements so every channel starts 256-byte aligned
     const long long dis = ((n + 31) / 32) * 32, dos = ((out_len + 31) / 32) * 32;
     const size_t row_bytes = (size_t)(dis + dos) * sizeof(T);
+    const auto tq = std::chrono::steady_clock::now();
     const bool stage_in = !host_ptr_is_pinned(in), stage_out = !host_ptr_is_pinned(out);
+    if (ctx->host_profile) {
+        for (int i = 6; i < 12; i++) ctx->host_prof_ms[i] = 0;
+        ctx->host_prof_ms[9] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tq).count();
+    }
     const bool staged = stage_in || stage_out;
     // chunk size: 96 MB measured best for DMA straight from pinned caller memory (tools/e2e_sweep.py); staged chunks are
     // smaller so that the five stages fill sooner and the pinned slots stay modest (kPipeSlots x 2 x chunk)
@@ -449,7 +454,7 @@ static adsp_status plan_run_host(adsp_plan *p, const T *in, long long n, long lo
             // H2D (device slot free once the kernels that last read it are done)
             if (j >= NS) ADSP_CUDA(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_comp[s], 0));
             if (stage_in) {
-                StagePool::wait(tk_in[s]);
+                pool->wait(tk_in[s]);
                 ADSP_CUDA(cudaMemcpy2DAsync(ctx->pipe_in[s].p, (size_t)dis * sizeof(T), ctx->h_in[s].p, (size_t)n * sizeof(T), (size_t)n * sizeof(T),
                                             (size_t)nc, cudaMemcpyHostToDevice, ctx->copy_in));
             } else {
@@ -465,7 +470,7 @@ static adsp_status plan_run_host(adsp_plan *p, const T *in, long long n, long lo
             // D2H (pinned slot free once the pool has copied its previous contents out)
             ADSP_CUDA(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_comp[s], 0));
             if (stage_out) {
-                StagePool::wait(tk_out[s]);
+                pool->wait(tk_out[s]);
                 ADSP_CUDA(cudaMemcpy2DAsync(ctx->h_out[s].p, (size_t)out_len * sizeof(T), ctx->pipe_out[s].p, (size_t)dos * sizeof(T),
                                             (size_t)out_len * sizeof(T), (size_t)nc, cudaMemcpyDeviceToHost, ctx->copy_out));
             } else {
@@ -482,7 +487,7 @@ static adsp_status plan_run_host(adsp_plan *p, const T *in, long long n, long lo
                                            (size_t)out_len * sizeof(T), (size_t)chunk_nc(j));
         }
     }
-    for (int s = 0; s < NS; s++) StagePool::wait(tk_out[s]);
+    for (int s = 0; s < NS; s++) pool->wait(tk_out[s]);
     ADSP_CUDA(cudaStreamSynchronize(ctx->copy_out));
     ADSP_CUDA(cudaStreamSynchronize(ctx->main));
     return ADSP_OK;
@@ -626,10 +631,10 @@ void adsp_ctx_host_profile(adsp_ctx *c, int enable) {
     c->host_profile = enable != 0;
     for (double &v : c->host_prof_ms) v = 0;
 }
-adsp_status adsp_ctx_host_profile_get(adsp_ctx *c, double *ms6, uint64_t *staged_in_bytes, uint64_t *staged_out_bytes) {
+adsp_status adsp_ctx_host_profile_get(adsp_ctx *c, double *ms, int cap, uint64_t *staged_in_bytes, uint64_t *staged_out_bytes) {
     if (!c) return ADSP_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> lk(c->mu);
-    if (ms6) for (int i = 0; i < 6; i++) ms6[i] = c->host_prof_ms[i];
+    if (ms) for (int i = 0; i < cap && i < 12; i++) ms[i] = c->host_prof_ms[i];
     if (staged_in_bytes) *staged_in_bytes = c->staged_bytes_in;
     if (staged_out_bytes) *staged_out_bytes = c->staged_bytes_out;
     return ADSP_OK;

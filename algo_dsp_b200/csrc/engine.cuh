@@ -74,11 +74,12 @@ public:
     int threads() const { return (int)workers_.size(); }
     // copies `rows` rows of `width` bytes (row pitches in bytes), split into slices run by the pool; returns at once
     Ticket copy2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows);
-    static void wait(const Ticket &t);
+    void wait(const Ticket &t);          // the waiting thread helps: it runs queued slices until its job is done
     void copy2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows) { wait(copy2d_async(dst, dpitch, src, spitch, width, rows)); }
 private:
     struct Slice { char *dst; const char *src; size_t dpitch, spitch, width, rows; Ticket job; };
     void run();
+    static void exec(Slice &s);
     std::vector<std::thread> workers_;
     std::deque<Slice> q_;
     std::mutex m_;
@@ -125,7 +126,7 @@ struct adsp_ctx {
     std::unique_ptr<adsp::StagePool> pool;                               // copy threads (created on the first pageable call)
     // host-path profile (adsp_ctx_host_profile): ms of {stage-in, H2D, kernels, D2H, stage-out, total} of the last small call
     bool host_profile = false;
-    double host_prof_ms[6] = {0, 0, 0, 0, 0, 0};
+    double host_prof_ms[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // [6] stage-in copy, [7] wait for D2H, [8] stage-out copy, [9] pointer queries
     uint64_t staged_bytes_in = 0, staged_bytes_out = 0;                  // bytes that went through pinned staging (diagnostic)
     std::atomic<uint64_t> launches{0};
     size_t scratch_budget = 0;  // bytes of scratch allowed in flight (fits L2)

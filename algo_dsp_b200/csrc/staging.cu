@@ -6,6 +6,10 @@
 // memcpy thread moves ~10 GB/s, PCIe Gen5 x16 needs ~50 GB/s per direction) while the DMA engines and the SMs work on
 // the neighbouring chunks.  Memory that is already pinned/registered is DMA'd in place.
 #include <algorithm>
+#include <chrono>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include "engine.cuh"
 
@@ -26,6 +30,44 @@ StagePool::~StagePool() {
     for (auto &t : workers_) t.join();
 }
 
+// Bulk copy for staging.  Both directions stream: a pinned slot is written by the CPU and then read only by the DMA
+// engine, the caller's output is far larger than the caches -- so the stores bypass the cache (no read-for-ownership, a
+// third less DRAM traffic than memcpy's cached stores below its non-temporal threshold) when the CPU has AVX2.
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) static void stream_copy_avx2(char *dst, const char *src, size_t n) {
+    const size_t head = (32 - ((uintptr_t)dst & 31)) & 31;
+    if (head) { const size_t h = head < n ? head : n; memcpy(dst, src, h); dst += h; src += h; n -= h; }
+    size_t i = 0;
+    for (; i + 128 <= n; i += 128) {
+        const __m256i a = _mm256_loadu_si256((const __m256i *)(src + i)), b = _mm256_loadu_si256((const __m256i *)(src + i + 32));
+        const __m256i c = _mm256_loadu_si256((const __m256i *)(src + i + 64)), d = _mm256_loadu_si256((const __m256i *)(src + i + 96));
+        _mm256_stream_si256((__m256i *)(dst + i), a); _mm256_stream_si256((__m256i *)(dst + i + 32), b);
+        _mm256_stream_si256((__m256i *)(dst + i + 64), c); _mm256_stream_si256((__m256i *)(dst + i + 96), d);
+    }
+    for (; i + 32 <= n; i += 32) _mm256_stream_si256((__m256i *)(dst + i), _mm256_loadu_si256((const __m256i *)(src + i)));
+    _mm_sfence();
+    if (i < n) memcpy(dst + i, src + i, n - i);
+}
+static const bool g_use_stream_copy = __builtin_cpu_supports("avx2") && env_ll("ADSP_STAGE_NT", 1) != 0;
+#else
+static const bool g_use_stream_copy = false;
+static void stream_copy_avx2(char *, const char *, size_t) {}
+#endif
+
+static inline void bulk_copy(char *dst, const char *src, size_t n) {
+    if (g_use_stream_copy && n >= 4096) stream_copy_avx2(dst, src, n);
+    else memcpy(dst, src, n);
+}
+
+void StagePool::exec(Slice &s) {
+    if (s.dpitch == s.width && s.spitch == s.width) bulk_copy(s.dst, s.src, s.width * s.rows);
+    else for (size_t r = 0; r < s.rows; r++) bulk_copy(s.dst + r * s.dpitch, s.src + r * s.spitch, s.width);
+    if (s.job->remaining.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+        std::lock_guard<std::mutex> lk(s.job->m);
+        s.job->cv.notify_all();
+    }
+}
+
 void StagePool::run() {
     for (;;) {
         Slice s;
@@ -36,21 +78,16 @@ void StagePool::run() {
             s = std::move(q_.front());
             q_.pop_front();
         }
-        if (s.dpitch == s.width && s.spitch == s.width) memcpy(s.dst, s.src, s.width * s.rows);
-        else for (size_t r = 0; r < s.rows; r++) memcpy(s.dst + r * s.dpitch, s.src + r * s.spitch, s.width);
-        if (s.job->remaining.fetch_sub(1, std::memory_order_acq_rel) == 1) {
-            std::lock_guard<std::mutex> lk(s.job->m);
-            s.job->cv.notify_all();
-        }
+        exec(s);
     }
 }
 
 StagePool::Ticket StagePool::copy2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows) {
     Ticket job = std::make_shared<Job>();
     if (rows == 0 || width == 0) return job;
-    // slices of about 1 MiB (never more than 4 per worker per job, so that tiny copies do not pay for the queue)
+    // slices of about 256 KiB, at most 8 per worker per job (tiny copies must not pay for the queue, large ones balance)
     const size_t total = width * rows;
-    size_t nsl = std::min<size_t>((total + (1u << 20) - 1) >> 20, (size_t)workers_.size() * 4);
+    size_t nsl = std::min<size_t>((total + (256u << 10) - 1) >> 18, (size_t)workers_.size() * 8);
     if (nsl < 1) nsl = 1;
     std::vector<Slice> sl;
     if (rows >= nsl) {                       // split by rows
@@ -71,14 +108,26 @@ StagePool::Ticket StagePool::copy2d_async(void *dst, size_t dpitch, const void *
         std::lock_guard<std::mutex> lk(m_);
         for (auto &s : sl) q_.push_back(std::move(s));
     }
-    cv_.notify_all();
+    if (sl.size() >= workers_.size()) cv_.notify_all();
+    else for (size_t i = 0; i < sl.size(); i++) cv_.notify_one();
     return job;
 }
 
+// The waiting thread works too: it takes slices (of any job) off the queue until its own job is complete, so a small
+// copy does not depend on how fast the sleeping workers wake up.
 void StagePool::wait(const Ticket &t) {
     if (!t) return;
-    std::unique_lock<std::mutex> lk(t->m);
-    t->cv.wait(lk, [&] { return t->remaining.load(std::memory_order_acquire) <= 0; });
+    while (t->remaining.load(std::memory_order_acquire) > 0) {
+        Slice s;
+        bool have = false;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            if (!q_.empty()) { s = std::move(q_.front()); q_.pop_front(); have = true; }
+        }
+        if (have) { exec(s); continue; }
+        std::unique_lock<std::mutex> lk(t->m);
+        t->cv.wait(lk, [&] { return t->remaining.load(std::memory_order_acquire) <= 0; });
+    }
 }
 
 bool host_ptr_is_pinned(const void *p) {
@@ -91,7 +140,7 @@ StagePool *stage_pool(adsp_ctx *ctx) {
     if (!ctx->pool) {
         const unsigned hw = std::thread::hardware_concurrency();
         long long n = env_ll("ADSP_STAGE_THREADS", 0);
-        if (n <= 0) n = std::max(1u, std::min(8u, hw ? hw / 2 : 4u));
+        if (n <= 0) n = std::max(1u, std::min(12u, hw ? (hw * 3) / 4 : 4u));   // the calling thread copies too while it waits
         ctx->pool.reset(new StagePool((int)n));
     }
     return ctx->pool.get();
@@ -123,7 +172,9 @@ adsp_status upload2d(adsp_ctx *ctx, void *dst_dev, size_t dpitch, const void *sr
     auto send = [&](char *d, const char *h, size_t dp, size_t sp, size_t w, size_t r) -> adsp_status {
         const int s = i++ % kPipeSlots;
         ADSP_CUDA(cudaEventSynchronize(ctx->ev_in[s]));                  // the DMA that last read this slot is done
+        const auto c0 = std::chrono::steady_clock::now();
         pool->copy2d(ctx->h_in[s].p, w, h, sp, w, r);                    // user memory -> pinned slot (dense rows)
+        if (ctx->host_profile) ctx->host_prof_ms[6] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - c0).count();
         if (r == 1) ADSP_CUDA(cudaMemcpyAsync(d, ctx->h_in[s].p, w, cudaMemcpyHostToDevice, ctx->main));
         else ADSP_CUDA(cudaMemcpy2DAsync(d, dp, ctx->h_in[s].p, w, w, r, cudaMemcpyHostToDevice, ctx->main));
         ADSP_CUDA(cudaEventRecord(ctx->ev_in[s], ctx->main));
@@ -170,7 +221,7 @@ adsp_status download2d(adsp_ctx *ctx, void *dst_host, size_t dpitch, const void 
     for (size_t i = 0; i <= np; i++) {
         if (i < np) {
             const int s = (int)(i % kPipeSlots);
-            StagePool::wait(tk[s]);                                      // the host copy that last read this slot is done
+            pool->wait(tk[s]);                                      // the host copy that last read this slot is done
             const Piece &pc = pieces[i];
             if (pc.r == 1) ADSP_CUDA(cudaMemcpyAsync(ctx->h_out[s].p, pc.d, pc.w, cudaMemcpyDeviceToHost, ctx->main));
             else ADSP_CUDA(cudaMemcpy2DAsync(ctx->h_out[s].p, pc.w, pc.d, pc.dp, pc.w, pc.r, cudaMemcpyDeviceToHost, ctx->main));
@@ -179,12 +230,16 @@ adsp_status download2d(adsp_ctx *ctx, void *dst_host, size_t dpitch, const void 
         if (i >= 1) {
             const size_t j = i - 1;
             const int s = (int)(j % kPipeSlots);
+            const auto c0 = std::chrono::steady_clock::now();
             ADSP_CUDA(cudaEventSynchronize(ctx->ev_out[s]));
+            if (ctx->host_profile) ctx->host_prof_ms[7] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - c0).count();
             const Piece &pc = pieces[j];
             tk[s] = pool->copy2d_async(pc.h, pc.r == 1 ? pc.w : pc.hp, ctx->h_out[s].p, pc.w, pc.w, pc.r);
         }
     }
-    for (int s = 0; s < kPipeSlots; s++) StagePool::wait(tk[s]);
+    const auto c1 = std::chrono::steady_clock::now();
+    for (int s = 0; s < kPipeSlots; s++) pool->wait(tk[s]);
+    if (ctx->host_profile) ctx->host_prof_ms[8] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - c1).count();
     return ADSP_OK;
 }
 

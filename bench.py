@@ -482,7 +482,8 @@ def run_ours(args):
         # FP64 / LSU pipe rooflines: work per output sample (~150 FP64 instructions and ~3.5 shared-memory/LSU
         # wavefronts of 128 B per complex point; a pair of channels shares N complex points per block) over the peaks
         # measured a moment ago on this GPU
-        pts_per_sample = (geom["fft_n"] / 2.0) / OUT_LEN if geom.get("fft_n") else None
+        cover = geom.get("cover") or []
+        pts_per_sample = (cover[0]["fft_n"] / 2.0) / OUT_LEN if len(cover) == 1 else None   # one block per channel, two channels per transform
         dp_per_pt = float(prof.get("fp64_instr_per_complex_point", 150.0))
         wf_per_pt = float(prof.get("lsu_wavefronts_per_complex_point", 3.5))
         fp64_roof = lsu_roof = None

@@ -88,10 +88,12 @@ ADSP_API void *adsp_ctx_stream(adsp_ctx *ctx);
  * (ADSP_STAGE_THREADS, default min(8, cores/2)), overlapped with H2D | kernels | D2H (csrc/staging.cu).  Memory from
  * adsp_host_alloc_pinned (or cudaHostRegister'ed by the caller) is DMA'd in place, which saves the two host copies.
  * adsp_ctx_host_profile(ctx, 1) makes the small-call path (one upload, kernels, one download) record a breakdown of the
- * last call: ms6 = {device allocation, upload (stage-in + H2D), kernels, download (D2H + stage-out), 0, total}; the
- * phases are serialised by a stream sync each while profiling is on.  staged_*_bytes count what went through staging. */
+ * last call: ms[0..5] = {device allocation, upload (stage-in + H2D), kernels, download (D2H + stage-out), 0, total},
+ * ms[6..9] = {host copy into the pinned slots, wait for the D2H, host copy out of the pinned slots, pointer-type queries};
+ * the phases are serialised by a stream sync each while profiling is on (up to `cap` <= 12 values are written).
+ * staged_*_bytes count what went through staging since the context was created. */
 ADSP_API void adsp_ctx_host_profile(adsp_ctx *ctx, int enable);
-ADSP_API adsp_status adsp_ctx_host_profile_get(adsp_ctx *ctx, double *ms6, uint64_t *staged_in_bytes, uint64_t *staged_out_bytes);
+ADSP_API adsp_status adsp_ctx_host_profile_get(adsp_ctx *ctx, double *ms, int cap, uint64_t *staged_in_bytes, uint64_t *staged_out_bytes);
 ADSP_API int adsp_host_ptr_is_pinned(const void *p);     /* 1: DMA-able in place, 0: pageable (will be staged) */
 ADSP_API int adsp_ctx_stage_threads(adsp_ctx *ctx);      /* size of the context's copy-thread pool (creates it) */
 
