@@ -20,6 +20,7 @@
 #include "../../include/algodsp_cuda.h"
 #include "conv_kernels.cuh"
 #include "conv_kernels_mr.cuh"
+#include "conv_kernels_mrp.cuh"
 #if ADSP_EXPERIMENTAL
 // measured-slower variants kept for the record: prefetching persistent kernels, interleaved rows
 #include "conv_kernels_pf.cuh"

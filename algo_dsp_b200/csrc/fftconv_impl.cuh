@@ -151,6 +151,11 @@ struct AttrOnce {
     bool need(int dev) { if (dev < 0 || dev >= 64) return true; if (done[dev]) return false; done[dev] = true; return true; }
 };
 
+struct OccPerDev {
+    int v[64] = {};
+    int *at(int dev) { return &v[(dev >= 0 && dev < 64) ? dev : 0]; }
+};
+
 template <typename T, int L, bool SPEC>
 static adsp_status launch_full_t(adsp_ctx *ctx, cudaStream_t st, const ConvGeom &g, const T *x, T *y, const cpx<T> *H,
                                  cpx<T> *spec, T scale, const cpx<T> *tw, long long npairs) {
@@ -255,12 +260,98 @@ static adsp_status launch_cols(adsp_ctx *ctx, cudaStream_t st, int N1, bool inve
 }
 
 // ------------------------------------------------------------------ mixed-radix columns (N1 = 16*P)
+// Tensor maps of one FftConv::run call for the persistent TMA-fed column kernels (conv_kernels_mrp.cuh); built on the
+// host per call (the input pointer is the caller's) and per scratch slot.  fwd_ok / inv_ok say which side may use them.
+struct MrpLaunch {
+    bool fwd_ok = false, inv_ok = false;
+    int r_part = -1;                 // row of the N1 x N2 view the signal ends in (-1: it ends on a row boundary)
+    int box_rows = 0, nbox = 0;      // forward: nbox boxes of box_rows signal rows per real block
+    CUtensorMap main, part;          // input: (columns, full rows, channels) and the narrower (n mod N2, 1, channels)
+    CUtensorMap scr;                 // scratch slot: (2*N2 reals, N1 rows x pairs)
+};
+
+template <typename T>
+static void mrp_build_input_maps(MrpLaunch *m, const FftChoice &ch, const ConvGeom &g, const T *x, long long channels) {
+    m->fwd_ok = false;
+    // ADSP_MRP: 0 (default) plain kernels, 1 both persistent TMA-fed kernels, 2 forward only, 3 inverse only.  Off by default:
+    // alone on the GPU the TMA-fed forward kernel is 11 % faster than the plain one (0.404 vs 0.453 ms per step), but in the
+    // real schedule -- one block pair per launch on four streams, so that the intermediates stay in L2 -- a launch has
+    // fewer tiles (256) than the machine has CTA slots (444), nothing is left to prefetch, and the step is 6-11 % slower in
+    // every streams x group x tiles-per-CTA setting tried (profiles/r02_i_mrp_schedule_sweep.log, r02_h_mrp_v3_ab.log).
+    static const bool use_mrp = env_ll("ADSP_MRP", 0) == 1 || env_ll("ADSP_MRP", 0) == 2;
+    if (!use_mrp || ch.P <= 1 || g.D != 0 || g.nblk != 1 || g.in_shift != 0 || g.n > ch.N) return;   // single zero-padded block plans only
+    const long long rows_full = g.n / ch.N2, rem = g.n % ch.N2;
+    if (rows_full < 1 || channels < 1) return;
+    const int TC = ADSP_MR_TC;
+    const bool f64 = sizeof(T) == 8;
+    // only the rows that hold signal are staged: one box of up to 256 rows, two beyond that
+    // (box heights in multiples of 128 bytes of shared memory: a TMA tile destination must be 128-byte aligned)
+    const int nbox = rows_full > 256 ? 2 : 1;
+    const int ralign = 128 / (TC * (int)sizeof(T));
+    const int BR = (int)(((rows_full + nbox - 1) / nbox + ralign - 1) / ralign * ralign);
+    m->box_rows = BR; m->nbox = nbox;
+    const uint64_t dims[3] = {(uint64_t)ch.N2, (uint64_t)rows_full, (uint64_t)channels};
+    const uint64_t strides[2] = {(uint64_t)ch.N2 * sizeof(T), (uint64_t)g.in_stride * sizeof(T)};
+    const uint32_t box[3] = {(uint32_t)TC, (uint32_t)BR, 1};
+    if (!tma_encode(&m->main, f64, 3, x, dims, strides, box)) return;
+    m->r_part = -1;
+    if (rem > 0) {
+        const uint64_t pd[3] = {(uint64_t)rem, 1, (uint64_t)channels};
+        const uint32_t pb[3] = {(uint32_t)TC, 1, 1};
+        if (!tma_encode(&m->part, f64, 3, x + rows_full * ch.N2, pd, strides, pb)) return;
+        m->r_part = (int)rows_full;
+    } else m->part = m->main;
+    m->fwd_ok = true;
+}
+
+template <typename T>
+static void mrp_build_scratch_map(MrpLaunch *m, const FftChoice &ch, const cpx<T> *slot, long long pairs) {
+    m->inv_ok = false;
+    static const bool use_mrp = env_ll("ADSP_MRP", 0) == 1 || env_ll("ADSP_MRP", 0) == 3;
+    if (!use_mrp || ch.P <= 1 || pairs < 1) return;
+    const int TC = ADSP_MR_TC, BR = ch.N1 <= 256 ? ch.N1 : ch.N1 / 2;
+    const uint64_t dims[2] = {(uint64_t)ch.N2 * 2, (uint64_t)ch.N1 * (uint64_t)pairs};
+    const uint64_t strides[1] = {(uint64_t)ch.N2 * sizeof(cpx<T>)};
+    const uint32_t box[2] = {(uint32_t)TC * 2, (uint32_t)BR};
+    m->inv_ok = tma_encode(&m->scr, sizeof(T) == 8, 2, slot, dims, strides, box);
+}
+
 template <typename T, int P>
 static adsp_status launch_cols_mr_t(adsp_ctx *ctx, cudaStream_t st, bool inverse, const ConvGeom &g, const T *x, T *y,
                                     cpx<T> *scratch, int N2, long long N, const cpx<T> *tw, const cpx<T> *hi, const cpx<T> *lo,
-                                    long long pair0, int pairs) {
+                                    long long pair0, int pairs, const MrpLaunch *mrp) {
     using CS = ColShapeMR<P>;
     const int ntiles = (N2 / CS::TC) * pairs;
+    // persistent TMA-fed kernels (conv_kernels_mrp.cuh) where the call has tensor maps for them (opt-in: ADSP_MRP=1)
+    if (mrp && (inverse ? mrp->inv_ok : mrp->fwd_ok)) {
+        using PS = ColShapeMRP<T, P>;
+        static AttrOnce once_p;
+        if (once_p.need(ctx->device)) {
+            ADSP_TRY(set_smem(fftconv_cols_fwd_mrp<T, P>, PS::smem_fwd(PS::N1)));
+            ADSP_TRY(set_smem(fftconv_cols_inv_mrp<T, P>, PS::SMEM_INV));
+        }
+        const size_t smem_p = inverse ? PS::SMEM_INV : PS::smem_fwd(mrp->box_rows * mrp->nbox);
+        int per_sm = 0;   // resident CTAs for this shared-memory size (the forward stage depends on the signal length)
+        if (!inverse) ADSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fftconv_cols_fwd_mrp<T, P>, CS::THREADS, smem_p));
+        else ADSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fftconv_cols_inv_mrp<T, P>, CS::THREADS, smem_p));
+        if (per_sm < 1) { set_error("persistent column kernel does not fit on an SM"); return ADSP_ERR_CUDA; }
+        const long long cap = env_ll("ADSP_MRP_GRID_CTAS", 0);   // tuning: resident CTAs per SM to use
+        if (cap > 0 && cap < per_sm) per_sm = (int)cap;
+        int grid = (int)std::min<long long>((long long)per_sm * ctx->sm_count, ntiles);
+        // launches that do not fill the machine (one or two pairs per group in the multi-stream schedule): k tiles per CTA, so
+        // that every CTA still overlaps the copies of its next tile with the current one
+        const long long k = env_ll("ADSP_MRP_TILES_PER_CTA", 2);
+        if (k > 0 && (long long)grid * k > ntiles) grid = (int)std::max<long long>(1, (ntiles + k - 1) / k);
+        LaunchTimer lt(ctx, st, inverse ? KK_COLS_INV : KK_COLS_FWD);
+        if (!inverse)
+            fftconv_cols_fwd_mrp<T, P><<<grid, CS::THREADS, smem_p, st>>>(mrp->main, mrp->part, mrp->r_part, mrp->box_rows, mrp->nbox, scratch, N2, (unsigned)N, tw,
+                                                                         hi, lo, pair0, ntiles);
+        else
+            fftconv_cols_inv_mrp<T, P><<<grid, CS::THREADS, smem_p, st>>>(g, mrp->scr, x, y, N2, (unsigned)N, tw, hi, lo, pair0, ntiles);
+        count_launch(ctx);
+        ADSP_CUDA(cudaGetLastError());
+        return ADSP_OK;
+    }
     const size_t smem = ((size_t)CS::SMEM_ELEMS + CS::TW_ENTRIES) * sizeof(cpx<T>);
     static AttrOnce once;
     if (once.need(ctx->device)) {
@@ -280,16 +371,16 @@ static adsp_status launch_cols_mr_t(adsp_ctx *ctx, cudaStream_t st, bool inverse
 template <typename T>
 static adsp_status launch_cols_mr(adsp_ctx *ctx, cudaStream_t st, int P, bool inverse, const ConvGeom &g, const T *x, T *y,
                                   cpx<T> *scratch, int N2, long long N, const cpx<T> *tw, const cpx<T> *hi, const cpx<T> *lo,
-                                  long long pair0, int pairs) {
+                                  long long pair0, int pairs, const MrpLaunch *mrp) {
     switch (P) {   // P here is M, the in-register DFT length (odd P, or 2P)
-    case 6: return launch_cols_mr_t<T, 6>(ctx, st, inverse, g, x, y, scratch, N2, N, tw, hi, lo, pair0, pairs);
-    case 10: return launch_cols_mr_t<T, 10>(ctx, st, inverse, g, x, y, scratch, N2, N, tw, hi, lo, pair0, pairs);
-    case 14: return launch_cols_mr_t<T, 14>(ctx, st, inverse, g, x, y, scratch, N2, N, tw, hi, lo, pair0, pairs);
-    case 18: return launch_cols_mr_t<T, 18>(ctx, st, inverse, g, x, y, scratch, N2, N, tw, hi, lo, pair0, pairs);
-    case 3: return launch_cols_mr_t<T, 3>(ctx, st, inverse, g, x, y, scratch, N2, N, tw, hi, lo, pair0, pairs);
-    case 5: return launch_cols_mr_t<T, 5>(ctx, st, inverse, g, x, y, scratch, N2, N, tw, hi, lo, pair0, pairs);
-    case 7: return launch_cols_mr_t<T, 7>(ctx, st, inverse, g, x, y, scratch, N2, N, tw, hi, lo, pair0, pairs);
-    case 9: return launch_cols_mr_t<T, 9>(ctx, st, inverse, g, x, y, scratch, N2, N, tw, hi, lo, pair0, pairs);
+    case 6: return launch_cols_mr_t<T, 6>(ctx, st, inverse, g, x, y, scratch, N2, N, tw, hi, lo, pair0, pairs, mrp);
+    case 10: return launch_cols_mr_t<T, 10>(ctx, st, inverse, g, x, y, scratch, N2, N, tw, hi, lo, pair0, pairs, mrp);
+    case 14: return launch_cols_mr_t<T, 14>(ctx, st, inverse, g, x, y, scratch, N2, N, tw, hi, lo, pair0, pairs, mrp);
+    case 18: return launch_cols_mr_t<T, 18>(ctx, st, inverse, g, x, y, scratch, N2, N, tw, hi, lo, pair0, pairs, mrp);
+    case 3: return launch_cols_mr_t<T, 3>(ctx, st, inverse, g, x, y, scratch, N2, N, tw, hi, lo, pair0, pairs, mrp);
+    case 5: return launch_cols_mr_t<T, 5>(ctx, st, inverse, g, x, y, scratch, N2, N, tw, hi, lo, pair0, pairs, mrp);
+    case 7: return launch_cols_mr_t<T, 7>(ctx, st, inverse, g, x, y, scratch, N2, N, tw, hi, lo, pair0, pairs, mrp);
+    case 9: return launch_cols_mr_t<T, 9>(ctx, st, inverse, g, x, y, scratch, N2, N, tw, hi, lo, pair0, pairs, mrp);
     default: set_error("unsupported odd column factor"); return ADSP_ERR_INVALID_ARG;
     }
 }
@@ -298,8 +389,8 @@ static adsp_status launch_cols_mr(adsp_ctx *ctx, cudaStream_t st, int P, bool in
 template <typename T>
 static adsp_status launch_cols_any(adsp_ctx *ctx, cudaStream_t st, const FftChoice &ch, bool inverse, const ConvGeom &g, const T *x,
                                    T *y, cpx<T> *scratch, const cpx<T> *tw, const cpx<T> *hi, const cpx<T> *lo, long long pair0,
-                                   int pairs) {
-    if (ch.P > 1) return launch_cols_mr<T>(ctx, st, ch.M, inverse, g, x, y, scratch, ch.N2, ch.N, tw, hi, lo, pair0, pairs);
+                                   int pairs, const MrpLaunch *mrp = nullptr) {
+    if (ch.P > 1) return launch_cols_mr<T>(ctx, st, ch.M, inverse, g, x, y, scratch, ch.N2, ch.N, tw, hi, lo, pair0, pairs, mrp);
     return launch_cols<T>(ctx, st, ch.N1, inverse, g, x, y, scratch, ch.N2, ch.lgN, tw, hi, lo, pair0, pairs);
 }
 
@@ -787,6 +878,16 @@ adsp_status FftConv<T>::run(const T *d_x, long long n, long long channels, long 
     ADSP_TRY(ctx->scratch.reserve((size_t)nslots * (size_t)G * per_pair));
     cpx<T> *scr = (cpx<T> *)ctx->scratch.p;
 
+    // tensor maps for the persistent TMA-fed column kernels (mixed-radix transforms): one pair over the caller's input,
+    // one per scratch slot
+    MrpLaunch mrp[kWorkerStreams];
+    if (ch.P > 1) {
+        mrp_build_input_maps<T>(&mrp[0], ch, g, d_x, channels);
+        for (int s = 0; s < nslots; s++) {
+            if (s > 0) { mrp[s] = mrp[0]; }
+            mrp_build_scratch_map<T>(&mrp[s], ch, scr + (size_t)s * (size_t)G * (size_t)ch.N, G);
+        }
+    }
     if (nslots > 1) {
         ADSP_CUDA(cudaEventRecord(ctx->ev_fork, ctx->main));
         for (int s = 0; s < nslots; s++) ADSP_CUDA(cudaStreamWaitEvent(ctx->worker[s], ctx->ev_fork, 0));
@@ -808,13 +909,13 @@ adsp_status FftConv<T>::run(const T *d_x, long long n, long long channels, long 
             continue;
         }
 #endif
-        ADSP_TRY(launch_cols_any<T>(ctx, st, ch, false, g, d_x, d_y, sl, tw_cols, tw_hi, tw_lo, pair0, gp));
+        ADSP_TRY(launch_cols_any<T>(ctx, st, ch, false, g, d_x, d_y, sl, tw_cols, tw_hi, tw_lo, pair0, gp, ch.P > 1 ? &mrp[slot] : nullptr));
 #if ADSP_EXPERIMENTAL
         if (use_il) ADSP_TRY(launch_rows_il<T>(ctx, st, ch.N2, sl, H, ch.N1, tw_rows, gp));
         else
 #endif
         ADSP_TRY((launch_rows<T, false>(ctx, st, ch.N2, sl, H, (cpx<T> *)nullptr, (T)0, ch.N1, tw_rows, gp)));
-        ADSP_TRY(launch_cols_any<T>(ctx, st, ch, true, g, d_x, d_y, sl, tw_cols, tw_hi, tw_lo, pair0, gp));
+        ADSP_TRY(launch_cols_any<T>(ctx, st, ch, true, g, d_x, d_y, sl, tw_cols, tw_hi, tw_lo, pair0, gp, ch.P > 1 ? &mrp[slot] : nullptr));
     }
     if (nslots > 1) {
         for (int s = 0; s < nslots; s++) {

@@ -12,8 +12,46 @@
 #endif
 
 #include "engine.cuh"
+#include "tma.cuh"
 
 namespace adsp {
+
+// ------------------------------------------------------------------ TMA tensor maps (tma.cuh)
+// cuTensorMapEncodeTiled lives in the driver library; it is looked up once through the runtime so that libalgodsp_cuda
+// needs no link-time dependency on libcuda.
+using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                   const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+        }
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+bool tma_encode(CUtensorMap *map, bool f64, int rank, const void *base, const uint64_t *dims, const uint64_t *strides_bytes, const uint32_t *box) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || rank < 1 || rank > 5) return false;
+    cuuint64_t d[5], s[5];
+    cuuint32_t b[5], es[5];
+    for (int i = 0; i < rank; i++) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; if (dims[i] == 0 || box[i] == 0 || box[i] > 256) return false; }
+    for (int i = 0; i + 1 < rank; i++) { s[i] = strides_bytes[i]; if (s[i] % 16 != 0) return false; }
+    if ((uintptr_t)base % 16 != 0) return false;
+    // L2 promotion: the granule the TMA unit requests from L2.  Without promotion it asks sector by sector (32 B), which
+    // caps a box of narrow rows at ~8 B/clk/SM on B200 (measured, profiles/r02_d_mrp_tensor_ab.log); 128-byte requests
+    // match the cache line.  ADSP_TMA_L2PROMO = 0 none, 1 64 B, 2 128 B (default), 3 256 B.
+    static const long long promo = env_ll("ADSP_TMA_L2PROMO", 2);
+    const CUtensorMapL2promotion pr = promo <= 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                      : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    const CUresult r = fn(map, f64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), d, s, b, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, pr, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
 
 // ------------------------------------------------------------------ copy-thread pool
 StagePool::StagePool(int nthreads) {

@@ -389,3 +389,37 @@ def test_one_process_many_plans_channel_and_time_sharding(conv, oracle):
     assert len(yl) == len(xl) + K - 1 and rel(yl, oracle.overlap_save(h, 0, xl)) <= TOL64
     short = G.white(50, seed=1)                          # fewer samples than shards * alignment: trailing plans idle
     assert rel(conv.ProcessLongMulti(plans, short), oracle.overlap_save(h, 0, short)) <= TOL64
+
+
+def test_tma_fed_persistent_column_kernels_parity():
+    """The opt-in persistent TMA-fed mixed-radix column kernels (ADSP_MRP=1, conv_kernels_mrp.cuh: cp.async.bulk.tensor tile
+    loads, mbarrier completion) give the same results as the default kernels and the oracle.  The switch is read once per
+    process, so the check runs in a subprocess."""
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np, sys
+sys.path.insert(0, %r)
+from algo_dsp_b200 import conv, siggen as G
+from oracle import oracle as O
+O.build()
+worst = 0.0
+# single zero-padded mixed-radix blocks: (K, n, channels) -> 9*2^16 (M=18), 3*2^12 .. (small M), odd channel count, signal
+# ending on / off a row boundary
+for K, n, ch in ((96000, 480000, 5), (3000, 17000, 3), (20000, 60000, 2), (9000, 2048 * 12, 4), (700, 11000, 1)):
+    h = G.decaying_ir(K)
+    x = np.stack([G.white(n, seed=10 + c) for c in range(ch)])
+    plan = conv.OverlapSave(h, 0)
+    y = plan.ProcessBatch(x)
+    for c in (0, ch - 1):
+        worst = max(worst, G.rel_l2(y[c], O.overlap_save(h, 0, x[c])))
+    y32 = conv.OverlapSave(h, 0, dtype=np.float32).ProcessBatch(x.astype(np.float32))
+    assert G.rel_l2(y32[0], O.overlap_save(h, 0, x[0])) <= 1e-5
+    print(K, n, ch, plan.describe_cover(n))
+print("WORST", worst)
+assert worst <= 1e-12
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, ADSP_MRP="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "WORST" in r.stdout
