@@ -54,6 +54,35 @@ PROTOTYPES = {
     "adsp_gen_linear_sweep_host": (None, [c_vp, c_i64, c_i64, c_i64, C.c_double, C.c_double, C.c_double, C.c_double]),
     "adsp_gen_log_sweep_host": (None, [c_vp, c_i64, c_i64, c_i64, C.c_double, C.c_double, C.c_double, C.c_double]),
     "adsp_gen_delay_host": (c_i64, [c_i64, c_i64, c_i64]),
+    "adsp_ir_schroeder_device": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64]),
+    "adsp_ir_find_impulse_start_device": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, C.c_double, c_vp]),
+    "adsp_ir_find_peak_device": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]),
+    "adsp_ir_schroeder": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),
+    "adsp_ir_find_impulse_start": (C.c_int, [c_vp, c_vp, c_i64, C.c_double, C.POINTER(c_i64)]),
+    "adsp_logsweep_samples": (c_i64, [C.c_double, C.c_double]),
+    "adsp_logsweep_generate_device": (C.c_int, [c_vp, c_vp, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "adsp_logsweep_inverse_filter_device": (C.c_int, [c_vp, c_vp, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "adsp_logsweep_generate_host": (C.c_int, [c_vp, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "adsp_logsweep_inverse_filter_host": (C.c_int, [c_vp, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "adsp_logsweep_deconvolve_device": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, C.c_double, C.c_double, C.c_double, C.c_double, c_vp, c_i64]),
+    "adsp_logsweep_deconvolve": (C.c_int, [c_vp, c_vp, c_i64, C.c_double, C.c_double, C.c_double, C.c_double, c_vp, c_i64]),
+    "adsp_fir_create": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, C.POINTER(c_vp)]),
+    "adsp_fir_process_block": (C.c_int, [c_vp, c_vp, c_i64, c_i64]),
+    "adsp_fir_process_block_device": (C.c_int, [c_vp, c_vp, c_i64, c_i64]),
+    "adsp_fir_order": (c_i64, [c_vp]),
+    "adsp_fir_reset": (None, [c_vp]),
+    "adsp_fir_destroy": (None, [c_vp]),
+    "adsp_resample_approximate_ratio": (None, [C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "adsp_resampler_create": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(c_vp)]),
+    "adsp_resampler_create_for_rates": (C.c_int, [c_vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(c_vp)]),
+    "adsp_resampler_ratio": (None, [c_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "adsp_resampler_taps_per_phase": (C.c_int, [c_vp]),
+    "adsp_resampler_prototype": (c_i64, [c_vp, c_vp, c_i64]),
+    "adsp_resampler_predict_output_len": (c_i64, [c_vp, c_i64]),
+    "adsp_resampler_process": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, C.POINTER(c_i64)]),
+    "adsp_resampler_process_device": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, C.POINTER(c_i64)]),
+    "adsp_resampler_reset": (None, [c_vp]),
+    "adsp_resampler_destroy": (None, [c_vp]),
     "adsp_host_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(c_vp)]),
     "adsp_host_free_pinned": (None, [c_vp]),
     "adsp_device_alloc": (C.c_int, [c_vp, C.c_size_t, C.POINTER(c_vp)]),

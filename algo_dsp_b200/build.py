@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libalgodsp_cuda.so")
-SOURCES = ["api.cu", "fftconv_f64.cu", "fftconv_f32.cu", "fdl.cu", "staging.cu", "siggen.cu", "diag.cu"]
+SOURCES = ["api.cu", "fftconv_f64.cu", "fftconv_f32.cu", "fdl.cu", "staging.cu", "siggen.cu", "diag.cu", "post.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off", "--expt-relaxed-constexpr",

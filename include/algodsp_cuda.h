@@ -263,6 +263,69 @@ ADSP_API void adsp_gen_log_sweep_host(double *out, int64_t n, int64_t index0, in
                                       double amplitude, double sample_rate);
 ADSP_API int64_t adsp_gen_delay_host(int64_t delay_seed, int64_t row, int64_t delay_mod);
 
+/* ---------------------------------------------------------------- the step AFTER the path: csrc/post.cu
+ * Consumers of correlation / deconvolution results, on device data so that nothing returns to the host in between.
+ * float64 like the reference.  Rows: `rows` signals of n samples, strides in elements (rows <= 65535 per call).
+ *
+ * measure/ir: SchroederIntegral (measure/ir/ir.go:94-130): backward cumulative energy, normalised, in dB (-200 dB floor;
+ * an all-zero IR returns the raw zero sums); FindImpulseStart (:381-404): first sample with |x| >= ratio * peak (the
+ * reference uses ratio 0.1), 0 when none; findPeak (:406-424): index of the absolute maximum, first one wins.
+ * n == 0 -> ADSP_ERR_EMPTY_IR (ir.ErrEmptyIR). */
+ADSP_API adsp_status adsp_ir_schroeder_device(adsp_ctx *, const double *ir_dev, int64_t n, int64_t rows, int64_t stride, double *out_dev, int64_t out_stride);
+ADSP_API adsp_status adsp_ir_find_impulse_start_device(adsp_ctx *, const double *ir_dev, int64_t n, int64_t rows, int64_t stride, double threshold_ratio,
+                                                       int64_t *index_dev);
+ADSP_API adsp_status adsp_ir_find_peak_device(adsp_ctx *, const double *ir_dev, int64_t n, int64_t rows, int64_t stride, int64_t *index_dev);
+ADSP_API adsp_status adsp_ir_schroeder(adsp_ctx *, const double *ir, int64_t n, double *out);                                       /* host pointers */
+ADSP_API adsp_status adsp_ir_find_impulse_start(adsp_ctx *, const double *ir, int64_t n, double threshold_ratio, int64_t *index); /* host pointers */
+/* measure/sweep LogSweep (measure/sweep/sweep.go): Generate :73-94, InverseFilter :104-155 (time-reversed sweep with a
+ * 6 dB/octave envelope, normalised by T*f1/ln(f2/f1)*sampleRate), Deconvolve :164-239 = full linear convolution of the
+ * response with the inverse filter (n + samples - 1 values; the IR peaks near index samples - 1).  samples =
+ * round(duration * sampleRate).  Validation as LogSweep.Validate (:37-55): ADSP_ERR_INVALID_ARG + the reference's text;
+ * an empty response -> ADSP_ERR_EMPTY_INPUT (sweep.ErrEmptyResponse).  The *_host twins are bit-identical to the device. */
+ADSP_API int64_t adsp_logsweep_samples(double duration, double sample_rate);
+ADSP_API adsp_status adsp_logsweep_generate_device(adsp_ctx *, double *out_dev, double start_hz, double end_hz, double duration, double sample_rate);
+ADSP_API adsp_status adsp_logsweep_inverse_filter_device(adsp_ctx *, double *out_dev, double start_hz, double end_hz, double duration, double sample_rate);
+ADSP_API adsp_status adsp_logsweep_generate_host(double *out, double start_hz, double end_hz, double duration, double sample_rate);
+ADSP_API adsp_status adsp_logsweep_inverse_filter_host(double *out, double start_hz, double end_hz, double duration, double sample_rate);
+ADSP_API adsp_status adsp_logsweep_deconvolve_device(adsp_ctx *, const double *response_dev, int64_t n, int64_t rows, int64_t in_stride, double start_hz,
+                                                     double end_hz, double duration, double sample_rate, double *out_dev, int64_t out_stride);
+ADSP_API adsp_status adsp_logsweep_deconvolve(adsp_ctx *, const double *response, int64_t n, double start_hz, double end_hz, double duration,
+                                              double sample_rate, double *out, int64_t out_len);
+/* dsp/filter/fir Filter (dsp/filter/fir/filter.go): New(coeffs) :18, ProcessBlock(buf) :61-103 in place with the delay
+ * line carried across calls, Reset, Order.  `channels` independent filters with the same coefficients, one per row.
+ * Tap order exactly as the reference applies it: below 32 taps y[n] = sum_k h[k] x[n-k] (ProcessSample, :36-59); from 32
+ * taps on the block path dots the coefficients with the window stored oldest first (:93-94), y[n] = sum_k h[N-1-k] x[n-k]
+ * -- identical for the symmetric filters the reference designs and tests. */
+typedef struct adsp_fir adsp_fir;
+ADSP_API adsp_status adsp_fir_create(adsp_ctx *, const double *coeffs, int64_t ntaps, int channels, adsp_fir **out);
+ADSP_API adsp_status adsp_fir_process_block(adsp_fir *, double *buf, int64_t n, int64_t stride);             /* host pointers */
+ADSP_API adsp_status adsp_fir_process_block_device(adsp_fir *, double *buf_dev, int64_t n, int64_t stride);
+ADSP_API int64_t adsp_fir_order(const adsp_fir *);
+ADSP_API void adsp_fir_reset(adsp_fir *);
+ADSP_API void adsp_fir_destroy(adsp_fir *);
+/* dsp/resample Resampler (dsp/resample/resample.go, resample_design.go): NewRational(up, down, options) :153 with the
+ * Kaiser-windowed-sinc polyphase design of designPolyphaseFIR; quality 0 fast / 1 balanced / 2 best (QualityProfile :35),
+ * taps_per_phase / cutoff_scale / kaiser_beta <= 0 keep the profile's value; NewForRates :194 (continued-fraction ratio,
+ * max_den <= 0 -> 4096).  Process :249-292 keeps phase, input index and history across calls; n_out receives the number
+ * of samples written per row (= adsp_resampler_predict_output_len before the call); out_cap smaller than that ->
+ * ADSP_ERR_LENGTH_MISMATCH.  up or down <= 0 -> ADSP_ERR_INVALID_ARG ("resample: invalid ratio"). */
+typedef struct adsp_resampler adsp_resampler;
+ADSP_API void adsp_resample_approximate_ratio(double v, int max_den, int *num, int *den);
+ADSP_API adsp_status adsp_resampler_create(adsp_ctx *, int up, int down, int quality, int taps_per_phase, double cutoff_scale, double kaiser_beta,
+                                           int channels, adsp_resampler **out);
+ADSP_API adsp_status adsp_resampler_create_for_rates(adsp_ctx *, double in_rate, double out_rate, int quality, int max_den, int channels,
+                                                     adsp_resampler **out);
+ADSP_API void adsp_resampler_ratio(const adsp_resampler *, int *up, int *down);
+ADSP_API int adsp_resampler_taps_per_phase(const adsp_resampler *);
+ADSP_API int64_t adsp_resampler_prototype(const adsp_resampler *, double *out, int64_t cap);
+ADSP_API int64_t adsp_resampler_predict_output_len(const adsp_resampler *, int64_t input_len);
+ADSP_API adsp_status adsp_resampler_process(adsp_resampler *, const double *in, int64_t n, int64_t in_stride, double *out, int64_t out_cap,
+                                            int64_t out_stride, int64_t *n_out);                             /* host pointers */
+ADSP_API adsp_status adsp_resampler_process_device(adsp_resampler *, const double *in_dev, int64_t n, int64_t in_stride, double *out_dev,
+                                                   int64_t out_cap, int64_t out_stride, int64_t *n_out);
+ADSP_API void adsp_resampler_reset(adsp_resampler *);
+ADSP_API void adsp_resampler_destroy(adsp_resampler *);
+
 /* ---------------------------------------------------------------- partitioned (long IR, streaming)
  * NewPartitionedConvolution(kernel, minBlockOrder, maxBlockOrder) partitioned.go:212,335.
  * ProcessBlock(input, output): equal lengths, output delayed by Latency() = 2^minBlockOrder. */
