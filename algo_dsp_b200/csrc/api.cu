@@ -758,7 +758,8 @@ adsp_status oneshot(adsp_ctx *ctx, OneShot op, const T *a, int64_t n, const T *b
     else {
         bool done = false;
         // long correlations: one packed transform of (a, reverse b) instead of a generic long-kernel convolution
-        if (corr && env_ll("ADSP_CORR_GENERIC", 0) == 0) ADSP_TRY(fft_correlate_pairs_device<T>(ctx, da, n, n, db, m, m, 1, dout, out_len, &done));
+        if (corr && env_ll("ADSP_CORR_GENERIC", 0) == 0)
+            ADSP_TRY(fft_correlate_pairs_device<T>(ctx, da, n, n, db, m, m, 1, dout, out_len, (T *)nullptr, (long long *)nullptr, &done));
         if (!done) ADSP_TRY(fft_convolve_device<T>(ctx, sig, sn, 1, 0, ker, km, dout, 0));
     }
     if (post) {
@@ -1003,26 +1004,51 @@ adsp_status correlate_batch_dev(adsp_ctx *ctx, const T *a, int64_t n, int64_t a_
                                 int64_t b_stride, int64_t pairs, T *out, int64_t out_stride, long long *peak_i, T *peak_v) {
     const int64_t out_len = n + m - 1;
     const bool want_peaks = peak_i && peak_v;
-    // long operands: one packed transform per pair + one shared inverse per two pairs
+    // ONE b for every pair (b_stride == 0: the measurement case, every response against the same excitation sweep):
+    // Correlate(a_p, b) = Convolve(a_p, reverse(b)) (correlate.go:16-28) is then a batched convolution with one cached
+    // kernel spectrum -- the overlap-save engine itself, two pairs per complex transform, no mirror-bin extraction at all
+    // (half the forward transforms of the per-pair path below).
+    if (b_stride == 0 && pairs >= 2 && std::min(n, m) > 64 && env_ll("ADSP_CORR_GENERIC", 0) == 0 && env_ll("ADSP_CORR_SHARED_B", 1) != 0) {
+        const FftChoice big = choose_fft(m);
+        if (big.parts == 1) {
+            ADSP_TRY(ctx->d_k.reserve((size_t)m * sizeof(T)));
+            T *dk = (T *)ctx->d_k.p;
+            reverse_kernel<T><<<(unsigned)((m + 255) / 256), 256, 0, ctx->main>>>(b, m, m, dk, m, 1);
+            count_launch(ctx);
+            struct Seg { Segment sg; FftConv<T> fc; };
+            std::vector<Seg> segs;
+            adsp_status st = ADSP_OK;
+            for (const Segment &sg : plan_segments(out_len, m, big)) {
+                segs.push_back({sg, FftConv<T>()});
+                st = segs.back().fc.init(ctx, dk, m, make_choice(m, sg.N));
+                if (st != ADSP_OK) break;
+            }
+            const int64_t tstride = ((out_len + 31) / 32) * 32;
+            const int64_t chunk = out ? pairs : std::min<int64_t>(pairs, 64);
+            if (st == ADSP_OK && !out) st = ctx->d_tmp.reserve((size_t)chunk * (size_t)tstride * sizeof(T));
+            for (int64_t c0 = 0; c0 < pairs && st == ADSP_OK; c0 += chunk) {
+                const int64_t np = std::min(chunk, pairs - c0);
+                T *o = out ? out + c0 * out_stride : (T *)ctx->d_tmp.p;
+                const int64_t os = out ? out_stride : tstride;
+                for (Seg &sgm : segs) {
+                    sgm.fc.no_discard = sgm.sg.no_discard;
+                    st = sgm.fc.run(a + c0 * a_stride, n, np, a_stride, o, os, sgm.sg.len, sgm.sg.off, sgm.sg.off, false);
+                    if (st != ADSP_OK) break;
+                }
+                if (st == ADSP_OK && want_peaks) st = peak_device<T>(ctx, o, out_len, os, np, peak_v + c0, peak_i + c0);
+            }
+            if (st == ADSP_OK && cudaStreamSynchronize(ctx->main) != cudaSuccess) st = ADSP_ERR_CUDA;   // the spectra are freed below
+            for (Seg &sgm : segs) sgm.fc.destroy();
+            return st;
+        }
+    }
+    // long operands: one packed transform per pair + one shared inverse per two pairs, the peak search in the epilogue of the
+    // inverse column pass; with out == NULL the correlation itself is never written
     if (std::min(n, m) > 64 && env_ll("ADSP_CORR_GENERIC", 0) == 0) {
-        const int64_t chunk = out ? pairs : std::min<int64_t>(pairs, 16);
-        const int64_t tstride = ((out_len + 31) / 32) * 32;
-        T *tmp = nullptr;
-        if (!out) {
-            ADSP_TRY(ctx->d_tmp.reserve((size_t)chunk * (size_t)tstride * sizeof(T)));
-            tmp = (T *)ctx->d_tmp.p;
-        }
-        bool all_done = true;
-        for (int64_t c0 = 0; c0 < pairs && all_done; c0 += chunk) {
-            const int64_t np = std::min(chunk, pairs - c0);
-            T *o = out ? out + c0 * out_stride : tmp;
-            const int64_t os = out ? out_stride : tstride;
-            bool done = false;
-            ADSP_TRY(fft_correlate_pairs_device<T>(ctx, a + c0 * a_stride, n, a_stride, b + c0 * b_stride, m, b_stride, np, o, os, &done));
-            if (!done) { all_done = false; break; }
-            if (want_peaks) ADSP_TRY(peak_device<T>(ctx, o, out_len, os, np, peak_v + c0, peak_i + c0));
-        }
-        if (all_done) return ADSP_OK;
+        bool done = false;
+        ADSP_TRY(fft_correlate_pairs_device<T>(ctx, a, n, a_stride, b, m, b_stride, pairs, out, out_stride, want_peaks ? peak_v : (T *)nullptr,
+                                               want_peaks ? peak_i : (long long *)nullptr, &done));
+        if (done) return ADSP_OK;
     }
     // generic path: Convolve(a, reverse(b)) per pair (direct for short operands, partitioned FFT beyond 2^22 points)
     ADSP_TRY(ctx->d_tmp.reserve((size_t)(m + (out ? 0 : out_len)) * sizeof(T)));

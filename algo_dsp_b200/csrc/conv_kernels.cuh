@@ -12,6 +12,7 @@
 //     N1 x N2 matrix + four-step twiddle) -> rows (N2-point FFT, *H, N2-point IFFT, in place in
 //     an L2-resident scratch) -> cols_inv (conj twiddle, N1-point inverse, discard, store).
 #pragma once
+#include "aux_kernels.cuh"
 #include "fft_core.cuh"
 
 namespace adsp {
@@ -628,6 +629,153 @@ __global__ void corr_pointwise(const cpx<T> *Z, cpx<T> *Q, int npairs, int N1, i
     qm.x = pa.x + pb.y; qm.y = -pa.y + pb.x;
     __stcg(&Qq[idx], qk);
     if (midx != idx) __stcg(&Qq[midx], qm);
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused correlation rows: forward row transforms of the packed spectrum Z = FFT(a + i*reverse(b)), the spectral product
+//     P[k] = (Z[k]^2 - conj(Z[N-k])^2) / (4i)            (= FFT(a)[k] * FFT(reverse b)[k], both real sequences)
+// of TWO pairs (Q = P_A + i*P_B: one inverse transform serves both, results in re / im) and the inverse row transforms,
+// in one launch -- what corr rows-forward + corr_pointwise + rows-inverse did in three with the spectrum making two extra
+// round trips through L2 / HBM.  The mirror bin N-k of row k1 lives in row N1-k1 at position N2-1-k2 (row 0: same row,
+// position (N2-k2) mod N2), so a CTA transforms the two partner rows side by side (2 * L/16 threads) and exchanges the
+// spectra through the shared-memory buffers the transforms have just finished with.  Q is written over pair A's rows
+// (the CTA owns rows k1 and N1-k1 of both pairs).  grid = (N1/2, pairs of pairs).
+template <typename T, int L>
+__global__ void __launch_bounds__(2 * (L / 16), (2 * (L / 16) <= 128) ? 4 : ((2 * (L / 16) <= 256) ? 2 : 1))
+corr_rows_fused(cpx<T> *__restrict__ Z, int npairs, int N1, T scale, const cpx<T> *__restrict__ tw) {
+    using C = cpx<T>;
+    using Sh = FftShape<L>;
+    constexpr int TPF = Sh::TPF;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C *buf = reinterpret_cast<C *>(smem_raw);
+    C *stw = buf + 2 * L;
+    load_tw_smem<T, L>(stw, tw, threadIdx.x, 2 * TPF);
+    const int grp = threadIdx.x / TPF;            // 0: row k1, 1: its partner row
+    const int j = threadIdx.x % TPF;
+    const int task = blockIdx.x;                  // 0: rows 0 and N1/2 (each its own partner), t >= 1: rows t and N1 - t
+    const int k1 = (task == 0) ? (grp == 0 ? 0 : N1 / 2) : (grp == 0 ? task : N1 - task);
+    const bool self = task == 0;                  // partner spectrum sits in this thread's own row buffer
+    const bool rule_a = self && grp == 0;         // row 0: mirror of k2 is (L - k2) mod L; every other row: L - 1 - k2
+    const size_t Nel = (size_t)N1 * L;
+    const int pa_idx = 2 * blockIdx.y, pb_idx = 2 * blockIdx.y + 1;
+    RowAddr<T, Sh::R0> addr{grp * L};
+    RowAddr<T, Sh::R0> paddr{(self ? grp : 1 - grp) * L};
+    CtaGate gate;
+    C *rowA = Z + (size_t)pa_idx * Nel + (size_t)k1 * L + j;
+    C e[16];
+    // one pair: forward transform of this thread's row, product with the mirror bins -> e[] = P[k1 + N1*k2], k2 = j + q*TPF
+    auto spectrum_product = [&](const C *row) {
+#pragma unroll
+        for (int q = 0; q < 16; q++) e[q] = __ldcg(&row[q * TPF]);
+        cta_fft<T, L, false>(e, buf, addr, stw, j, gate);
+        // every thread parks its spectrum in the slots it alone read in the last pass, then reads the mirror bins
+#pragma unroll
+        for (int q = 0; q < 16; q++) buf[addr.at(j + q * TPF, Sh::P - 1)] = e[q];
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const int k2 = j + q * TPF;
+            const int m2 = rule_a ? ((L - k2) & (L - 1)) : (L - 1 - k2);
+            const C zm = buf[paddr.at(m2, Sh::P - 1)];
+            const C zk = e[q];
+            const T ar = zk.x * zk.x - zk.y * zk.y, ai = 2 * zk.x * zk.y;      // zk^2
+            const T br = zm.x * zm.x - zm.y * zm.y, bi = -2 * zm.x * zm.y;     // conj(zm)^2
+            const T dr = ar - br, di = ai - bi;                                  // (dr + i di) / (4i) = (di - i dr) / 4
+            e[q].x = di * (scale * (T)0.25);
+            e[q].y = -dr * (scale * (T)0.25);
+        }
+    };
+    spectrum_product(rowA);
+    if (pb_idx < npairs) {
+        // park P_A in its own rows (L2), transform pair B, then Q = P_A + i*P_B
+#pragma unroll
+        for (int q = 0; q < 16; q++) __stcg(&rowA[q * TPF], e[q]);
+        __syncthreads();                          // everyone has read the mirror bins of pair A: the buffers are free again
+        spectrum_product(Z + (size_t)pb_idx * Nel + (size_t)k1 * L + j);
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const C pa = __ldcg(&rowA[q * TPF]);
+            const C pb = e[q];
+            e[q].x = pa.x - pb.y;
+            e[q].y = pa.y + pb.x;
+        }
+    }
+    cta_fft<T, L, true>(e, buf, addr, stw, j, gate);     // (its first barrier also covers the mirror reads above)
+#pragma unroll
+    for (int q = 0; q < 16; q++) __stcg(&rowA[q * TPF], e[q]);
+}
+
+// Inverse column pass of the correlation with the peak search folded into its epilogue (FindPeak, correlate.go:200-216:
+// signed maximum, first index wins, NaN never wins): every CTA leaves one (value, index) candidate per real output block
+// in part_v / part_i [pair][tile]; peak_final_kernel reduces them.  `slot_mult`: Q of pairs (2q, 2q+1) sits in the scratch
+// slot of pair 2q.  STORE = false skips the output stores (peak lags only: the correlation itself never reaches HBM).
+template <typename T, int N1, bool STORE>
+__global__ void __launch_bounds__(ColShape<N1>::THREADS, min_ctas_for<T>(ColShape<N1>::THREADS, ColShape<N1>::MIN_CTAS > 2 ? ColShape<N1>::MIN_CTAS - 1 : ColShape<N1>::MIN_CTAS))
+corr_cols_inv_peak(ConvGeom g, const cpx<T> *__restrict__ scratch, int slot_mult, T *__restrict__ y, int N2, int lgN, const cpx<T> *__restrict__ tw,
+                   const cpx<T> *__restrict__ tw_hi, const cpx<T> *__restrict__ tw_lo, long long pair0, T *__restrict__ part_v,
+                   long long *__restrict__ part_i, T *__restrict__ first_v) {
+    using C = cpx<T>;
+    using CS = ColShape<N1>;
+    constexpr int TPF = CS::TPF, TC = CS::TC, NW = CS::THREADS / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C *buf = reinterpret_cast<C *>(smem_raw);
+    C *stw = buf + ((FftShape<N1>::P > 0) ? CS::SMEM_ELEMS : 0);
+    load_tw_smem<T, N1>(stw, tw, threadIdx.x, CS::THREADS);
+    __shared__ T sv[2][NW > 0 ? NW : 1];
+    __shared__ long long si[2][NW > 0 ? NW : 1];
+    const int tid = threadIdx.x;
+    const int c = tid % TC, j = tid / TC;
+    const int tile = blockIdx.x, pl = blockIdx.y;
+    const int n2 = tile * TC + c;
+    ColAddr<TC> addr{c};
+    const unsigned maskN = (1u << lgN) - 1u;
+    const C tw_base = twiddle_n<T>(tw_hi, tw_lo, ((unsigned)n2 * (unsigned)j) & maskN);
+    const C tw_rho = twiddle_n<T>(tw_hi, tw_lo, ((unsigned)n2 * (unsigned)TPF) & maskN);
+    const C *src = scratch + (size_t)pl * (size_t)slot_mult * ((size_t)N1 * N2) + n2;
+    C e[16];
+    const uint64_t drop = l2_policy_drop();
+#pragma unroll
+    for (int q = 0; q < 16; q++) e[q] = ld_scratch(&src[(size_t)(j + q * TPF) * N2], drop);
+    CtaGate gate;
+    apply_geometric16<true>(e, tw_base, tw_rho);
+    cta_fft<T, N1, true, true, false>(e, buf, addr, stw, j, gate);
+    const long long pair = pair0 + pl;
+    const BlockIO<T> a = block_io<T>(g, (const T *)nullptr, y, 2 * pair);
+    const BlockIO<T> b = block_io<T>(g, (const T *)nullptr, y, 2 * pair + 1);
+    T va = (T)0, vb = (T)0;
+    long long ia = -1, ib = -1;
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+        const long long o = (long long)(j + r * TPF) * N2 + n2;
+        if (o < a.cnt) {
+            const T x = e[r].x;
+            if (STORE) __stcs(a.out + o, x);
+            if (x == x && (ia < 0 || x > va)) { va = x; ia = o; }
+            if (o == 0) first_v[2 * pair] = x;
+        }
+        if (o < b.cnt) {
+            const T x = e[r].y;
+            if (STORE) __stcs(b.out + o, x);
+            if (x == x && (ib < 0 || x > vb)) { vb = x; ib = o; }
+            if (o == 0) first_v[2 * pair + 1] = x;
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        peak_combine(va, ia, __shfl_xor_sync(0xffffffffu, va, o), __shfl_xor_sync(0xffffffffu, ia, o));
+        peak_combine(vb, ib, __shfl_xor_sync(0xffffffffu, vb, o), __shfl_xor_sync(0xffffffffu, ib, o));
+    }
+    if ((tid & 31) == 0) { sv[0][tid >> 5] = va; si[0][tid >> 5] = ia; sv[1][tid >> 5] = vb; si[1][tid >> 5] = ib; }
+    __syncthreads();
+    if (tid < 2) {
+        T v = sv[tid][0];
+        long long i = si[tid][0];
+        for (int w = 1; w < NW; w++) peak_combine(v, i, sv[tid][w], si[tid][w]);
+        const long long blk = 2 * pair + tid;
+        if (blk < g.total_blocks) {
+            part_v[blk * gridDim.x + tile] = v;
+            part_i[blk * gridDim.x + tile] = i;
+        }
+    }
 }
 
 // Regularised / naive spectral division for deconvolution (deconvolve.go:143-151, 216-220, 304-308), in four-step order,

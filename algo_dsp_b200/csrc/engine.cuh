@@ -183,7 +183,7 @@ adsp_status fft_convolve_device(adsp_ctx *ctx, const T *d_x, long long n, long l
 
 template <typename T>
 adsp_status fft_correlate_pairs_device(adsp_ctx *ctx, const T *a, long long n, long long a_stride, const T *b, long long m,
-                                       long long b_stride, long long pairs, T *out, long long out_stride, bool *done);
+                                       long long b_stride, long long pairs, T *out, long long out_stride, T *peak_v, long long *peak_i, bool *done);
 
 template <typename T>
 adsp_status fft_deconvolve_device(adsp_ctx *ctx, const T *sig, long long n, long long s_stride, const T *ker, long long m,

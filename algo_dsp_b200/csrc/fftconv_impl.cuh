@@ -972,11 +972,43 @@ static adsp_status launch_corr_cols_t(adsp_ctx *ctx, cudaStream_t st, const T *a
     return ADSP_OK;
 }
 
-// out[p][k] = sum_i a[p][i] * b[p][i - (k - (m-1))], k < n+m-1, for `pairs` pairs (device pointers).
+template <typename T, int L>
+static adsp_status launch_corr_rows_fused_t(adsp_ctx *ctx, cudaStream_t st, cpx<T> *Z, int npairs, int N1, T scale, const cpx<T> *tw) {
+    constexpr int THREADS = 2 * (L / 16);
+    const size_t smem = ((size_t)2 * L + FftShape<L>::TW_ENTRIES) * sizeof(cpx<T>);
+    static AttrOnce once;
+    if (once.need(ctx->device)) ADSP_TRY(set_smem(corr_rows_fused<T, L>, smem));
+    dim3 grid((unsigned)(N1 / 2), (unsigned)((npairs + 1) / 2));
+    LaunchTimer lt(ctx, st, KK_ROWS);
+    corr_rows_fused<T, L><<<grid, THREADS, smem, st>>>(Z, npairs, N1, scale, tw);
+    count_launch(ctx);
+    ADSP_CUDA(cudaGetLastError());
+    return ADSP_OK;
+}
+
+template <typename T, int N1, bool STORE>
+static adsp_status launch_corr_cols_inv_t(adsp_ctx *ctx, cudaStream_t st, const ConvGeom &g, const cpx<T> *scratch, T *y, int N2, int lgN, const cpx<T> *tw,
+                                          const cpx<T> *hi, const cpx<T> *lo, long long pair0, int nq, T *part_v, long long *part_i, T *first_v) {
+    using CS = ColShape<N1>;
+    const size_t smem = (FftShape<N1>::P > 0) ? ((size_t)CS::SMEM_ELEMS + FftShape<N1>::TW_ENTRIES) * sizeof(cpx<T>) : 16;
+    static AttrOnce once;
+    if (once.need(ctx->device)) ADSP_TRY(set_smem(corr_cols_inv_peak<T, N1, STORE>, smem));
+    dim3 grid((unsigned)(N2 / CS::TC), (unsigned)nq);
+    LaunchTimer lt(ctx, st, KK_COLS_INV);
+    corr_cols_inv_peak<T, N1, STORE><<<grid, CS::THREADS, smem, st>>>(g, scratch, 2, y, N2, lgN, tw, hi, lo, pair0, part_v, part_i, first_v);
+    count_launch(ctx);
+    ADSP_CUDA(cudaGetLastError());
+    return ADSP_OK;
+}
+
+// out[p][k] = sum_i a[p][i] * b[p][i - (k - (m-1))], k < n+m-1, for `pairs` pairs (device pointers); out may be null
+// (peak search only).  peak_v / peak_i (nullable, device): FindPeak of every pair (correlate.go:200-216).
+// Three launches per group of pairs: packed forward columns, fused rows (forward, spectral product of two pairs, inverse),
+// inverse columns with the peak search in their epilogue; one final reduction per call.
 // Returns *done=false when the shape is outside the transform sizes of this path.
 template <typename T>
 adsp_status fft_correlate_pairs_device(adsp_ctx *ctx, const T *a, long long n, long long a_stride, const T *b, long long m,
-                                       long long b_stride, long long pairs, T *out, long long out_stride, bool *done) {
+                                       long long b_stride, long long pairs, T *out, long long out_stride, T *peak_v, long long *peak_i, bool *done) {
     *done = false;
     const long long out_len = n + m - 1;
     long long N = 8192;
@@ -987,16 +1019,25 @@ adsp_status fft_correlate_pairs_device(adsp_ctx *ctx, const T *a, long long n, l
     ADSP_TRY(get_tw_table<T>(ctx, ch.N2, &tw_rows));
     ADSP_TRY(get_tw_table<T>(ctx, ch.N1, &tw_cols));
     ADSP_TRY(get_tw4_tables<T>(ctx, ch.N, &tw_hi, &tw_lo));
-    // groups of pairs whose spectra (one slot each) and shared inverse transforms (one slot per two pairs) fit the L2
-    // scratch budget; a group of two pairs (the 2^21-point case of BASELINE config 4) keeps Q in place in slot 0
+    // groups of an even number of pairs whose spectra (one slot each; Q of two pairs reuses the first one's slot) fit the L2
+    // scratch budget, never fewer than two
     const size_t slot = (size_t)N * sizeof(cpx<T>);
-    long long G = (long long)(ctx->scratch_budget / slot) * 2 / 3;
+    long long budget = (long long)ctx->scratch_budget;
+    const long long mb = env_ll("ADSP_CORR_SCRATCH_MB", 0);
+    if (mb > 0) budget = mb << 20;
+    long long G = budget / (long long)slot;
     G = std::max<long long>(2, G - (G & 1));
-    G = std::min<long long>(G, std::min<long long>(pairs + (pairs & 1), 4096));
-    const bool in_place = (G == 2);
-    ADSP_TRY(ctx->scratch.reserve((size_t)(in_place ? 2 : G + G / 2) * slot));
+    G = std::min<long long>(G, std::min<long long>(pairs + (pairs & 1), 8192));
+    ADSP_TRY(ctx->scratch.reserve((size_t)G * slot));
     cpx<T> *Z = (cpx<T> *)ctx->scratch.p;
-    cpx<T> *Q = in_place ? Z : Z + (size_t)G * N;
+    // peak candidates: one (value, index) per output row and column tile, plus each row's first sample (the NaN rule of
+    // FindPeak needs corr[0])
+    const int tiles = ch.N2 / (ch.N1 <= 256 ? (ADSP_COLS_CTA_THREADS / (ch.N1 / 16)) : (ch.N1 == 512 ? ADSP_COLS_TC_512 : ADSP_COLS_TC_1024));
+    const long long rows_pad = pairs + (pairs & 1);
+    ADSP_TRY(ctx->d_small.reserve((size_t)rows_pad * tiles * (sizeof(T) + sizeof(long long)) + (size_t)rows_pad * sizeof(T) + 256));
+    long long *part_i = (long long *)ctx->d_small.p;
+    T *part_v = (T *)(part_i + rows_pad * tiles);
+    T *first_v = part_v + rows_pad * tiles;
     ConvGeom g{};                          // output side: block 2q -> pair 2q (re), block 2q+1 -> pair 2q+1 (im)
     g.n = N; g.out_len = out_len; g.in_stride = 0; g.out_stride = out_stride; g.S = N; g.D = 0;
     g.total_blocks = pairs; g.in_shift = 0; g.out_shift = 0; g.nblk = 1; g.accumulate = 0;
@@ -1010,15 +1051,26 @@ adsp_status fft_correlate_pairs_device(adsp_ctx *ctx, const T *a, long long n, l
         default: set_error("correlate: unsupported transform shape"); return ADSP_ERR_INVALID_ARG;
         }
 #undef ADSP_CORR_COLS
-        ADSP_TRY((launch_rows<T, 1>(ctx, st, ch.N2, Z, (const cpx<T> *)nullptr, Z, (T)1, ch.N1, tw_rows, np)));   // forward rows, in place
-        {
-            LaunchTimer lt(ctx, st, KK_OTHER);
-            dim3 grid((unsigned)((N + 255) / 256), (unsigned)nq);
-            corr_pointwise<T><<<grid, 256, 0, st>>>(Z, Q, np, ch.N1, ch.N2, scale);
-            count_launch(ctx);
+        switch (ch.N2) {
+#define ADSP_CORR_ROWS(l) case l: ADSP_TRY((launch_corr_rows_fused_t<T, l>(ctx, st, Z, np, ch.N1, scale, tw_rows))); break;
+            ADSP_CORR_ROWS(256) ADSP_CORR_ROWS(512) ADSP_CORR_ROWS(1024) ADSP_CORR_ROWS(2048) ADSP_CORR_ROWS(4096)
+#undef ADSP_CORR_ROWS
+        default: set_error("correlate: unsupported row length"); return ADSP_ERR_INVALID_ARG;
         }
-        ADSP_TRY((launch_rows<T, 2>(ctx, st, ch.N2, Q, (const cpx<T> *)nullptr, Q, (T)1, ch.N1, tw_rows, nq)));     // inverse rows of Q
-        ADSP_TRY(launch_cols<T>(ctx, st, ch.N1, true, g, (const T *)nullptr, out, Q, ch.N2, ch.lgN, tw_cols, tw_hi, tw_lo, p0 / 2, nq));
+#define ADSP_CORR_INV(n1) \
+    case n1: \
+        if (out) ADSP_TRY((launch_corr_cols_inv_t<T, n1, true>(ctx, st, g, Z, out, ch.N2, ch.lgN, tw_cols, tw_hi, tw_lo, p0 / 2, nq, part_v, part_i, first_v))); \
+        else ADSP_TRY((launch_corr_cols_inv_t<T, n1, false>(ctx, st, g, Z, out, ch.N2, ch.lgN, tw_cols, tw_hi, tw_lo, p0 / 2, nq, part_v, part_i, first_v))); \
+        break;
+        switch (ch.N1) {
+            ADSP_CORR_INV(16) ADSP_CORR_INV(32) ADSP_CORR_INV(64) ADSP_CORR_INV(128) ADSP_CORR_INV(256) ADSP_CORR_INV(512) ADSP_CORR_INV(1024)
+        default: set_error("correlate: unsupported transform shape"); return ADSP_ERR_INVALID_ARG;
+        }
+#undef ADSP_CORR_INV
+    }
+    if (peak_v && peak_i) {
+        peak_final_kernel<T><<<(unsigned)pairs, 32, 0, st>>>(first_v, 1, part_v, part_i, tiles, pairs, peak_v, peak_i);
+        count_launch(ctx);
     }
     ADSP_CUDA(cudaGetLastError());
     *done = true;
@@ -1115,7 +1167,7 @@ template adsp_status fft_deconvolve_device<ADSP_REAL>(adsp_ctx *, const ADSP_REA
                                                       long long, ADSP_REAL *, long long, long long, ADSP_REAL, long long *);
 
 template adsp_status fft_correlate_pairs_device<ADSP_REAL>(adsp_ctx *, const ADSP_REAL *, long long, long long, const ADSP_REAL *, long long,
-                                                           long long, long long, ADSP_REAL *, long long, bool *);
+                                                           long long, long long, ADSP_REAL *, long long, ADSP_REAL *, long long *, bool *);
 
 template struct FftConv<ADSP_REAL>;
 template adsp_status get_tw_table<ADSP_REAL>(adsp_ctx *, int, const cpx<ADSP_REAL> **);

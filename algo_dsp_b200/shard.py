@@ -78,3 +78,26 @@ def gather_outputs(local: np.ndarray, shards: list[TimeShard], dist=None) -> np.
     bufs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(bufs, pad)
     return np.concatenate([b[:sz].cpu().numpy() for b, sz in zip(bufs, sizes)])
+
+
+def gather_outputs_device(local, sizes, dist=None):
+    """Device-resident all-gather ("reported separately"): `local` is this rank's output piece as a torch tensor
+    living where the backend wants it (CUDA for NCCL over NVLink / NVSwitch, CPU for gloo); `sizes[r]` the number of valid
+    leading elements along dim 0 of rank r's piece.  Every rank receives all pieces in one collective on equally padded
+    slots and returns the list of per-rank views (no host round trip, no concatenation copy)."""
+    import torch
+    if dist is None:
+        import torch.distributed as dist  # noqa: PLW0642
+    world = dist.get_world_size()
+    mx = max(sizes)
+    slot = local
+    if local.shape[0] != mx:
+        slot = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        slot[: local.shape[0]] = local
+    out = torch.empty((world * mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    try:
+        dist.all_gather_into_tensor(out, slot.contiguous())
+    except (RuntimeError, NotImplementedError):          # backends without the single-tensor form
+        bufs = [out[r * mx:(r + 1) * mx] for r in range(world)]
+        dist.all_gather(bufs, slot.contiguous())
+    return [out[r * mx: r * mx + sizes[r]] for r in range(world)]

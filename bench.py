@@ -134,7 +134,7 @@ def run_reference(args):
     from oracle import oracle as O
     O.build()
     threads = O.num_procs()
-    channels = max(threads * 8, 8)
+    channels = CHANNELS_PER_GPU          # the same 256-channel step as the GPU arm (about a second of CPU work per step on 16 cores)
     from algo_dsp_b200 import siggen as G
     h = G.decaying_ir(K_TAPS)
     x = np.stack([G.white(N_SAMPLES, seed=1 + c) for c in range(channels)])
@@ -145,11 +145,12 @@ def run_reference(args):
         O.bench_ols(h, x, 0, threads)
     dt = (time.perf_counter() - t0) / args.steps
     value = channels * OUT_LEN / dt
-    sample = f"{channels} channels x {N_SAMPLES} samples x {K_TAPS} taps per step (bounded sample of the {CHANNELS_PER_GPU}-channel workload)"
+    sample = f"{channels} channels x {N_SAMPLES} samples x {K_TAPS} taps per step (the whole {CHANNELS_PER_GPU}-channel step of the GPU arm)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "ols96k_batch", "kernel_taps": K_TAPS, "signal_samples": N_SAMPLES, "channels_per_step": channels,
+        "config": {"workload": "ols96k_batch", "kernel_taps": K_TAPS, "signal_samples": N_SAMPLES, "channels_per_gpu": channels,
+                   "output_samples_per_channel": OUT_LEN,
                    "reference_shape": "OverlapSave.Process, N=262144 complex128 FFT per block (overlap_save.go:126-254)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                          "note": "C restatement of the Go reference (Go toolchain and algo-fft are absent); one convolver per thread"},
@@ -247,24 +248,47 @@ def other_configs(torch, conv, G, ctx, stream):
         stream_res[f"block_{nblk}"] = {"ms_per_call": ms, "samples_per_s": 64 * nblk / ms * 1e3, "x_realtime_48k": nblk / 48000.0 / (ms * 1e-3)}
     out["config3_streaming_reverb_288k"] = stream_res
     rv.Close()
-    # config 4: sweep/response correlation + peak lag, 16 of the 1024 pairs x 2^20
-    pairs, n = 16, 1 << 20
-    # b_p = log sweep; a_p = b_p delayed by d_p = hash(p) mod 4096 + white at -40 dB (seed 1000 + p); all built in HBM
+    # config 4: sweep/response correlation + peak lag, 256 of the 1024 pairs x 2^20.  SURVEY 8d: every pair correlates against
+    # the SAME log sweep b; a_p = b delayed by d_p = hash(p) mod 4096 + white at -40 dB (seed 1000 + p); all built in HBM.
+    # (a) b_stride = 0, one b for all pairs: a batched convolution with one cached spectrum; (b) every pair with its own
+    # copy of b: packed transform + mirror-bin product per pair.  Wall clock around the (synchronous) call.
+    pairs, n = 256, 1 << 20
     B1 = torch.empty((1, n), device="cuda", dtype=torch.float64)
     G.log_sweep_device(ctx, B1.data_ptr(), n)
     A = torch.empty((pairs, n), device="cuda", dtype=torch.float64)
     G.delay_mix_device(ctx, A.data_ptr(), n, pairs, n, B1.data_ptr(), noise_amp=0.01, seed0=1000, delay_seed=0, delay_mod=4096)
     ctx.sync()
-    delays = [G.delay_of(p) for p in range(pairs)]
+    delays = np.array([G.delay_of(p) for p in range(pairs)])
     B = B1.expand(pairs, n).contiguous()
     o = torch.empty((pairs, 2 * n - 1), device="cuda", dtype=torch.float64)
     pi = torch.empty(pairs, device="cuda", dtype=torch.int64)
     pv = torch.empty(pairs, device="cuda", dtype=torch.float64)
-    ms = timeit(lambda: lib.adsp_correlate_batch_device(ctx.handle, A.data_ptr(), n, n, B.data_ptr(), n, n, pairs, o.data_ptr(), 2 * n - 1,
-                                                        pi.data_ptr(), pv.data_ptr(), 0), iters=3)
-    lags_ok = bool(np.array_equal(pi.cpu().numpy() - (n - 1), np.array(delays)))
-    out["config4_correlate_peak"] = {"pairs": pairs, "pairs_per_s": pairs / ms * 1e3, "algorithmic_GBps": pairs * (4 * n - 1) * 8 / ms / 1e6,
-                                     "lags_exact": lags_ok, "ms": ms}
+
+    def corr(bptr, bstride, with_out):
+        st = lib.adsp_correlate_batch_device(ctx.handle, A.data_ptr(), n, n, bptr, n, bstride, pairs, o.data_ptr() if with_out else None,
+                                             2 * n - 1 if with_out else 0, pi.data_ptr(), pv.data_ptr(), 0)
+        assert st == 0, L.last_error()
+        ctx.sync()
+
+    def wall(fn, iters=3):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            fn()
+        return (time.perf_counter() - t0) / iters * 1e3
+
+    c4 = {"pairs": pairs}
+    for name, bptr, bstride in (("shared_b", B1.data_ptr(), 0), ("per_pair_b", B.data_ptr(), n)):
+        for with_out in (True, False):
+            ms = wall(lambda: corr(bptr, bstride, with_out))
+            ok = bool(np.array_equal(pi.cpu().numpy() - (n - 1), delays))
+            alg = (4 * n - 1) * 8 if with_out else 2 * n * 8
+            c4[name + ("" if with_out else "_peaks_only")] = {"pairs_per_s": pairs / ms * 1e3, "ms": ms, "lags_exact": ok,
+                                                               "algorithmic_GBps": pairs * alg / ms / 1e6, "hbm_frac": pairs * alg / ms / 1e6 / peak}
+    c4["pairs_per_s"] = c4["shared_b"]["pairs_per_s"]
+    c4["lags_exact"] = all(v["lags_exact"] for v in c4.values() if isinstance(v, dict))
+    out["config4_correlate_peak"] = c4
+    del A, B, o
     # deconvolution: 16 problems x 2^20 samples, 4096-tap kernel, regularized spectral division, device resident
     probs, n, m = 16, 1 << 20, 4096
     sig = gen_white(probs, n, 1)
@@ -420,6 +444,33 @@ def run_ours(args):
     c_both, c_in, c_out = C.c_double(), C.c_double(), C.c_double()
     lib.adsp_ctx_copy_ceiling(ctx.handle, h2d_bytes, d2h_bytes, 3, C.byref(c_both), C.byref(c_in), C.byref(c_out))
     barrier()
+    # ---- optional collective (reported separately): every rank receives every rank's device-resident output
+    # rows through one NCCL all-gather over NVLink / NVSwitch; the data path itself has no collective
+    allgather = None
+    if dist is not None:
+        from algo_dsp_b200 import shard
+        ag_rows = min(channels, args.allgather_channels)
+        piece = y[:ag_rows]
+        sizes = [ag_rows] * world
+        for _ in range(2):
+            shard.gather_outputs_device(piece, sizes, dist)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(3):
+            views = shard.gather_outputs_device(piece, sizes, dist)
+        g1.record()
+        torch.cuda.synchronize()
+        ag_ms = g0.elapsed_time(g1) / 3
+        ag_ok = bool(torch.equal(views[rank], piece))
+        tag = torch.tensor([ag_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tag, op=dist.ReduceOp.MAX)
+        bytes_rank = ag_rows * ostride * 8
+        allgather = {"bytes_per_rank": bytes_rank, "ms": float(tag[0]), "own_piece_intact": ag_ok,
+                     "bus_GBps": bytes_rank * (world - 1) / (float(tag[0]) * 1e-3) / 1e9,
+                     "what": f"torch.distributed all_gather_into_tensor (NCCL) of {ag_rows} output channels per rank, device resident, max over ranks; "
+                             "not part of `value` (shards are independent)"}
+        del views
     if sampler:
         sampler.stop()
 
@@ -561,6 +612,7 @@ def run_ours(args):
                                      "e2e_frac_of_ceiling": ceil_ms / e2e_ms if e2e_ms else None,
                                      "what": "one cudaMemcpyAsync H2D + one D2H of the step's byte counts from/to pinned memory, concurrently, "
                                              "every rank at the same time, max over ranks"}},
+            "allgather": allgather,
             "gpu_launches": launches,
             "clocks": clocks_timed,
             "other_configs": other,
@@ -590,6 +642,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--channels", type=int, default=CHANNELS_PER_GPU)
     ap.add_argument("--skip-other", action="store_true", help="skip the auxiliary measurements of BASELINE configs 1-4")
+    ap.add_argument("--allgather-channels", type=int, default=64, help="N > 1: output channels per rank in the optional all-gather leg")
     ap.add_argument("--sustain-s", type=float, default=2.5, help="seconds of back-to-back steps for the `sustained` leg (0: skip)")
     args = ap.parse_args()
     if args.impl == "reference":

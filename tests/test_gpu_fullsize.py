@@ -112,6 +112,26 @@ def test_config4_correlate_1024_pairs_x_2e20_peak_lags(conv, oracle, ctx):
         assert G.rel_l2(got, ref) <= TOL64
         idx, val = oracle.find_peak(ref)
         assert idx == int(pi[p]) and abs(val - float(pv[p])) <= 1e-9 * abs(val)
+    # every pair with its OWN copy of b (b_stride = n): the per-pair path (packed transform + mirror-bin product), where the
+    # call above (b_stride = 0, one b for all pairs) ran as a batched convolution with one cached spectrum
+    bb = b.expand(pairs, n).contiguous()
+    out2 = torch.empty((pairs, ol), device="cuda", dtype=torch.float64)
+    pi3 = torch.empty(pairs, device="cuda", dtype=torch.int64)
+    pv3 = torch.empty(pairs, device="cuda", dtype=torch.float64)
+    st = L.load().adsp_correlate_batch_device(ctx.handle, a.data_ptr(), n, n, bb.data_ptr(), n, n, pairs, out2.data_ptr(), ol, pi3.data_ptr(), pv3.data_ptr(),
+                                              L.F64)
+    assert st == L.OK
+    ctx.sync()
+    assert torch.equal(pi3, pi)
+    for p in (3, pairs - 1):
+        assert G.rel_l2(out2[p].cpu().numpy(), out[p].cpu().numpy()) <= TOL64
+    pi4 = torch.empty(pairs, device="cuda", dtype=torch.int64)
+    pv4 = torch.empty(pairs, device="cuda", dtype=torch.float64)
+    st = L.load().adsp_correlate_batch_device(ctx.handle, a.data_ptr(), n, n, bb.data_ptr(), n, n, pairs, None, 0, pi4.data_ptr(), pv4.data_ptr(), L.F64)
+    assert st == L.OK
+    ctx.sync()
+    assert torch.equal(pi4, pi3) and torch.equal(pv4, pv3)
+    del bb, out2
     # peaks only (out == NULL): same indices and values
     pi2 = torch.empty(pairs, device="cuda", dtype=torch.int64)
     pv2 = torch.empty(pairs, device="cuda", dtype=torch.float64)

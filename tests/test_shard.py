@@ -50,8 +50,13 @@ def _worker(rank, world, port, n, K, channels, q):
         s = sh[rank]
         local = shard.process_time_shard(lambda seg: O.overlap_save(h, 0, seg), x[s.in_lo:s.in_hi], s)
         full = shard.gather_outputs(local, sh, dist)
-        # channel sharding: every rank convolves its own channels; gather the per-channel checksums
+        # the device-resident form of the same collective (CPU tensors under gloo, CUDA tensors under NCCL)
         import torch
+        sizes = [t.out_hi - t.out_lo for t in sh]
+        views = shard.gather_outputs_device(torch.from_numpy(np.ascontiguousarray(local)), sizes, dist)
+        assert len(views) == world and all(v.shape[0] == sz for v, sz in zip(views, sizes))
+        assert np.array_equal(np.concatenate([v.numpy() for v in views]), full)
+        # channel sharding: every rank convolves its own channels; gather the per-channel checksums
         lo, hi = shard.channel_range(channels, rank, world)
         sums = torch.zeros(channels, dtype=torch.float64)
         for c in range(lo, hi):
