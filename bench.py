@@ -220,7 +220,27 @@ def other_configs(torch, conv, G, ctx, stream):
     y = torch.empty((ch, n + m - 1), device="cuda", dtype=torch.float64)
     ms = timeit(lambda: lib.adsp_direct_batch_device(ctx.handle, x.data_ptr(), n, n, k.data_ptr(), m, 0, ch, y.data_ptr(), n + m - 1, 0))
     sps = ch * (n + m - 1) / ms * 1e3
-    out["config2_direct_64tap"] = {"channels": ch, "samples_per_s": sps, "hbm_frac": sps * 16 / 1e9 / peak, "ms": ms}
+    # the kernel is 64 DFMA per output sample: sample clock and power while it runs back to back (a pure FP64 stream sits at
+    # the 1 kW power cap, so the clock it really runs at matters for the FP64-pipe fraction)
+    cs = ClockSampler(torch.cuda.current_device())
+    cs.start()
+    time.sleep(0.2)
+    mark = cs.mark()
+    t0 = time.perf_counter()
+    reps = 0
+    while time.perf_counter() - t0 < 1.0:
+        for _ in range(20):
+            lib.adsp_direct_batch_device(ctx.handle, x.data_ptr(), n, n, k.data_ptr(), m, 0, ch, y.data_ptr(), n + m - 1, 0)
+        ctx.sync()
+        reps += 20
+    sus_ms = (time.perf_counter() - t0) / reps * 1e3
+    cl = cs.summary(mark)
+    cs.stop()
+    dfma_per_s = ch * (n + m - 1) * m / (sus_ms * 1e-3)
+    out["config2_direct_64tap"] = {"channels": ch, "samples_per_s": sps, "hbm_frac": sps * 16 / 1e9 / peak, "ms": ms,
+                                   "sustained_1s": {"ms": sus_ms, "samples_per_s": ch * (n + m - 1) / sus_ms * 1e3, "sm_mhz_median": cl["sm_mhz"],
+                                                    "power_w_max": cl["power_w_max"], "reasons": cl["reasons"], "dfma_per_s": dfma_per_s,
+                                                    "dfma_per_clk_per_sm": (dfma_per_s / (cl["sm_mhz"] * 1e6) / 148) if cl["sm_mhz"] else None}}
     del x, y
     # config 3: long-IR reverb shape, 8 of the 64 channels x 14.4 M samples, 288k taps
     ch, n, K = 8, 14_400_000, 288_000
