@@ -428,6 +428,10 @@ static adsp_status plan_run_host(adsp_plan *p, const T *in, long long n, long lo
     }
     constexpr int NS = kPipeSlots;
     StagePool *pool = staged ? stage_pool(ctx) : nullptr;
+    // Flushing the pinned slot's lines after the stage-out read (see staging.cu) takes a mono call from 1.0 to 0.35 ms, but
+    // costs the bulk pipeline 15 % (39.7 -> 45.9 ms per 2.2 GB step: with 32 MB chunks the inbound DMA mostly lands in lines
+    // that have left the caches anyway, and the flushes compete with the copies): off here, on in the small-call path.
+    static const bool flush_pipe = env_ll("ADSP_STAGE_FLUSH_PIPE", 0) != 0;
     for (int s = 0; s < NS; s++) {
         ADSP_TRY(ctx->pipe_in[s].reserve((size_t)dis * cc * sizeof(T)));
         ADSP_TRY(ctx->pipe_out[s].reserve((size_t)dos * cc * sizeof(T)));
@@ -484,7 +488,7 @@ static adsp_status plan_run_host(adsp_plan *p, const T *in, long long n, long lo
             const int s = (int)(j % NS);
             ADSP_CUDA(cudaEventSynchronize(ctx->ev_out[s]));
             tk_out[s] = pool->copy2d_async(out + chunk_c0(j) * out_stride, (size_t)out_stride * sizeof(T), ctx->h_out[s].p, (size_t)out_len * sizeof(T),
-                                           (size_t)out_len * sizeof(T), (size_t)chunk_nc(j));
+                                           (size_t)out_len * sizeof(T), (size_t)chunk_nc(j), flush_pipe);
         }
     }
     for (int s = 0; s < NS; s++) pool->wait(tk_out[s]);
@@ -579,6 +583,7 @@ void adsp_ctx_destroy(adsp_ctx *c) {
     cudaDeviceSynchronize();
     for (auto &kv : c->tw_tables) cudaFree(kv.second);
     for (auto &kv : c->tw4_tables) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
+    c->spec_cache.release();
     c->scratch.release(); c->d_in.release(); c->d_out.release(); c->d_k.release(); c->d_tmp.release(); c->d_small.release(); c->d_counters.release();
     c->pool.reset();
     for (int i = 0; i < kPipeSlots; i++) {
@@ -1018,9 +1023,15 @@ adsp_status correlate_batch_dev(adsp_ctx *ctx, const T *a, int64_t n, int64_t a_
             struct Seg { Segment sg; FftConv<T> fc; };
             std::vector<Seg> segs;
             adsp_status st = ADSP_OK;
-            for (const Segment &sg : plan_segments(out_len, m, big)) {
+            const std::vector<Segment> cover = plan_segments(out_len, m, big);
+            size_t spec_elems = 0;
+            for (const Segment &sg : cover) spec_elems += (size_t)sg.N;
+            ADSP_TRY(ctx->spec_cache.reserve(spec_elems * sizeof(cpx<T>)));   // the spectra live in the context's cache: no cudaMalloc / cudaFree per call
+            cpx<T> *hc = (cpx<T> *)ctx->spec_cache.p;
+            for (const Segment &sg : cover) {
                 segs.push_back({sg, FftConv<T>()});
-                st = segs.back().fc.init(ctx, dk, m, make_choice(m, sg.N));
+                st = segs.back().fc.init(ctx, dk, m, make_choice(m, sg.N), hc);
+                hc += sg.N;
                 if (st != ADSP_OK) break;
             }
             const int64_t tstride = ((out_len + 31) / 32) * 32;
@@ -1037,8 +1048,7 @@ adsp_status correlate_batch_dev(adsp_ctx *ctx, const T *a, int64_t n, int64_t a_
                 }
                 if (st == ADSP_OK && want_peaks) st = peak_device<T>(ctx, o, out_len, os, np, peak_v + c0, peak_i + c0);
             }
-            if (st == ADSP_OK && cudaStreamSynchronize(ctx->main) != cudaSuccess) st = ADSP_ERR_CUDA;   // the spectra are freed below
-            for (Seg &sgm : segs) sgm.fc.destroy();
+            for (Seg &sgm : segs) sgm.fc.destroy();          // (the spectra stay in the context's cache: nothing to wait for)
             return st;
         }
     }

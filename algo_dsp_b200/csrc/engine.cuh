@@ -74,11 +74,12 @@ public:
     ~StagePool();
     int threads() const { return (int)workers_.size(); }
     // copies `rows` rows of `width` bytes (row pitches in bytes), split into slices run by the pool; returns at once
-    Ticket copy2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows);
+    // flush_src: evict every source line from the CPU caches once read (stage-out: the source is the next DMA target)
+    Ticket copy2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows, bool flush_src = false);
     void wait(const Ticket &t);          // the waiting thread helps: it runs queued slices until its job is done
     void copy2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows) { wait(copy2d_async(dst, dpitch, src, spitch, width, rows)); }
 private:
-    struct Slice { char *dst; const char *src; size_t dpitch, spitch, width, rows; Ticket job; };
+    struct Slice { char *dst; const char *src; size_t dpitch, spitch, width, rows; Ticket job; bool flush_src = false; };
     void run();
     static void exec(Slice &s);
     std::vector<std::thread> workers_;
@@ -123,6 +124,7 @@ struct adsp_ctx {
     std::map<std::pair<int, int>, std::pair<void *, void *>> tw4_tables;  // (lgN, prec) -> (hi, lo)
     adsp::DevBuf scratch;              // four-step intermediates (L2 resident by construction)
     adsp::DevBuf d_in, d_out, d_k, d_tmp, d_small, d_counters;
+    adsp::DevBuf spec_cache;           // spectra of transient convolvers (one-shot calls, shared-b correlation): no cudaMalloc / cudaFree per call
     adsp::PinnedBuf h_in[adsp::kPipeSlots], h_out[adsp::kPipeSlots];   // pinned staging of pageable caller memory
     std::unique_ptr<adsp::StagePool> pool;                               // copy threads (created on the first pageable call)
     // host-path profile (adsp_ctx_host_profile): ms of {stage-in, H2D, kernels, D2H, stage-out, total} of the last small call
@@ -161,8 +163,10 @@ template <typename T> struct FftConv {
     cpx<T> *H = nullptr;  // cached spectrum (four-step order, scaled 1/N)
     const cpx<T> *tw_rows = nullptr, *tw_cols = nullptr, *tw_hi = nullptr, *tw_lo = nullptr;
     bool no_discard = false;  // next run(): single zero-padded block, D = 0, S = N (set by the caller per segment)
+    bool owns_H = true;       // false: H lives in a buffer of the caller (transient convolvers reuse the context's spectrum cache)
 
-    adsp_status init(adsp_ctx *c, const T *d_kernel, long long K_, const FftChoice &choice);
+    // H_ext != nullptr: build the spectrum into that buffer (ch.N complex elements) instead of allocating one
+    adsp_status init(adsp_ctx *c, const T *d_kernel, long long K_, const FftChoice &choice, cpx<T> *H_ext = nullptr);
     void destroy();
     // y[ch][out_shift + o] (=|+=) conv(x[ch], h)[o + in_shift'], see ConvGeom
     adsp_status run(const T *d_x, long long n, long long channels, long long in_stride, T *d_y,

@@ -759,12 +759,13 @@ static adsp_status launch_fused(adsp_ctx *ctx, int N1, int N2, const ConvGeom &g
 
 // ------------------------------------------------------------------ FftConv
 template <typename T>
-adsp_status FftConv<T>::init(adsp_ctx *c, const T *d_kernel, long long K_, const FftChoice &choice) {
+adsp_status FftConv<T>::init(adsp_ctx *c, const T *d_kernel, long long K_, const FftChoice &choice, cpx<T> *H_ext) {
     ctx = c;
     K = K_;
     ch = choice;
     const size_t hbytes = (size_t)ch.N * sizeof(cpx<T>);
-    ADSP_CUDA(cudaMalloc((void **)&H, hbytes));
+    if (H_ext) { H = H_ext; owns_H = false; }
+    else ADSP_CUDA(cudaMalloc((void **)&H, hbytes));
     ADSP_TRY(get_tw_table<T>(ctx, ch.N2, &tw_rows));
     // geometry that presents the kernel as one zero-padded block (im part absent -> 0)
     ConvGeom g{};
@@ -788,7 +789,7 @@ adsp_status FftConv<T>::init(adsp_ctx *c, const T *d_kernel, long long K_, const
 }
 
 template <typename T> void FftConv<T>::destroy() {
-    if (H) cudaFree(H);
+    if (H && owns_H) cudaFree(H);
     H = nullptr;
     if (fused.d_order) cudaFree(fused.d_order);
     fused.d_order = nullptr;
@@ -931,9 +932,13 @@ adsp_status fft_convolve_device(adsp_ctx *ctx, const T *d_x, long long n, long l
                                 const T *d_k, long long K, T *d_y, long long out_stride) {
     const FftChoice ch = choose_fft(K);
     const long long out_len = n + K - 1;
+    // the spectrum of a one-shot call lives in the context's cache buffer: no cudaMalloc / cudaFree (a device-wide
+    // synchronisation, with millisecond spikes) per call
+    ADSP_TRY(ctx->spec_cache.reserve((size_t)ch.N * sizeof(cpx<T>)));
+    cpx<T> *Hc = (cpx<T> *)ctx->spec_cache.p;
     if (ch.parts == 1) {
         FftConv<T> fc;
-        adsp_status st = fc.init(ctx, d_k, K, ch);
+        adsp_status st = fc.init(ctx, d_k, K, ch, Hc);
         if (st == ADSP_OK) st = fc.run(d_x, n, channels, in_stride, d_y, out_stride, out_len, 0, 0, false);
         if (st == ADSP_OK) { cudaError_t e = cudaStreamSynchronize(ctx->main); if (e != cudaSuccess) st = cuda_fail(e, "sync", __FILE__, __LINE__); }
         fc.destroy();
@@ -946,7 +951,7 @@ adsp_status fft_convolve_device(adsp_ctx *ctx, const T *d_x, long long n, long l
         const long long kp = (K - k0 < ch.part_len) ? (K - k0) : ch.part_len;
         if (kp <= 0) break;
         FftConv<T> fc;
-        adsp_status st = fc.init(ctx, d_k + k0, kp, ch);
+        adsp_status st = fc.init(ctx, d_k + k0, kp, ch, Hc);
         if (st == ADSP_OK) st = fc.run(d_x, n, channels, in_stride, d_y, out_stride, n + kp - 1, 0, k0, true);
         if (st == ADSP_OK) { cudaError_t e = cudaStreamSynchronize(ctx->main); if (e != cudaSuccess) st = cuda_fail(e, "sync", __FILE__, __LINE__); }
         fc.destroy();

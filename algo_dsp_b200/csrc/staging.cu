@@ -86,20 +86,46 @@ __attribute__((target("avx2"))) static void stream_copy_avx2(char *dst, const ch
     _mm_sfence();
     if (i < n) memcpy(dst + i, src + i, n - i);
 }
+// Stage-OUT variant (pinned slot -> caller memory): the same streaming copy, and every source line is flushed from the CPU
+// caches once it has been read.  The slot is the target of the NEXT device-to-host DMA; lines the copy threads left in
+// their caches make that DMA 6x slower (measured on the B200 host, 4.6 MB: 0.61 ms against 0.09 ms into memory no CPU has
+// touched -- every inbound write has to invalidate the cached copies first).
+__attribute__((target("avx2,clflushopt"))) static void stream_copy_flush_avx2(char *dst, const char *src, size_t n) {
+    const size_t head = (64 - ((uintptr_t)src & 63)) & 63;          // align the SOURCE to cache lines here (it is the one flushed)
+    if (head) { const size_t h = head < n ? head : n; memcpy(dst, src, h); _mm_clflushopt((void *)src); dst += h; src += h; n -= h; }
+    size_t i = 0;
+    const bool dst_al = (((uintptr_t)dst) & 31) == 0;
+    for (; i + 64 <= n; i += 64) {
+        const __m256i a = _mm256_load_si256((const __m256i *)(src + i)), b = _mm256_load_si256((const __m256i *)(src + i + 32));
+        if (dst_al) { _mm256_stream_si256((__m256i *)(dst + i), a); _mm256_stream_si256((__m256i *)(dst + i + 32), b); }
+        else { _mm256_storeu_si256((__m256i *)(dst + i), a); _mm256_storeu_si256((__m256i *)(dst + i + 32), b); }
+        _mm_clflushopt((void *)(src + i));
+    }
+    if (i < n) { memcpy(dst + i, src + i, n - i); _mm_clflushopt((void *)(src + i)); }
+    _mm_sfence();
+}
+static bool cpu_has_clflushopt() {
+    unsigned a = 7, b = 0, c = 0, d = 0;   // leaf 7, sub-leaf 0
+    __asm__ __volatile__("cpuid" : "+a"(a), "=b"(b), "+c"(c), "=d"(d));
+    return (b >> 23) & 1;                                           // CPUID.(EAX=7,ECX=0):EBX bit 23
+}
 static const bool g_use_stream_copy = __builtin_cpu_supports("avx2") && env_ll("ADSP_STAGE_NT", 1) != 0;
+static const bool g_use_flush = __builtin_cpu_supports("avx2") && cpu_has_clflushopt() && env_ll("ADSP_STAGE_FLUSH", 1) != 0;
 #else
-static const bool g_use_stream_copy = false;
+static const bool g_use_stream_copy = false, g_use_flush = false;
 static void stream_copy_avx2(char *, const char *, size_t) {}
+static void stream_copy_flush_avx2(char *, const char *, size_t) {}
 #endif
 
-static inline void bulk_copy(char *dst, const char *src, size_t n) {
-    if (g_use_stream_copy && n >= 4096) stream_copy_avx2(dst, src, n);
+static inline void bulk_copy(char *dst, const char *src, size_t n, bool flush_src) {
+    if (flush_src && g_use_flush && n >= 64) stream_copy_flush_avx2(dst, src, n);
+    else if (g_use_stream_copy && n >= 4096) stream_copy_avx2(dst, src, n);
     else memcpy(dst, src, n);
 }
 
 void StagePool::exec(Slice &s) {
-    if (s.dpitch == s.width && s.spitch == s.width) bulk_copy(s.dst, s.src, s.width * s.rows);
-    else for (size_t r = 0; r < s.rows; r++) bulk_copy(s.dst + r * s.dpitch, s.src + r * s.spitch, s.width);
+    if (s.dpitch == s.width && s.spitch == s.width) bulk_copy(s.dst, s.src, s.width * s.rows, s.flush_src);
+    else for (size_t r = 0; r < s.rows; r++) bulk_copy(s.dst + r * s.dpitch, s.src + r * s.spitch, s.width, s.flush_src);
     if (s.job->remaining.fetch_sub(1, std::memory_order_acq_rel) == 1) {
         std::lock_guard<std::mutex> lk(s.job->m);
         s.job->cv.notify_all();
@@ -120,7 +146,7 @@ void StagePool::run() {
     }
 }
 
-StagePool::Ticket StagePool::copy2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows) {
+StagePool::Ticket StagePool::copy2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows, bool flush_src) {
     Ticket job = std::make_shared<Job>();
     if (rows == 0 || width == 0) return job;
     // slices of about 256 KiB, at most 8 per worker per job (tiny copies must not pay for the queue, large ones balance)
@@ -131,14 +157,14 @@ StagePool::Ticket StagePool::copy2d_async(void *dst, size_t dpitch, const void *
     if (rows >= nsl) {                       // split by rows
         const size_t per = (rows + nsl - 1) / nsl;
         for (size_t r0 = 0; r0 < rows; r0 += per)
-            sl.push_back({(char *)dst + r0 * dpitch, (const char *)src + r0 * spitch, dpitch, spitch, width, std::min(per, rows - r0), job});
+            sl.push_back({(char *)dst + r0 * dpitch, (const char *)src + r0 * spitch, dpitch, spitch, width, std::min(per, rows - r0), job, flush_src});
     } else {                                 // few long rows: split every row by columns (64-byte aligned cuts)
         const size_t per_row = (nsl + rows - 1) / rows;
         size_t seg = (width + per_row - 1) / per_row;
         seg = (seg + 63) & ~(size_t)63;
         for (size_t r = 0; r < rows; r++)
             for (size_t c0 = 0; c0 < width; c0 += seg)
-                sl.push_back({(char *)dst + r * dpitch + c0, (const char *)src + r * spitch + c0, 0, 0, std::min(seg, width - c0), 1, job});
+                sl.push_back({(char *)dst + r * dpitch + c0, (const char *)src + r * spitch + c0, 0, 0, std::min(seg, width - c0), 1, job, flush_src});
         for (auto &s : sl) { s.dpitch = s.width; s.spitch = s.width; }
     }
     job->remaining.store((long long)sl.size(), std::memory_order_release);
@@ -272,7 +298,7 @@ adsp_status download2d(adsp_ctx *ctx, void *dst_host, size_t dpitch, const void 
             ADSP_CUDA(cudaEventSynchronize(ctx->ev_out[s]));
             if (ctx->host_profile) ctx->host_prof_ms[7] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - c0).count();
             const Piece &pc = pieces[j];
-            tk[s] = pool->copy2d_async(pc.h, pc.r == 1 ? pc.w : pc.hp, ctx->h_out[s].p, pc.w, pc.w, pc.r);
+            tk[s] = pool->copy2d_async(pc.h, pc.r == 1 ? pc.w : pc.hp, ctx->h_out[s].p, pc.w, pc.w, pc.r, true);
         }
     }
     const auto c1 = std::chrono::steady_clock::now();
