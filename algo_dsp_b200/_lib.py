@@ -83,6 +83,8 @@ PROTOTYPES = {
     "adsp_resampler_process_device": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, C.POINTER(c_i64)]),
     "adsp_resampler_reset": (None, [c_vp]),
     "adsp_resampler_destroy": (None, [c_vp]),
+    "adsp_host_register": (C.c_int, [c_vp, C.c_size_t]),
+    "adsp_host_unregister": (C.c_int, [c_vp]),
     "adsp_host_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(c_vp)]),
     "adsp_host_free_pinned": (None, [c_vp]),
     "adsp_device_alloc": (C.c_int, [c_vp, C.c_size_t, C.POINTER(c_vp)]),

@@ -658,6 +658,20 @@ adsp_status adsp_host_alloc_pinned(size_t bytes, void **out) {
 }
 void adsp_host_free_pinned(void *p) { if (p) cudaFreeHost(p); }
 
+// In-place pinning of caller memory the caller keeps alive (a long-lived Go slice held by a runtime.Pinner, a C buffer):
+// afterwards every host-pointer call DMAs from / to it directly, like memory from adsp_host_alloc_pinned.  The range MUST be
+// unregistered before it is freed or moved.
+adsp_status adsp_host_register(void *p, size_t bytes) {
+    if (!p || bytes == 0) return ADSP_ERR_INVALID_ARG;
+    ADSP_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return ADSP_OK;
+}
+adsp_status adsp_host_unregister(void *p) {
+    if (!p) return ADSP_ERR_INVALID_ARG;
+    ADSP_CUDA(cudaHostUnregister(p));
+    return ADSP_OK;
+}
+
 adsp_status adsp_device_alloc(adsp_ctx *c, size_t bytes, void **out) {
     if (!c || !out) return ADSP_ERR_INVALID_ARG;
     ADSP_CUDA(cudaSetDevice(c->device));

@@ -100,6 +100,11 @@ ADSP_API int adsp_ctx_stage_threads(adsp_ctx *ctx);      /* size of the context'
 /* Pinned host memory for callers that want zero-copy DMA (Go side: C.malloc replacement). */
 ADSP_API adsp_status adsp_host_alloc_pinned(size_t bytes, void **out);
 ADSP_API void adsp_host_free_pinned(void *p);
+/* Pin caller-owned memory in place (cudaHostRegister): host-pointer calls then DMA from / to it directly instead of staging.
+ * For buffers the caller keeps alive and in place (Go: a slice held by runtime.Pinner for the lifetime of the
+ * registration); must be unregistered before the memory is freed. */
+ADSP_API adsp_status adsp_host_register(void *p, size_t bytes);
+ADSP_API adsp_status adsp_host_unregister(void *p);
 ADSP_API adsp_status adsp_device_alloc(adsp_ctx *ctx, size_t bytes, void **out);
 ADSP_API void adsp_device_free(adsp_ctx *ctx, void *p);
 ADSP_API adsp_status adsp_memcpy_h2d(adsp_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);

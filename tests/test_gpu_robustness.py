@@ -200,3 +200,26 @@ def test_partitioned_nan_stays_local(conv):
     bad = np.isnan(y)
     assert bad[i0 + lat: i0 + lat + K].all()
     assert not bad[: i0 + lat - 4096].any() and not bad[i0 + lat + K + 8192:].any()
+
+
+def test_host_register_makes_caller_memory_dma_able(conv, oracle):
+    """adsp_host_register pins ordinary caller memory in place: the call then takes the direct DMA path (nothing staged)."""
+    ctx = conv.Context(0)
+    h, x = G.decaying_ir(20000), G.white(300000, seed=8)
+    y = np.empty(x.size + h.size - 1)
+    lib = L.load()
+    assert lib.adsp_host_ptr_is_pinned(C.c_void_p(x.ctypes.data)) == 0
+    assert lib.adsp_host_register(C.c_void_p(x.ctypes.data), x.nbytes) == L.OK
+    assert lib.adsp_host_register(C.c_void_p(y.ctypes.data), y.nbytes) == L.OK
+    try:
+        assert lib.adsp_host_ptr_is_pinned(C.c_void_p(x.ctypes.data)) == 1
+        plan = conv.OverlapSave(h, 0, ctx=ctx)
+        before = ctx.host_profile_get()
+        plan.ProcessTo(y, x)
+        after = ctx.host_profile_get()
+        assert after["staged_in_bytes"] == before["staged_in_bytes"] and after["staged_out_bytes"] == before["staged_out_bytes"]
+        assert G.rel_l2(y, oracle.overlap_save(h, 0, x)) <= 1e-12
+        plan.Close()
+    finally:
+        assert lib.adsp_host_unregister(C.c_void_p(x.ctypes.data)) == L.OK
+        assert lib.adsp_host_unregister(C.c_void_p(y.ctypes.data)) == L.OK
