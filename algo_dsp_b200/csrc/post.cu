@@ -34,13 +34,26 @@ __global__ void __launch_bounds__(SCH_THREADS) sch_tile_energy(const double *__r
     }
     if (threadIdx.x == 0) tsum[(long long)blockIdx.y * tiles + blockIdx.x] = sh[0];
 }
-// pass 2: per row, energy BEHIND every tile (exclusive suffix sum over tiles, last tile first) and the total
-__global__ void sch_tile_suffix(double *__restrict__ tsum, long long tiles, double *__restrict__ total) {
-    if (threadIdx.x != 0) return;
+// pass 2: per row, energy BEHIND every tile (exclusive suffix sum over tiles, last tile first) and the total.  One CTA per
+// row: thread t owns a contiguous run of tiles (its own suffix sums first, then an exclusive suffix scan over the runs).
+__global__ void __launch_bounds__(256) sch_tile_suffix(double *__restrict__ tsum, long long tiles, double *__restrict__ total) {
+    __shared__ double sh[256];
     double *t = tsum + (long long)blockIdx.x * tiles;
+    const long long per = (tiles + 255) / 256;
+    const long long lo = (long long)threadIdx.x * per, hi = lo + per < tiles ? lo + per : tiles;
     double acc = 0.0;
-    for (long long b = tiles - 1; b >= 0; b--) { const double e = t[b]; t[b] = acc; acc = ADSP_ADD(acc, e); }
-    total[blockIdx.x] = acc;
+    for (long long b = hi - 1; b >= lo; b--) acc = ADSP_ADD(acc, t[b]);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int d = 1; d < 256; d <<= 1) {                      // inclusive suffix scan over the threads' runs
+        const double add = ((int)threadIdx.x + d < 256) ? sh[threadIdx.x + d] : 0.0;
+        __syncthreads();
+        sh[threadIdx.x] = ADSP_ADD(sh[threadIdx.x], add);
+        __syncthreads();
+    }
+    double behind = (threadIdx.x + 1 < 256) ? sh[threadIdx.x + 1] : 0.0;
+    if (threadIdx.x == 0) total[blockIdx.x] = sh[0];
+    for (long long b = hi - 1; b >= lo; b--) { const double e = t[b]; t[b] = behind; behind = ADSP_ADD(behind, e); }
 }
 // pass 3: backward cumulative energy inside the tile + energy behind it, normalised, in dB (ir.go:117-127)
 __global__ void __launch_bounds__(SCH_THREADS) sch_emit(const double *__restrict__ x, long long n, long long stride, long long tiles, const double *__restrict__ tsuf,
@@ -255,7 +268,7 @@ adsp_status adsp_ir_schroeder_device(adsp_ctx *ctx, const double *ir_dev, int64_
     double *tsum = (double *)ctx->d_tmp.p, *total = tsum + rows * tiles;
     dim3 grid((unsigned)tiles, (unsigned)rows);
     sch_tile_energy<<<grid, SCH_THREADS, 0, ctx->main>>>(ir_dev, n, stride, tiles, tsum);
-    sch_tile_suffix<<<(unsigned)rows, 32, 0, ctx->main>>>(tsum, tiles, total);
+    sch_tile_suffix<<<(unsigned)rows, 256, 0, ctx->main>>>(tsum, tiles, total);
     sch_emit<<<grid, SCH_THREADS, 0, ctx->main>>>(ir_dev, n, stride, tiles, tsum, total, out_dev, out_stride);
     count_launch(ctx, 3);
     ADSP_CUDA(cudaGetLastError());

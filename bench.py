@@ -316,6 +316,56 @@ def other_configs(torch, conv, G, ctx, stream):
     o = torch.empty((probs, n - m + 1), device="cuda", dtype=torch.float64)
     ms = timeit(lambda: lib.adsp_deconvolve_batch_device(ctx.handle, sig.data_ptr(), n, n, ker.data_ptr(), m, 0, probs, C.c_double(1e-6),
                                                          o.data_ptr(), n - m + 1), iters=3)
+    del sig, o
+    # the optional fp32 mode on the headline workload (north star: fp32 within 1e-5): same channels, same IR, float inputs
+    ch32 = CHANNELS_PER_GPU
+    x32 = torch.empty((ch32, N_SAMPLES), device="cuda", dtype=torch.float32)
+    G.white_device(ctx, x32.data_ptr(), N_SAMPLES, ch32, N_SAMPLES, amp=1.0, seed0=1, seed_step=1, prec=1)
+    ctx.sync()
+    os32 = (OUT_LEN + 31) // 32 * 32
+    y32 = torch.empty((ch32, os32), device="cuda", dtype=torch.float32)
+    h64 = G.decaying_ir(K_TAPS)
+    p32 = conv.OverlapSave(h64, 0, ctx=ctx, dtype=np.float32)
+    ms32 = timeit(lambda: p32.process_device(x32.data_ptr(), N_SAMPLES, ch32, N_SAMPLES, y32.data_ptr(), os32), iters=10)
+    sps32 = ch32 * OUT_LEN / ms32 * 1e3
+    out["headline_fp32_mode"] = {"channels": ch32, "samples_per_s": sps32, "ms": ms32, "hbm_frac": sps32 * 8 / 1e9 / peak,
+                                 "algorithmic_bytes_per_sample": 8}
+    p32.Close()
+    del x32, y32
+    # the step after the path, device resident: Schroeder integral + onset of 64 IRs of 2^21 samples, a 257-tap
+    # block FIR and a 160/147 polyphase resampler over 64 channels x 2^20 samples
+    rows_p, n_p = 64, 1 << 21
+    irs = gen_white(rows_p, n_p, 500)
+    sch = torch.empty((rows_p, n_p), device="cuda", dtype=torch.float64)
+    idx = torch.empty(rows_p, device="cuda", dtype=torch.int64)
+    ms_s = timeit(lambda: lib.adsp_ir_schroeder_device(ctx.handle, irs.data_ptr(), n_p, rows_p, n_p, sch.data_ptr(), n_p))
+    ms_o = timeit(lambda: lib.adsp_ir_find_impulse_start_device(ctx.handle, irs.data_ptr(), n_p, rows_p, n_p, C.c_double(0.1), idx.data_ptr()))
+    post = {"schroeder_64x2e21": {"ms": ms_s, "GBps": rows_p * n_p * 16 / ms_s / 1e6, "hbm_frac": rows_p * n_p * 16 / ms_s / 1e6 / peak},
+            "impulse_start_64x2e21": {"ms": ms_o, "GBps": rows_p * n_p * 8 / ms_o / 1e6}}
+    del sch
+    n_f = 1 << 20
+    blk = irs[:, :n_f].contiguous()
+    fh = C.c_void_p()
+    taps = np.hanning(257)
+    taps /= taps.sum()
+    assert lib.adsp_fir_create(ctx.handle, taps.ctypes.data_as(C.c_void_p), 257, rows_p, C.byref(fh)) == 0
+    ms_f = timeit(lambda: lib.adsp_fir_process_block_device(fh, blk.data_ptr(), n_f, n_f))
+    post["fir_257tap_64x2e20"] = {"ms": ms_f, "samples_per_s": rows_p * n_f / ms_f * 1e3}
+    lib.adsp_fir_destroy(fh)
+    rh = C.c_void_p()
+    assert lib.adsp_resampler_create(ctx.handle, 160, 147, 1, 0, C.c_double(0), C.c_double(0), rows_p, C.byref(rh)) == 0
+    n_r = int(lib.adsp_resampler_predict_output_len(rh, n_f))
+    ro = torch.empty((rows_p, n_r + 64), device="cuda", dtype=torch.float64)
+    got = C.c_int64()
+
+    def rs():
+        lib.adsp_resampler_reset(rh)
+        assert lib.adsp_resampler_process_device(rh, blk.data_ptr(), n_f, n_f, ro.data_ptr(), n_r + 64, n_r + 64, C.byref(got)) == 0
+    ms_r = timeit(rs)
+    post["resample_160_147_64x2e20"] = {"ms": ms_r, "output_samples_per_s": rows_p * n_r / ms_r * 1e3, "taps_per_phase": int(lib.adsp_resampler_taps_per_phase(rh))}
+    lib.adsp_resampler_destroy(rh)
+    out["post_path"] = post
+    del irs, blk, ro
     out["deconvolve_regularized"] = {"problems": probs, "samples": n, "kernel_taps": m, "problems_per_s": probs / ms * 1e3,
                                      "algorithmic_GBps": probs * (2 * n - m + 1 + m) * 8 / ms / 1e6, "ms": ms}
     return out
