@@ -90,21 +90,17 @@ template <typename T> __device__ __forceinline__ TileOut<T> tile_out(const Block
 
 // CTA shapes (compile-time knobs; tools/ builds variants with -D to A/B them on the GPU).
 // A row CTA owns 16 points per thread: L/16 threads per row, rows_cta_threads(L)/(L/16) rows per CTA.
-// ADSP_EXPERIMENTAL=1 additionally compiles the ping-pong and persistent fused kernels (both measured
-// slower than the default path on B200); they need 256-thread tiles.
-#ifndef ADSP_EXPERIMENTAL
-#define ADSP_EXPERIMENTAL 0
-#endif
+// (Round 1 also carried ping-pong, persistent fused, stage-merged, prefetching and interleaved variants of these kernels;
+// all were measured slower and have been removed -- results and artefacts in DESIGN.md section 7.)
 #ifndef ADSP_H_DIRECT
 #define ADSP_H_DIRECT 0
 #endif
 #ifndef ADSP_ROWS_SMALL_CTA
-#define ADSP_ROWS_SMALL_CTA (ADSP_EXPERIMENTAL ? 0 : 1)
+#define ADSP_ROWS_SMALL_CTA 1
 #endif
 #ifndef ADSP_COLS_CTA_THREADS
-#define ADSP_COLS_CTA_THREADS (ADSP_EXPERIMENTAL ? 256 : 128)
+#define ADSP_COLS_CTA_THREADS 128
 #endif
-#define ADSP_WIDE_TILES (ADSP_EXPERIMENTAL && ADSP_COLS_CTA_THREADS == 256 && !ADSP_ROWS_SMALL_CTA)
 #ifndef ADSP_MIN_CTAS_128
 #define ADSP_MIN_CTAS_128 4      // resident 128-thread CTAs per SM the register allocator must allow (4 -> 128 regs, 5 -> 102)
 #endif
@@ -115,7 +111,7 @@ constexpr int rows_min_ctas(int L) { return rows_cta_threads(L) == 128 ? ADSP_MI
 #define ADSP_MIN_CTAS_128_F32 6
 #endif
 template <typename T> constexpr int min_ctas_for(int threads, int fp64_ctas) {
-    return (sizeof(T) == 4 && threads <= 128 && !ADSP_EXPERIMENTAL) ? ((fp64_ctas + 2 > ADSP_MIN_CTAS_128_F32) ? fp64_ctas + 2 : ADSP_MIN_CTAS_128_F32) : fp64_ctas;
+    return (sizeof(T) == 4 && threads <= 128) ? ((fp64_ctas + 2 > ADSP_MIN_CTAS_128_F32) ? fp64_ctas + 2 : ADSP_MIN_CTAS_128_F32) : fp64_ctas;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -252,8 +248,7 @@ template <int N1> struct ColShape {
 };
 
 // ------------------------------------------------------------------------------------------
-// Tile bodies (device functions) shared by the stand-alone kernels, the ping-pong kernels and the
-// persistent fused kernel.  `tid` is the thread's index inside its 256-thread tile group, `gate` the
+// Tile bodies (device functions) of the stand-alone kernels.  `tid` is the thread's index inside its tile, `gate` the
 // barrier/phase policy (fft_core.cuh), `active` false for padding tiles (they run the same barrier
 // sequence on zeros and store nothing).  Scratch is read with ld.global.cg (L2 only): another CTA
 // produced it and L1 could hold stale lines from an earlier use of the same scratch slot.
@@ -494,62 +489,6 @@ fftconv_cols_inv(ConvGeom g, const cpx<T> *__restrict__ scratch, const T *__rest
 }
 
 // ------------------------------------------------------------------------------------------
-// Stage-merged kernel: ONE launch carries the row tiles of group t-1, the forward-column tiles of group
-// t and the inverse-column tiles of group t-2 (three different scratch slots).  The dependencies between
-// the three phases of a group are then plain stream order between consecutive launches, the number of
-// launches per call drops 3x (an empty 768-CTA kernel costs ~5 us on B200: tools/ubench/launch.cu), and
-// FP64-heavy row tiles share the SMs with the memory-heavy column tiles of the neighbouring groups --
-// scheduled by the hardware block scheduler, not by software tickets.
-struct StageArgs {
-    ConvGeom g;
-    long long pair0_r, pair0_cf, pair0_ci;   // first block pair of each group
-    int n_r, n_cf, n_ci;                     // tiles of each kind in this launch (rows first: longest tasks)
-    int N2, lgN;
-};
-
-#if (ADSP_COLS_CTA_THREADS == 128 && ADSP_ROWS_SMALL_CTA)
-template <typename T, int N1, int L>
-__global__ void __launch_bounds__(128, ADSP_MIN_CTAS_128)
-fftconv_stages(StageArgs a, const T *__restrict__ x, T *__restrict__ y, cpx<T> *scratch_r, cpx<T> *scratch_cf,
-               const cpx<T> *scratch_ci, const cpx<T> *__restrict__ H, const cpx<T> *__restrict__ tw_rows,
-               const cpx<T> *__restrict__ tw_cols, const cpx<T> *__restrict__ tw_hi, const cpx<T> *__restrict__ tw_lo) {
-    using C = cpx<T>;
-    using CS = ColShape<N1>;
-    static_assert(CS::THREADS == 128 && rows_cta_threads(L) == 128, "stage-merged kernel uses 128-thread tiles");
-    constexpr int ROWS = 128 / FftShape<L>::TPF;
-    constexpr int BUF_ELEMS = (ROWS * L > CS::SMEM_ELEMS) ? ROWS * L : CS::SMEM_ELEMS;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    C *buf = reinterpret_cast<C *>(smem_raw);
-    C *stw = buf + BUF_ELEMS;
-    CtaGate gate;
-    const size_t pair_elems = (size_t)N1 * L;
-    int t = blockIdx.x;
-    if (t < a.n_r) {
-        load_tw_smem<T, L>(stw, tw_rows, threadIdx.x, 128);
-        constexpr int tiles_per_pair = N1 / ROWS;
-        const int pl = t / tiles_per_pair, tile = t - pl * tiles_per_pair;
-        rows_tile<T, L>(scratch_r + (size_t)pl * pair_elems, H, tile, buf, stw, threadIdx.x, gate, true);
-        return;
-    }
-    t -= a.n_r;
-    load_tw_smem<T, N1>(stw, tw_cols, threadIdx.x, 128);
-    constexpr int tiles_per_pair = L / CS::TC;
-    if (t < a.n_cf) {
-        const int pl = t / tiles_per_pair, tile = t - pl * tiles_per_pair;
-        cols_fwd_tile<T, N1>(a.g, x, scratch_cf + (size_t)pl * pair_elems, a.N2, a.lgN, stw, tw_hi, tw_lo, a.pair0_cf + pl, tile,
-                             buf, threadIdx.x, gate, true);
-        return;
-    }
-    t -= a.n_cf;
-    {
-        const int pl = t / tiles_per_pair, tile = t - pl * tiles_per_pair;
-        cols_inv_tile<T, N1>(a.g, scratch_ci + (size_t)pl * pair_elems, x, y, a.N2, a.lgN, stw, tw_hi, tw_lo, a.pair0_ci + pl, tile,
-                             buf, threadIdx.x, gate, true);
-    }
-}
-#endif
-
-// ------------------------------------------------------------------------------------------
 // Pairwise FFT correlation (correlate.go:16-28 evaluated as one transform per pair instead of a
 // generic long-kernel convolution): z = a + i*reverse(b) -> Z; for real a, b
 //     FFT(a)*FFT(rev b) = (Z[k]^2 - conj(Z[N-k])^2) / (4i),
@@ -590,45 +529,6 @@ corr_cols_fwd(const T *__restrict__ a, long long n, long long a_stride, const T 
     C *dst = scratch + (size_t)blockIdx.y * ((size_t)N1 * N2) + n2;
 #pragma unroll
     for (int r = 0; r < 16; r++) __stcg(&dst[(size_t)(j + r * TPF) * N2], e[r]);
-}
-
-// Spectral product in four-step order.  grid.y = q: pairs 2q (spectrum Z[2q]) and 2q+1 (Z[2q+1], absent when npairs is
-// odd) share one inverse transform: Q[q] <- P_A + i*P_B.  Q may alias Z when the group holds at most two pairs (a thread
-// reads all four of its inputs before it writes).  Element (k1, k2) holds Z[k1 + N1*k2]; its mirror N-k sits at
-// ((N1-k1)%N1, .).  One thread handles k and N-k.
-template <typename T>
-__global__ void corr_pointwise(const cpx<T> *Z, cpx<T> *Q, int npairs, int N1, int N2, T scale) {
-    using C = cpx<T>;
-    const long long N = (long long)N1 * N2;
-    const cpx<T> *ZA = Z + (size_t)(2 * blockIdx.y) * N;
-    const cpx<T> *ZB = (2 * (int)blockIdx.y + 1 < npairs) ? ZA + N : nullptr;
-    cpx<T> *Qq = Q + (size_t)blockIdx.y * N;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= N) return;
-    const long long k1 = idx / N2, k2 = idx - k1 * N2;
-    const long long k = k1 + (long long)N1 * k2;
-    const long long km = (N - k) & (N - 1);
-    if (k > km) return;                       // the mirror thread does both
-    const long long m1 = km & (N1 - 1), m2 = km / N1;
-    const long long midx = m1 * N2 + m2;
-    auto prod = [&](C zk, C zm) {             // (zk^2 - conj(zm)^2) / (4i) * scale
-        C r;
-        const T ar = zk.x * zk.x - zk.y * zk.y, ai = 2 * zk.x * zk.y;      // zk^2
-        const T br = zm.x * zm.x - zm.y * zm.y, bi = -2 * zm.x * zm.y;     // conj(zm)^2 = conj(zm^2)
-        const T dr = ar - br, di = ai - bi;                                  // divide by 4i: (dr + i di)/(4i) = (di - i dr)/4
-        r.x = di * (scale * (T)0.25);
-        r.y = -dr * (scale * (T)0.25);
-        return r;
-    };
-    const C pa = prod(__ldcg(&ZA[idx]), __ldcg(&ZA[midx]));
-    C pb; pb.x = 0; pb.y = 0;
-    if (ZB) pb = prod(__ldcg(&ZB[idx]), __ldcg(&ZB[midx]));
-    // Q[k] = pa + i*pb ; Q[N-k] = conj(pa) + i*conj(pb)
-    C qk, qm;
-    qk.x = pa.x - pb.y; qk.y = pa.y + pb.x;
-    qm.x = pa.x + pb.y; qm.y = -pa.y + pb.x;
-    __stcg(&Qq[idx], qk);
-    if (midx != idx) __stcg(&Qq[midx], qm);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -907,191 +807,5 @@ __global__ void deconv_tiny(const T *sig, long long n, long long s_stride, const
         op[i] = (T)(acc / N);
     }
 }
-
-#if ADSP_WIDE_TILES
-// ------------------------------------------------------------------------------------------
-// Ping-pong kernels: persistent 512-thread CTAs (one per SM); each CTA runs two tiles at a time, one
-// per 256-thread group, phase-locked by PingPongGate so the FP64 pipe and the shared-memory pipe of
-// the SM are busy simultaneously.  Tile T of the launch = (iteration*gridDim.x + blockIdx.x)*2 + group;
-// T -> (pair = T / tiles_per_pair, tile = T % tiles_per_pair).  Padding tiles keep the barrier
-// sequences of the two groups identical.
-enum { PP_COLS_FWD = 0, PP_ROWS = 1, PP_COLS_INV = 2 };
-
-template <typename T, int N1, int L, int KIND>
-__global__ void __launch_bounds__(512, 1)
-fftconv_pingpong(ConvGeom g, const T *__restrict__ x, T *__restrict__ y, cpx<T> *__restrict__ scratch,
-                 const cpx<T> *__restrict__ H, int lgN, const cpx<T> *__restrict__ tw, const cpx<T> *__restrict__ tw_hi,
-                 const cpx<T> *__restrict__ tw_lo, long long pair0, int tiles_per_pair, int ntiles) {
-    using C = cpx<T>;
-    using CS = ColShape<N1>;
-    static_assert(CS::THREADS == 256 && rows_cta_threads(L) == 256, "ping-pong groups are 256 threads");
-    constexpr int BUF_ELEMS = (KIND == PP_ROWS) ? (256 / FftShape<L>::TPF) * L : CS::SMEM_ELEMS;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int grp = threadIdx.x >> 8;
-    const int tid = threadIdx.x & 255;
-    C *buf = reinterpret_cast<C *>(smem_raw) + (size_t)grp * BUF_ELEMS;
-    C *stw = reinterpret_cast<C *>(smem_raw) + 2 * (size_t)BUF_ELEMS;
-    if (KIND == PP_ROWS) load_tw_smem<T, L>(stw, tw, threadIdx.x, 512);
-    else load_tw_smem<T, N1>(stw, tw, threadIdx.x, 512);
-    cp_async_wait_all();
-    __syncthreads();
-    PingPongGate gate(grp);
-    const size_t pair_elems = (size_t)N1 * L;
-    const int per_iter = 2 * (int)gridDim.x;
-    const int iters = (ntiles + per_iter - 1) / per_iter;
-    for (int it = 0; it < iters; it++) {
-        const int Tix = (it * (int)gridDim.x + (int)blockIdx.x) * 2 + grp;
-        const bool active = Tix < ntiles;
-        const int pl = active ? Tix / tiles_per_pair : 0;
-        const int tile = active ? Tix - pl * tiles_per_pair : 0;
-        C *sp = scratch + (size_t)pl * pair_elems;
-        if (KIND == PP_COLS_FWD) cols_fwd_tile<T, N1>(g, x, sp, L, lgN, stw, tw_hi, tw_lo, pair0 + pl, tile, buf, tid, gate, active);
-        else if (KIND == PP_ROWS) rows_tile<T, L>(sp, H, tile, buf, stw, tid, gate, active);
-        else cols_inv_tile<T, N1>(g, sp, x, y, L, lgN, stw, tw_hi, tw_lo, pair0 + pl, tile, buf, tid, gate, active);
-    }
-}
-#endif
-
-// ------------------------------------------------------------------------------------------
-// Persistent fused kernel: ONE launch runs all three phases of every block pair as a dataflow over
-// tiles.  CTAs (2 per SM) draw tickets from a global counter; ticket t maps to a task through a
-// host-built periodic order table in which, per "round", the forward-column tiles of pair m, the row
-// tiles of pairs m-2/m-1 (offset 1.5 rounds) and the inverse-column tiles of pair m-3 are interleaved,
-// so memory-latency-bound column tiles and FP64-bound row tiles share every SM, every dependency has
-// >= half a round of slack (more than the in-flight ticket window), and intermediates live in
-// `nslots` scratch slots that stay L2 resident.  A task only ever waits on smaller tickets, so the
-// scheme cannot deadlock whatever the residency.
-struct FusedParams {
-    ConvGeom g;
-    long long npairs;
-    int N2, lgN, nslots;
-    int tiles_c, tiles_r, round_len;   // column tiles, row tiles and tasks per round
-    int flags;                         // bit0: dry run (scheduling only), bit1: static ticket assignment
-    long long total_tickets;
-};
-
-enum { TASK_CF = 0, TASK_R = 1, TASK_CI = 2 };
-
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-// stats (optional, may be null): [type] = spin iterations, [4 + type] = tasks that had to wait
-__device__ __forceinline__ void wait_count(const unsigned *p, unsigned need, unsigned *stats, int type) {
-    if (threadIdx.x == 0) {
-        unsigned spins = 0;
-        while (ld_acquire_u32(p) < need) { __nanosleep(64); spins++; }
-        if (spins && stats) { atomicAdd(&stats[type], spins); atomicAdd(&stats[4 + type], 1u); }
-    }
-    __syncthreads();
-}
-
-#if ADSP_WIDE_TILES
-// order[s] = type | idx << 2 | pair_delta << 20
-template <typename T, int N1, int L>
-__global__ void __launch_bounds__(256, 2)
-fftconv_fused(FusedParams prm, const T *__restrict__ x, T *__restrict__ y, cpx<T> *__restrict__ scratch,
-              const cpx<T> *__restrict__ H, const cpx<T> *__restrict__ tw_rows, const cpx<T> *__restrict__ tw_cols,
-              const cpx<T> *__restrict__ tw_hi, const cpx<T> *__restrict__ tw_lo, const unsigned *__restrict__ order,
-              unsigned *counters /* [0] ticket, then done_cf[npairs], done_r[npairs], done_ci[npairs] */) {
-    using C = cpx<T>;
-    using CS = ColShape<N1>;
-    static_assert(CS::THREADS == 256 && rows_cta_threads(L) == 256, "fused kernel needs 256-thread tiles");
-    constexpr int ROWS = 256 / FftShape<L>::TPF;
-    constexpr int BUF_ELEMS = (ROWS * L > CS::SMEM_ELEMS) ? ROWS * L : CS::SMEM_ELEMS;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    C *buf = reinterpret_cast<C *>(smem_raw);
-    C *stw_r = buf + BUF_ELEMS;
-    C *stw_c = stw_r + FftShape<L>::TW_ENTRIES;
-    __shared__ long long s_ticket;
-    load_tw_smem<T, L>(stw_r, tw_rows, threadIdx.x, 256);
-    load_tw_smem<T, N1>(stw_c, tw_cols, threadIdx.x, 256);
-
-    unsigned *done_cf = counters + 1;
-    unsigned *done_r = done_cf + prm.npairs;
-    unsigned *done_ci = done_r + prm.npairs;
-    unsigned *stats = done_ci + prm.npairs;   // 8 words
-    const size_t pair_elems = (size_t)N1 * L;
-
-    CtaGate cgate;
-    const bool dry = (prm.flags & 1) != 0;          // scheduling only (overhead measurement)
-    const bool static_tickets = (prm.flags & 2) != 0;
-    long long t = static_tickets ? (long long)blockIdx.x : -1;
-    unsigned dep_prefetched = 0;   // thread 0: value of the next task's dependency counter, loaded a task ahead
-    bool have_prefetch = false;
-    for (;;) {
-        __syncthreads();  // previous task finished everywhere (smem + s_ticket reusable)
-        if (!static_tickets) {
-            if (threadIdx.x == 0) s_ticket = (long long)atomicAdd(&counters[0], 1u);
-            __syncthreads();
-            t = s_ticket;
-        }
-        if (t >= prm.total_tickets) break;
-        const long long round = t / prm.round_len;
-        const unsigned ent = __ldg(&order[(int)(t - round * prm.round_len)]);
-        const int type = ent & 3u;
-        const int idx = (ent >> 2) & 0x3ffffu;
-        const long long pair = round - (long long)(ent >> 20);
-        // static mode: look one task ahead and start loading its dependency counter now
-        const unsigned *dep_next = nullptr;
-        unsigned need_next = 0;
-        if (static_tickets) {
-            const long long tn = t + gridDim.x;
-            if (tn < prm.total_tickets) {
-                const long long rn = tn / prm.round_len;
-                const unsigned en = __ldg(&order[(int)(tn - rn * prm.round_len)]);
-                const int ty = en & 3u;
-                const long long pn = rn - (long long)(en >> 20);
-                if (pn >= 0 && pn < prm.npairs) {
-                    if (ty == TASK_CF) { if (pn >= prm.nslots) { dep_next = &done_ci[pn - prm.nslots]; need_next = prm.tiles_c; } }
-                    else if (ty == TASK_R) { dep_next = &done_cf[pn]; need_next = prm.tiles_c; }
-                    else { dep_next = &done_r[pn]; need_next = prm.tiles_r; }
-                }
-            }
-        }
-        const bool valid = pair >= 0 && pair < prm.npairs;
-        if (valid) {
-            C *slot = scratch + (size_t)(pair % prm.nslots) * pair_elems;
-            const unsigned *dep = nullptr;
-            unsigned need = 0;
-            if (type == TASK_CF) { if (pair >= prm.nslots) { dep = &done_ci[pair - prm.nslots]; need = prm.tiles_c; } }
-            else if (type == TASK_R) { dep = &done_cf[pair]; need = prm.tiles_c; }
-            else { dep = &done_r[pair]; need = prm.tiles_r; }
-            if (dep) {
-                if (static_tickets && have_prefetch) {
-                    // thread 0 already holds a (possibly stale) value; only poll if it was not yet complete
-                    if (threadIdx.x == 0 && dep_prefetched < need) {
-                        unsigned spins = 0;
-                        while (ld_acquire_u32(dep) < need) { __nanosleep(64); spins++; }
-                        atomicAdd(&stats[type], spins + 1); atomicAdd(&stats[4 + type], 1u);
-                    }
-                    __syncthreads();
-                } else {
-                    wait_count(dep, need, stats, type);
-                }
-            }
-            unsigned pf = 0;
-            if (dep_next && threadIdx.x == 0) pf = ld_acquire_u32(dep_next);   // consumed after the task body
-            if (!dry) {
-                if (type == TASK_CF) cols_fwd_tile<T, N1>(prm.g, x, slot, prm.N2, prm.lgN, stw_c, tw_hi, tw_lo, pair, idx, buf, threadIdx.x, cgate, true);
-                else if (type == TASK_R) rows_tile<T, L>(slot, H, idx, buf, stw_r, threadIdx.x, cgate, true);
-                else cols_inv_tile<T, N1>(prm.g, slot, x, y, prm.N2, prm.lgN, stw_c, tw_hi, tw_lo, pair, idx, buf, threadIdx.x, cgate, true);
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                __threadfence();
-                atomicAdd(type == TASK_CF ? &done_cf[pair] : (type == TASK_R ? &done_r[pair] : &done_ci[pair]), 1u);
-                dep_prefetched = pf;
-            }
-            have_prefetch = (dep_next != nullptr);
-        } else {
-            have_prefetch = false;
-        }
-        if (static_tickets) t += gridDim.x;
-    }
-}
-
-#endif
 
 }  // namespace adsp

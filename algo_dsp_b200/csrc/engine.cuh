@@ -21,11 +21,6 @@
 #include "conv_kernels.cuh"
 #include "conv_kernels_mr.cuh"
 #include "conv_kernels_mrp.cuh"
-#if ADSP_EXPERIMENTAL
-// measured-slower variants kept for the record: prefetching persistent kernels, interleaved rows
-#include "conv_kernels_pf.cuh"
-#include "conv_kernels_il.cuh"
-#endif
 
 namespace adsp {
 
@@ -148,15 +143,8 @@ struct adsp_ctx {
 
 namespace adsp {
 
-// per-engine cache of the fused kernel's task-order table
-struct FusedCache {
-    unsigned *d_order = nullptr;
-    int round_len = 0, tiles_c = 0, tiles_r = 0, nslots = 0, extra_rounds = 0, resident = 0;
-};
-
 // Device-resident FFT convolver for one (partition of an) impulse response.
 template <typename T> struct FftConv {
-    FusedCache fused;
     adsp_ctx *ctx = nullptr;
     long long K = 0;  // taps of this partition
     FftChoice ch;

@@ -361,42 +361,14 @@ __device__ __forceinline__ void load_tw_smem(cpx<T> *stw, const cpx<T> *__restri
 
 // ---------------------------------------------------------------- phase gates
 // A transform alternates FP64-pipe phases (butterflies, "D") and shared-memory phases (Stockham
-// exchanges, "L").
-//  * CtaGate: one tile per CTA, whole-CTA barriers, no gating.
-//  * PingPongGate: a 512-thread CTA runs TWO tiles, one per 256-thread group.  Named barriers hand a
-//    D token and an L token back and forth, so one group is always in a D phase while the other is
-//    in an L phase (group 1 trails group 0 by one phase): a deterministic FP64 | LSU pipeline on
-//    every SM instead of the random overlap of independent CTAs.
+// exchanges, "L").  CtaGate: one tile per CTA, whole-CTA barriers, no gating.  (The gate is a template parameter of cta_fft:
+// round 1 measured a ping-pong gate that phase-locks two tiles per CTA with named barriers -- slower)
 struct CtaGate {
     __device__ __forceinline__ void sync() { __syncthreads(); }
     __device__ __forceinline__ void d_begin() {}
     __device__ __forceinline__ void d_end() {}
     __device__ __forceinline__ void l_begin() {}
     __device__ __forceinline__ void l_end() {}
-};
-
-__device__ __forceinline__ void named_bar_sync(int id, int count) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-__device__ __forceinline__ void named_bar_arrive(int id, int count) {
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-
-struct PingPongGate {
-    // barrier ids: 1/2 group-local sync, 3 D 0->1, 4 D 1->0, 5 L 0->1, 6 L 1->0
-    int g;
-    bool first_d = true, first_l = true;
-    __device__ __forceinline__ explicit PingPongGate(int group) : g(group) {}
-    __device__ __forceinline__ void sync() { named_bar_sync(1 + g, 256); }
-    __device__ __forceinline__ void acquire(int id01, int id10, bool &first) {
-        if (g == 0) { if (!first) named_bar_sync(id10, 512); first = false; }
-        else named_bar_sync(id01, 512);
-    }
-    __device__ __forceinline__ void release(int id01, int id10) { named_bar_arrive(g == 0 ? id01 : id10, 512); }
-    __device__ __forceinline__ void d_begin() { acquire(3, 4, first_d); }
-    __device__ __forceinline__ void d_end() { release(3, 4); }
-    __device__ __forceinline__ void l_begin() { acquire(5, 6, first_l); }
-    __device__ __forceinline__ void l_end() { release(5, 6); }
 };
 
 // ---------------------------------------------------------------- the in-CTA transform

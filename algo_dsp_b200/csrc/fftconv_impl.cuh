@@ -394,369 +394,6 @@ static adsp_status launch_cols_any(adsp_ctx *ctx, cudaStream_t st, const FftChoi
     return launch_cols<T>(ctx, st, ch.N1, inverse, g, x, y, scratch, ch.N2, ch.lgN, tw, hi, lo, pair0, pairs);
 }
 
-#if ADSP_EXPERIMENTAL
-// ------------------------------------------------------------------ prefetching persistent kernels
-// grid = resident CTAs (occupancy x SMs, queried once per kernel and device), never more than tiles
-template <typename K> static adsp_status pf_grid(adsp_ctx *ctx, K kern, int threads, size_t smem, int ntiles, int *cache, int *grid) {
-    if (*cache <= 0) {
-        ADSP_TRY(set_smem(kern, smem));
-        int per_sm = 0;
-        ADSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
-        if (per_sm < 1) { set_error("prefetching kernel does not fit on an SM"); return ADSP_ERR_CUDA; }
-        *cache = per_sm;
-    }
-    const long long cap = env_ll("ADSP_PF_GRID_CTAS", 0);   // tuning: resident CTAs per SM to use
-    const int per_sm = (cap > 0 && cap < *cache) ? (int)cap : *cache;
-    const long long resident = (long long)per_sm * ctx->sm_count;
-    *grid = (int)std::min<long long>(resident, ntiles);
-    return ADSP_OK;
-}
-
-struct OccCache {
-    int v[64] = {};
-    int *at(int dev) { return &v[(dev >= 0 && dev < 64) ? dev : 0]; }
-};
-
-template <typename T, int N1>
-static adsp_status launch_cols_pf_t(adsp_ctx *ctx, cudaStream_t st, bool inverse, const ConvGeom &g, const T *x, T *y,
-                                    cpx<T> *scratch, int N2, int lgN, const cpx<T> *tw, const cpx<T> *hi, const cpx<T> *lo,
-                                    long long pair0, int pairs) {
-    using CS = ColShape<N1>;
-    using PF = ColShapePF<T, N1>;
-    static OccCache occ_f, occ_i;
-    const int ntiles = (N2 / CS::TC) * pairs;
-    int grid = 0;
-    LaunchTimer lt(ctx, st, inverse ? KK_COLS_INV : KK_COLS_FWD);
-    if (!inverse) {
-        ADSP_TRY(pf_grid(ctx, fftconv_cols_fwd_pf<T, N1>, CS::THREADS, PF::SMEM, ntiles, occ_f.at(ctx->device), &grid));
-        fftconv_cols_fwd_pf<T, N1><<<grid, CS::THREADS, PF::SMEM, st>>>(g, x, scratch, N2, lgN, tw, hi, lo, pair0, ntiles);
-    } else {
-        ADSP_TRY(pf_grid(ctx, fftconv_cols_inv_pf<T, N1>, CS::THREADS, PF::SMEM, ntiles, occ_i.at(ctx->device), &grid));
-        fftconv_cols_inv_pf<T, N1><<<grid, CS::THREADS, PF::SMEM, st>>>(g, scratch, x, y, N2, lgN, tw, hi, lo, pair0, ntiles);
-    }
-    count_launch(ctx);
-    ADSP_CUDA(cudaGetLastError());
-    return ADSP_OK;
-}
-
-template <typename T, int L>
-static adsp_status launch_rows_pf_t(adsp_ctx *ctx, cudaStream_t st, cpx<T> *scratch, const cpx<T> *H, int N1, const cpx<T> *tw,
-                                    int pairs) {
-    using PF = RowShapePF<T, L>;
-    static OccCache occ;
-    const int ntiles = (N1 / PF::ROWS) * pairs;
-    int grid = 0;
-    LaunchTimer lt(ctx, st, KK_ROWS);
-    ADSP_TRY(pf_grid(ctx, fftconv_rows_pf<T, L>, PF::THREADS, PF::SMEM, ntiles, occ.at(ctx->device), &grid));
-    fftconv_rows_pf<T, L><<<grid, PF::THREADS, PF::SMEM, st>>>(scratch, H, N1, tw, ntiles);
-    count_launch(ctx);
-    ADSP_CUDA(cudaGetLastError());
-    return ADSP_OK;
-}
-
-// shapes the prefetching kernels are instantiated for: 128-thread tiles whose exchange buffer + landing zone
-// leave room for three CTAs per SM
-static bool pf_supported(int N1, int N2) {
-    return (N1 == 16 || N1 == 32 || N1 == 64 || N1 == 128 || N1 == 256) && (N2 == 256 || N2 == 512 || N2 == 1024 || N2 == 2048) &&
-           N1 <= N2 * 8;
-}
-
-template <typename T>
-static adsp_status launch_cols_pf(adsp_ctx *ctx, cudaStream_t st, int N1, bool inverse, const ConvGeom &g, const T *x, T *y,
-                                  cpx<T> *scratch, int N2, int lgN, const cpx<T> *tw, const cpx<T> *hi, const cpx<T> *lo,
-                                  long long pair0, int pairs) {
-    switch (N1) {
-    case 16:   return launch_cols_pf_t<T, 16>(ctx, st, inverse, g, x, y, scratch, N2, lgN, tw, hi, lo, pair0, pairs);
-    case 32:   return launch_cols_pf_t<T, 32>(ctx, st, inverse, g, x, y, scratch, N2, lgN, tw, hi, lo, pair0, pairs);
-    case 64:   return launch_cols_pf_t<T, 64>(ctx, st, inverse, g, x, y, scratch, N2, lgN, tw, hi, lo, pair0, pairs);
-    case 128:  return launch_cols_pf_t<T, 128>(ctx, st, inverse, g, x, y, scratch, N2, lgN, tw, hi, lo, pair0, pairs);
-    case 256:  return launch_cols_pf_t<T, 256>(ctx, st, inverse, g, x, y, scratch, N2, lgN, tw, hi, lo, pair0, pairs);
-    default: set_error("unsupported column FFT length (prefetching path)"); return ADSP_ERR_INVALID_ARG;
-    }
-}
-
-template <typename T>
-static adsp_status launch_rows_pf(adsp_ctx *ctx, cudaStream_t st, int L, cpx<T> *scratch, const cpx<T> *H, int N1,
-                                  const cpx<T> *tw, int pairs) {
-    switch (L) {
-    case 256:  return launch_rows_pf_t<T, 256>(ctx, st, scratch, H, N1, tw, pairs);
-    case 512:  return launch_rows_pf_t<T, 512>(ctx, st, scratch, H, N1, tw, pairs);
-    case 1024: return launch_rows_pf_t<T, 1024>(ctx, st, scratch, H, N1, tw, pairs);
-    case 2048: return launch_rows_pf_t<T, 2048>(ctx, st, scratch, H, N1, tw, pairs);
-    default: set_error("unsupported row FFT length (prefetching path)"); return ADSP_ERR_INVALID_ARG;
-    }
-}
-
-// ------------------------------------------------------------------ interleaved (two tiles per thread) rows
-template <typename T, int L>
-static adsp_status launch_rows_il_t(adsp_ctx *ctx, cudaStream_t st, cpx<T> *scratch, const cpx<T> *H, int N1, const cpx<T> *tw,
-                                    int pairs) {
-    constexpr int THREADS = rows_cta_threads(L);
-    constexpr int ROWS = THREADS / FftShape<L>::TPF;
-    const size_t smem = (2 * (size_t)ROWS * L + FftShape<L>::TW_ENTRIES) * sizeof(cpx<T>);
-    static AttrOnce once;
-    if (once.need(ctx->device)) ADSP_TRY(set_smem(fftconv_rows_il<T, L>, smem));
-    const int ntiles = (N1 / ROWS) * pairs;
-    int grid = (ntiles + 1) / 2;
-    const long long k = env_ll("ADSP_IL_TILEPAIRS_PER_CTA", 1);
-    if (k > 1) grid = (int)std::max<long long>(std::min<long long>(grid, (long long)ctx->sm_count * 2), (grid + k - 1) / k);
-    LaunchTimer lt(ctx, st, KK_ROWS);
-    fftconv_rows_il<T, L><<<grid, THREADS, smem, st>>>(scratch, H, N1, tw, ntiles);
-    count_launch(ctx);
-    ADSP_CUDA(cudaGetLastError());
-    return ADSP_OK;
-}
-
-template <typename T>
-static adsp_status launch_rows_il(adsp_ctx *ctx, cudaStream_t st, int L, cpx<T> *scratch, const cpx<T> *H, int N1,
-                                  const cpx<T> *tw, int pairs) {
-    switch (L) {
-    case 1024: return launch_rows_il_t<T, 1024>(ctx, st, scratch, H, N1, tw, pairs);
-    case 2048: return launch_rows_il_t<T, 2048>(ctx, st, scratch, H, N1, tw, pairs);
-    case 4096: return launch_rows_il_t<T, 4096>(ctx, st, scratch, H, N1, tw, pairs);
-    default: set_error("unsupported row FFT length (interleaved rows)"); return ADSP_ERR_INVALID_ARG;
-    }
-}
-static bool il_supported(int N2) { return N2 == 1024 || N2 == 2048 || N2 == 4096; }
-
-#endif  // ADSP_EXPERIMENTAL
-
-// ------------------------------------------------------------------ stage-merged kernel
-#define ADSP_STAGES_AVAILABLE (ADSP_COLS_CTA_THREADS == 128 && ADSP_ROWS_SMALL_CTA)
-#if ADSP_STAGES_AVAILABLE
-template <typename T, int N1, int L>
-static adsp_status run_stages_t(adsp_ctx *ctx, const FftChoice &ch, const ConvGeom &g, long long npairs, const T *x, T *y,
-                                const cpx<T> *H, const cpx<T> *tw_rows, const cpx<T> *tw_cols, const cpx<T> *tw_hi,
-                                const cpx<T> *tw_lo) {
-    using CS = ColShape<N1>;
-    constexpr int ROWS = 128 / FftShape<L>::TPF;
-    constexpr int BUF_ELEMS = (ROWS * L > CS::SMEM_ELEMS) ? ROWS * L : CS::SMEM_ELEMS;
-    constexpr int TW = (FftShape<L>::TW_ENTRIES > FftShape<N1>::TW_ENTRIES) ? FftShape<L>::TW_ENTRIES : FftShape<N1>::TW_ENTRIES;
-    const size_t smem = ((size_t)BUF_ELEMS + TW) * sizeof(cpx<T>);
-    static AttrOnce once;
-    if (once.need(ctx->device)) ADSP_TRY(set_smem(fftconv_stages<T, N1, L>, smem));
-    const int tiles_r = N1 / ROWS, tiles_c = L / CS::TC;
-    // three groups are in flight (one per phase): three scratch slots inside the L2 budget
-    const size_t per_pair = (size_t)ch.N * sizeof(cpx<T>);
-    size_t budget = ctx->scratch_budget;
-    const long long mb = env_ll("ADSP_SCRATCH_MB", 0);
-    if (mb > 0) budget = (size_t)mb << 20;
-    long long G = (long long)(budget / 3 / per_pair);
-    if (G < 1) G = 1;
-    if (G > npairs) G = npairs;
-    ADSP_TRY(ctx->scratch.reserve(3 * (size_t)G * per_pair));
-    cpx<T> *scr = (cpx<T> *)ctx->scratch.p;
-    const long long ngroups = (npairs + G - 1) / G;
-    auto gpairs = [&](long long q) { return (int)std::min<long long>(G, npairs - q * G); };
-    auto slot = [&](long long q) { return scr + (size_t)(q % 3) * (size_t)G * (size_t)ch.N; };
-    for (long long t = 0; t < ngroups + 2; t++) {
-        StageArgs a;
-        a.g = g; a.N2 = L; a.lgN = ch.lgN;
-        const long long qcf = t, qr = t - 1, qci = t - 2;
-        a.n_cf = (qcf < ngroups) ? gpairs(qcf) * tiles_c : 0;
-        a.n_r = (qr >= 0 && qr < ngroups) ? gpairs(qr) * tiles_r : 0;
-        a.n_ci = (qci >= 0 && qci < ngroups) ? gpairs(qci) * tiles_c : 0;
-        a.pair0_cf = qcf * G; a.pair0_r = qr * G; a.pair0_ci = qci * G;
-        const int grid = a.n_r + a.n_cf + a.n_ci;
-        if (grid <= 0) continue;
-        LaunchTimer lt(ctx, ctx->main, KK_FUSED);
-        fftconv_stages<T, N1, L><<<grid, 128, smem, ctx->main>>>(a, x, y, slot(qr < 0 ? 0 : qr), slot(qcf), slot(qci < 0 ? 0 : qci), H, tw_rows,
-                                                                 tw_cols, tw_hi, tw_lo);
-        count_launch(ctx);
-    }
-    ADSP_CUDA(cudaGetLastError());
-    return ADSP_OK;
-}
-#endif
-
-template <typename T>
-static adsp_status run_stages(adsp_ctx *ctx, const FftChoice &ch, const ConvGeom &g, long long npairs, const T *x, T *y,
-                              const cpx<T> *H, const cpx<T> *tw_rows, const cpx<T> *tw_cols, const cpx<T> *tw_hi,
-                              const cpx<T> *tw_lo, bool *done) {
-    *done = true;
-#if ADSP_STAGES_AVAILABLE
-#define ADSP_ST_CASE(n1, n2) \
-    if (ch.N1 == n1 && ch.N2 == n2) return run_stages_t<T, n1, n2>(ctx, ch, g, npairs, x, y, H, tw_rows, tw_cols, tw_hi, tw_lo);
-    ADSP_ST_CASE(16, 512) ADSP_ST_CASE(16, 1024) ADSP_ST_CASE(16, 2048) ADSP_ST_CASE(32, 2048) ADSP_ST_CASE(64, 2048)
-    ADSP_ST_CASE(128, 2048) ADSP_ST_CASE(256, 2048)
-#undef ADSP_ST_CASE
-#endif
-    *done = false;
-    return ADSP_OK;
-}
-
-// ------------------------------------------------------------------ ping-pong kernels
-#define ADSP_PINGPONG_AVAILABLE ADSP_WIDE_TILES
-#if ADSP_PINGPONG_AVAILABLE
-template <typename T, int N1, int L, int KIND>
-static adsp_status launch_pp_t(adsp_ctx *ctx, cudaStream_t st, const ConvGeom &g, const T *x, T *y, cpx<T> *scratch,
-                               const cpx<T> *H, int lgN, const cpx<T> *tw, const cpx<T> *hi, const cpx<T> *lo, long long pair0,
-                               int pairs) {
-    using CS = ColShape<N1>;
-    constexpr int BUF_ELEMS = (KIND == PP_ROWS) ? (256 / FftShape<L>::TPF) * L : CS::SMEM_ELEMS;
-    constexpr int TW = (KIND == PP_ROWS) ? FftShape<L>::TW_ENTRIES : FftShape<N1>::TW_ENTRIES;
-    const size_t smem = (2 * (size_t)BUF_ELEMS + TW) * sizeof(cpx<T>);
-    static AttrOnce once;
-    if (once.need(ctx->device)) ADSP_TRY(set_smem(fftconv_pingpong<T, N1, L, KIND>, smem));
-    const int tiles_per_pair = (KIND == PP_ROWS) ? N1 / (256 / FftShape<L>::TPF) : L / CS::TC;
-    const int ntiles = tiles_per_pair * pairs;
-    int grid = (ntiles + 1) / 2;
-    if (grid > ctx->sm_count) grid = ctx->sm_count;
-    LaunchTimer lt(ctx, st, KIND == PP_ROWS ? KK_ROWS : (KIND == PP_COLS_FWD ? KK_COLS_FWD : KK_COLS_INV));
-    fftconv_pingpong<T, N1, L, KIND><<<grid, 512, smem, st>>>(g, x, y, scratch, H, lgN, tw, hi, lo, pair0, tiles_per_pair, ntiles);
-    count_launch(ctx);
-    ADSP_CUDA(cudaGetLastError());
-    return ADSP_OK;
-}
-
-template <typename T, int N1, int L>
-static adsp_status launch_pp_group(adsp_ctx *ctx, cudaStream_t st, const ConvGeom &g, const T *x, T *y, cpx<T> *scratch,
-                                   const cpx<T> *H, int lgN, const cpx<T> *tw_rows, const cpx<T> *tw_cols, const cpx<T> *hi,
-                                   const cpx<T> *lo, long long pair0, int pairs) {
-    ADSP_TRY((launch_pp_t<T, N1, L, PP_COLS_FWD>(ctx, st, g, x, y, scratch, H, lgN, tw_cols, hi, lo, pair0, pairs)));
-    ADSP_TRY((launch_pp_t<T, N1, L, PP_ROWS>(ctx, st, g, x, y, scratch, H, lgN, tw_rows, hi, lo, pair0, pairs)));
-    ADSP_TRY((launch_pp_t<T, N1, L, PP_COLS_INV>(ctx, st, g, x, y, scratch, H, lgN, tw_cols, hi, lo, pair0, pairs)));
-    return ADSP_OK;
-}
-#endif
-
-// one group (cols_fwd -> rows -> cols_inv) through the ping-pong kernels; *done=false if (N1,N2) has no instantiation
-template <typename T>
-static adsp_status launch_pp(adsp_ctx *ctx, cudaStream_t st, int N1, int N2, const ConvGeom &g, const T *x, T *y,
-                             cpx<T> *scratch, const cpx<T> *H, int lgN, const cpx<T> *tw_rows, const cpx<T> *tw_cols,
-                             const cpx<T> *hi, const cpx<T> *lo, long long pair0, int pairs, bool *done) {
-    *done = true;
-#if ADSP_PINGPONG_AVAILABLE
-#define ADSP_PP_CASE(n1, n2) \
-    if (N1 == n1 && N2 == n2) return launch_pp_group<T, n1, n2>(ctx, st, g, x, y, scratch, H, lgN, tw_rows, tw_cols, hi, lo, pair0, pairs);
-    ADSP_PP_CASE(16, 4096) ADSP_PP_CASE(32, 4096) ADSP_PP_CASE(64, 4096) ADSP_PP_CASE(128, 4096) ADSP_PP_CASE(256, 4096)
-    ADSP_PP_CASE(128, 2048) ADSP_PP_CASE(256, 2048)
-#undef ADSP_PP_CASE
-#endif
-    *done = false;
-    return ADSP_OK;
-}
-
-static bool pp_supported(int N1, int N2) {
-#if ADSP_PINGPONG_AVAILABLE
-    return (N2 == 4096 && (N1 == 16 || N1 == 32 || N1 == 64 || N1 == 128 || N1 == 256)) || (N2 == 2048 && (N1 == 128 || N1 == 256));
-#else
-    (void)N1; (void)N2;
-    return false;
-#endif
-}
-
-// ------------------------------------------------------------------ persistent fused kernel
-#define ADSP_FUSED_AVAILABLE ADSP_WIDE_TILES
-struct FusedPlan {
-    std::vector<unsigned> order;
-    int round_len = 0, tiles_c = 0, tiles_r = 0, nslots = 0, extra_rounds = 0;
-};
-
-// Periodic task order: forward-column tiles at offset 0, row tiles at offset `lag` rounds, inverse
-// column tiles at 2*lag; `lag` exceeds the in-flight ticket window so no task ever finds its
-// producers unfinished in steady state.
-static FusedPlan make_fused_plan(int tiles_c, int tiles_r, int resident_ctas) {
-    FusedPlan fp;
-    fp.tiles_c = tiles_c; fp.tiles_r = tiles_r;
-    fp.round_len = 2 * tiles_c + tiles_r;
-    const double window = (double)resident_ctas / fp.round_len;
-    // producers of a pair span one full round, so consumers must trail by a round plus the window
-    double lag = 1.0 + window * 1.3;
-    lag = std::ceil(lag * 2.0) / 2.0;            // multiples of half a round
-    const double forced = (double)env_ll("ADSP_FUSED_LAG_X2", 0) / 2.0;
-    if (forced > 0) lag = forced;
-    fp.nslots = (int)std::ceil(3.0 * lag + 1.0);
-    fp.extra_rounds = (int)std::ceil(2.0 * lag) + 1;
-    struct Ent { double key; unsigned val; };
-    std::vector<Ent> ents;
-    auto add = [&](int type, int count, double off) {
-        for (int i = 0; i < count; i++) {
-            const double u = (i + 0.5) / count + off;
-            const double fl = std::floor(u);
-            ents.push_back({u - fl + 1e-9 * type, (unsigned)type | ((unsigned)i << 2) | ((unsigned)fl << 20)});
-        }
-    };
-    add(TASK_CF, tiles_c, 0.0);
-    add(TASK_R, tiles_r, lag);
-    add(TASK_CI, tiles_c, 2.0 * lag);
-    std::stable_sort(ents.begin(), ents.end(), [](const Ent &a, const Ent &b) { return a.key < b.key; });
-    for (auto &e : ents) fp.order.push_back(e.val);
-    return fp;
-}
-
-#if ADSP_FUSED_AVAILABLE
-template <typename T, int N1, int L>
-static adsp_status launch_fused_t(adsp_ctx *ctx, const ConvGeom &g, long long npairs, int lgN, const T *x, T *y,
-                                  const cpx<T> *H, const cpx<T> *tw_rows, const cpx<T> *tw_cols, const cpx<T> *tw_hi,
-                                  const cpx<T> *tw_lo, FusedCache &fc) {
-    using CS = ColShape<N1>;
-    constexpr int ROWS = 256 / FftShape<L>::TPF;
-    constexpr int BUF_ELEMS = (ROWS * L > CS::SMEM_ELEMS) ? ROWS * L : CS::SMEM_ELEMS;
-    const size_t smem = ((size_t)BUF_ELEMS + FftShape<L>::TW_ENTRIES + FftShape<N1>::TW_ENTRIES) * sizeof(cpx<T>);
-    static AttrOnce once;
-    if (once.need(ctx->device)) ADSP_TRY(set_smem(fftconv_fused<T, N1, L>, smem));
-    int per_sm = 0;
-    ADSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fftconv_fused<T, N1, L>, 256, smem));
-    if (per_sm < 1) { set_error("fused kernel does not fit on an SM"); return ADSP_ERR_CUDA; }
-    const int resident = per_sm * ctx->sm_count;
-    if (fc.d_order == nullptr || fc.resident != resident) {
-        FusedPlan fp = make_fused_plan(L / CS::TC, N1 / ROWS, resident);
-        if (fc.d_order) cudaFree(fc.d_order);
-        ADSP_CUDA(cudaMalloc((void **)&fc.d_order, fp.order.size() * sizeof(unsigned)));
-        ADSP_CUDA(cudaMemcpyAsync(fc.d_order, fp.order.data(), fp.order.size() * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->main));
-        ADSP_CUDA(cudaStreamSynchronize(ctx->main));
-        fc.round_len = fp.round_len; fc.tiles_c = fp.tiles_c; fc.tiles_r = fp.tiles_r; fc.nslots = fp.nslots;
-        fc.extra_rounds = fp.extra_rounds; fc.resident = resident;
-    }
-    const size_t pair_bytes = (size_t)N1 * L * sizeof(cpx<T>);
-    const int nslots = (int)std::min<long long>(fc.nslots, npairs);
-    ADSP_TRY(ctx->scratch.reserve((size_t)nslots * pair_bytes));
-    const size_t ncount = 1 + 3 * (size_t)npairs + 8;
-    ADSP_TRY(ctx->d_counters.reserve(ncount * sizeof(unsigned)));
-    ADSP_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, ncount * sizeof(unsigned), ctx->main));
-    FusedParams prm;
-    prm.g = g; prm.npairs = npairs; prm.N2 = L; prm.lgN = lgN; prm.nslots = nslots;
-    prm.tiles_c = fc.tiles_c; prm.tiles_r = fc.tiles_r; prm.round_len = fc.round_len;
-    prm.total_tickets = (npairs + fc.extra_rounds) * (long long)fc.round_len;
-    prm.flags = (int)env_ll("ADSP_FUSED_FLAGS", 0);
-    const long long grid = std::min<long long>(resident, prm.total_tickets);
-    {
-        LaunchTimer lt(ctx, ctx->main, KK_FUSED);
-        fftconv_fused<T, N1, L><<<(unsigned)grid, 256, smem, ctx->main>>>(prm, x, y, (cpx<T> *)ctx->scratch.p, H, tw_rows, tw_cols,
-                                                                       tw_hi, tw_lo, fc.d_order, (unsigned *)ctx->d_counters.p);
-    }
-    count_launch(ctx);
-    ADSP_CUDA(cudaGetLastError());
-    if (env_ll("ADSP_FUSED_STATS", 0)) {
-        unsigned st[8];
-        ADSP_CUDA(cudaMemcpyAsync(st, (unsigned *)ctx->d_counters.p + 1 + 3 * npairs, sizeof st, cudaMemcpyDeviceToHost, ctx->main));
-        ADSP_CUDA(cudaStreamSynchronize(ctx->main));
-        fprintf(stderr, "[fused N1=%d N2=%d pairs=%lld round=%d slots=%d extra=%d grid=%lld] spins cf/r/ci = %u/%u/%u  waited tasks = %u/%u/%u\n",
-                N1, L, npairs, fc.round_len, nslots, fc.extra_rounds, grid, st[0], st[1], st[2], st[4], st[5], st[6]);
-    }
-    return ADSP_OK;
-}
-
-#endif
-
-// returns ADSP_OK and sets *done when the (N1, N2) combination has a fused instantiation
-template <typename T>
-static adsp_status launch_fused(adsp_ctx *ctx, int N1, int N2, const ConvGeom &g, long long npairs, int lgN, const T *x, T *y,
-                                const cpx<T> *H, const cpx<T> *tw_rows, const cpx<T> *tw_cols, const cpx<T> *tw_hi,
-                                const cpx<T> *tw_lo, FusedCache &fc, bool *done) {
-    *done = true;
-#if ADSP_FUSED_AVAILABLE
-#define ADSP_FUSED_CASE(n1, n2) \
-    if (N1 == n1 && N2 == n2) return launch_fused_t<T, n1, n2>(ctx, g, npairs, lgN, x, y, H, tw_rows, tw_cols, tw_hi, tw_lo, fc);
-    ADSP_FUSED_CASE(16, 512) ADSP_FUSED_CASE(16, 1024) ADSP_FUSED_CASE(16, 2048) ADSP_FUSED_CASE(16, 4096)
-    ADSP_FUSED_CASE(32, 4096) ADSP_FUSED_CASE(64, 4096) ADSP_FUSED_CASE(128, 4096) ADSP_FUSED_CASE(256, 4096)
-#undef ADSP_FUSED_CASE
-#endif
-    *done = false;
-    return ADSP_OK;
-}
-
 // ------------------------------------------------------------------ FftConv
 template <typename T>
 adsp_status FftConv<T>::init(adsp_ctx *c, const T *d_kernel, long long K_, const FftChoice &choice, cpx<T> *H_ext) {
@@ -791,8 +428,6 @@ adsp_status FftConv<T>::init(adsp_ctx *c, const T *d_kernel, long long K_, const
 template <typename T> void FftConv<T>::destroy() {
     if (H && owns_H) cudaFree(H);
     H = nullptr;
-    if (fused.d_order) cudaFree(fused.d_order);
-    fused.d_order = nullptr;
 }
 
 template <typename T>
@@ -816,65 +451,23 @@ adsp_status FftConv<T>::run(const T *d_x, long long n, long long channels, long 
     if (ch.N1 == 1)
         return launch_full<T, false>(ctx, ctx->main, ch.N2, g, d_x, d_y, H, (cpx<T> *)nullptr, (T)0, tw_rows, npairs);
 
-    // four-step, persistent fused kernel (one launch for the whole batch) when the batch is large enough
-    // (opt-in, ADSP_FUSED=1: measured slower than the three-kernel path)
-    if (ch.P <= 1 && ADSP_FUSED_AVAILABLE && npairs >= env_ll("ADSP_FUSED_MIN_PAIRS", 12) && env_ll("ADSP_FUSED", 0) != 0 && env_ll("ADSP_NO_FUSED", 0) == 0) {
-        bool done = false;
-        ADSP_TRY(launch_fused<T>(ctx, ch.N1, ch.N2, g, npairs, ch.lgN, d_x, d_y, H, tw_rows, tw_cols, tw_hi, tw_lo, fused, &done));
-        if (done) return ADSP_OK;
-    }
-    // four-step, stage-merged: one launch per group step (rows of group t-1 + forward columns of t + inverse columns of t-2).
-    // Opt-in (ADSP_STAGES=1): measured 2.17 ms vs 1.97 ms for the three-kernel, three-stream schedule below.
-    if (ch.P <= 1 && env_ll("ADSP_STAGES", 0) != 0) {
-        bool done = false;
-        ADSP_TRY(run_stages<T>(ctx, ch, g, npairs, d_x, d_y, H, tw_rows, tw_cols, tw_hi, tw_lo, &done));
-        if (done) return ADSP_OK;
-    }
     // four-step, three kernels per group of pairs sized so that the intermediates of all in-flight groups stay in L2
     const size_t per_pair = (size_t)ch.N * sizeof(cpx<T>);
     size_t budget = ctx->scratch_budget;
     const long long mb = env_ll("ADSP_SCRATCH_MB", 0);  // tuning override
     if (mb > 0) budget = (size_t)mb << 20;
 
-    // ping-pong kernels: persistent 512-thread CTAs, two phase-locked tiles per SM
-    const int conc = 2 * ctx->sm_count;   // tiles in flight
-    const int tiles_r = ch.N1 / (256 / (ch.N2 / 16) > 0 ? 256 / (ch.N2 / 16) : 1);
-    const bool use_pp = ch.P <= 1 && pp_supported(ch.N1, ch.N2) && env_ll("ADSP_PINGPONG", 0) != 0 && npairs * (long long)tiles_r >= conc;
-#if ADSP_EXPERIMENTAL
-    const bool use_pf = ch.P <= 1 && !use_pp && pf_supported(ch.N1, ch.N2) && env_ll("ADSP_PF", 0) != 0;
-    const bool use_il = il_supported(ch.N2) && env_ll("ADSP_IL", 0) != 0;
-#else
-    const bool use_pf = false, use_il = false;
-#endif
     int nstreams = (int)env_ll("ADSP_STREAMS", 4);
     if (nstreams < 1) nstreams = 1;
     if (nstreams > kWorkerStreams) nstreams = kWorkerStreams;
     if (per_pair * 2 >= budget && nstreams > 2) nstreams = 2;   // pairs that alone fill the budget (N >= 2^21): two in flight
-    int nslots_max = use_pp ? 2 : nstreams;
+    int nslots_max = nstreams;
     long long G = (long long)(budget / nslots_max / per_pair);
     const long long forced_g = env_ll("ADSP_GROUP_PAIRS", 0);   // tuning override
     if (forced_g > 0) G = forced_g;
     if (G < 1) G = 1;
     if (G > npairs) G = npairs;
     if (G > 32768) G = 32768;
-    if (use_pp && G > 1) {
-        // pick the group size whose tile counts fill whole waves of `conc` tiles best
-        const int tiles_c = ch.N2 / (256 / (ch.N1 / 16));
-        long long best = G;
-        double best_eff = 0;
-        for (long long cand = G; cand >= (G + 1) / 2 && cand >= 1; cand--) {
-            double eff = 1.0;
-            for (int tp : {tiles_r, tiles_c}) {
-                const long long nt = cand * tp;
-                const double e = (double)nt / (double)(((nt + conc - 1) / conc) * conc);
-                if (e < eff) eff = e;
-            }
-            if (eff > best_eff + 1e-9) { best_eff = eff; best = cand; }
-        }
-        G = best;
-        const long long forced = env_ll("ADSP_PP_GROUP", 0);
-        if (forced > 0) G = std::min<long long>(forced, npairs);
-    }
     const int nslots = (npairs > G) ? nslots_max : 1;
     ADSP_TRY(ctx->scratch.reserve((size_t)nslots * (size_t)G * per_pair));
     cpx<T> *scr = (cpx<T> *)ctx->scratch.p;
@@ -899,22 +492,7 @@ adsp_status FftConv<T>::run(const T *d_x, long long n, long long channels, long 
         const int slot = (int)(grp % nslots);
         cudaStream_t st = (nslots > 1) ? ctx->worker[slot] : ctx->main;
         cpx<T> *sl = scr + (size_t)slot * (size_t)G * (size_t)ch.N;
-        bool done = false;
-        if (use_pp) ADSP_TRY(launch_pp<T>(ctx, st, ch.N1, ch.N2, g, d_x, d_y, sl, H, ch.lgN, tw_rows, tw_cols, tw_hi, tw_lo, pair0, gp, &done));
-        if (done) continue;
-#if ADSP_EXPERIMENTAL
-        if (use_pf) {
-            ADSP_TRY(launch_cols_pf<T>(ctx, st, ch.N1, false, g, d_x, d_y, sl, ch.N2, ch.lgN, tw_cols, tw_hi, tw_lo, pair0, gp));
-            ADSP_TRY(launch_rows_pf<T>(ctx, st, ch.N2, sl, H, ch.N1, tw_rows, gp));
-            ADSP_TRY(launch_cols_pf<T>(ctx, st, ch.N1, true, g, d_x, d_y, sl, ch.N2, ch.lgN, tw_cols, tw_hi, tw_lo, pair0, gp));
-            continue;
-        }
-#endif
         ADSP_TRY(launch_cols_any<T>(ctx, st, ch, false, g, d_x, d_y, sl, tw_cols, tw_hi, tw_lo, pair0, gp, ch.P > 1 ? &mrp[slot] : nullptr));
-#if ADSP_EXPERIMENTAL
-        if (use_il) ADSP_TRY(launch_rows_il<T>(ctx, st, ch.N2, sl, H, ch.N1, tw_rows, gp));
-        else
-#endif
         ADSP_TRY((launch_rows<T, false>(ctx, st, ch.N2, sl, H, (cpx<T> *)nullptr, (T)0, ch.N1, tw_rows, gp)));
         ADSP_TRY(launch_cols_any<T>(ctx, st, ch, true, g, d_x, d_y, sl, tw_cols, tw_hi, tw_lo, pair0, gp, ch.P > 1 ? &mrp[slot] : nullptr));
     }
