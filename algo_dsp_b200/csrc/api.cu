@@ -444,6 +444,16 @@ static adsp_status plan_run_host(adsp_plan *p, const T *in, long long n, long lo
     auto chunk_c0 = [&](long long i) { return i * cc; };
     auto chunk_nc = [&](long long i) { return std::min(cc, channels - i * cc); };
     StagePool::Ticket tk_in[NS], tk_out[NS];
+    // The copy threads read and write CALLER memory: whatever way this function is left (an error in the middle of the
+    // pipeline included), no copy may still be running when it returns (cgo pointer rule: the memory is only ours during
+    // the call), and no DMA either.
+    struct Drain {
+        adsp_ctx *ctx; StagePool *pool; StagePool::Ticket *a, *b; int n;
+        ~Drain() {
+            if (pool) for (int i = 0; i < n; i++) { pool->wait(a[i]); pool->wait(b[i]); }
+            cudaStreamSynchronize(ctx->copy_in); cudaStreamSynchronize(ctx->copy_out); cudaStreamSynchronize(ctx->main);
+        }
+    } drain{ctx, pool, tk_in, tk_out, NS};
     // iteration i: stage-in of chunk i | enqueue H2D + kernels + D2H of chunk i-1 | stage-out of chunk i-2
     for (long long i = 0; i < nchunks + 2; i++) {
         if (i < nchunks && stage_in) {

@@ -281,6 +281,10 @@ adsp_status download2d(adsp_ctx *ctx, void *dst_host, size_t dpitch, const void 
             pieces.push_back({(char *)dst_host + r0 * dpitch, (const char *)src_dev + r0 * spitch, dpitch, spitch, width, std::min(per, rows - r0)});
     }
     StagePool::Ticket tk[kPipeSlots];
+    struct Drain {   // no copy into caller memory may outlive this call, error paths included
+        StagePool *pool; StagePool::Ticket *t;
+        ~Drain() { for (int i = 0; i < kPipeSlots; i++) pool->wait(t[i]); }
+    } drain{pool, tk};
     const size_t np = pieces.size();
     for (size_t i = 0; i <= np; i++) {
         if (i < np) {
