@@ -44,6 +44,26 @@ __device__ __forceinline__ void direct_chunk(T (&acc)[DIRECT_RO], const T *sa, c
 #undef ADSP_SA
 }
 
+// Output epilogue of a tile: a thread owns RO CONSECUTIVE outputs, so storing them directly makes every warp store touch
+// 32 segments of RO*sizeof(T) bytes (16 LSU wavefronts per fp64 instruction; half of the kernel's wavefronts, ncu round 2).
+// The outputs are transposed through the (now idle) signal tile instead: padded writes and unit-stride reads are both
+// conflict free, and every warp store covers 32 consecutive samples (2 wavefronts).  No alignment requirement.
+template <typename T>
+__device__ __forceinline__ void direct_store_tile(const T (&acc)[DIRECT_RO], T *sa, T *__restrict__ oc, long long k0, long long out_len, int t) {
+#define ADSP_SA(i) sa[(i) + ((i) >> DIRECT_PAD_SHIFT)]
+    __syncthreads();                                   // every thread has finished reading its window
+#pragma unroll
+    for (int r = 0; r < DIRECT_RO; r++) ADSP_SA(t * DIRECT_RO + r) = acc[r];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < DIRECT_RO; r++) {
+        const int i = r * DIRECT_THREADS + t;
+        const long long k = k0 + i;
+        if (k < out_len) __stcs(oc + k, ADSP_SA(i));
+    }
+#undef ADSP_SA
+}
+
 template <typename T, bool FUSED>
 __global__ void __launch_bounds__(DIRECT_THREADS)
 direct_conv_kernel(const T *__restrict__ a, long long n, long long a_stride,
@@ -88,12 +108,7 @@ direct_conv_kernel(const T *__restrict__ a, long long n, long long a_stride,
         if (lim == DIRECT_MC) direct_chunk<T, FUSED, false>(acc, sa, sb, base, lim);
         else direct_chunk<T, FUSED, true>(acc, sa, sb, base, lim);
     }
-    T *oc = out + ch * out_stride;
-#pragma unroll
-    for (int r = 0; r < DIRECT_RO; r++) {
-        const long long k = k0 + (long long)t * DIRECT_RO + r;
-        if (k < out_len) oc[k] = acc[r];
-    }
+    direct_store_tile<T>(acc, sa, out + ch * out_stride, k0, out_len, t);
 #undef ADSP_SA
 }
 
@@ -141,12 +156,7 @@ direct_conv_ctaps_kernel(const T *__restrict__ a, long long n, long long a_strid
             else acc[r] = __fadd_rn((float)acc[r], __fmul_rn((float)w[r], (float)bj));
         }
     }
-    T *oc = out + ch * out_stride;
-#pragma unroll
-    for (int r = 0; r < DIRECT_RO; r++) {
-        const long long k = k0 + (long long)t * DIRECT_RO + r;
-        if (k < out_len) oc[k] = acc[r];
-    }
+    direct_store_tile<T>(acc, sa, out + ch * out_stride, k0, out_len, t);
 #undef ADSP_SA
 }
 
