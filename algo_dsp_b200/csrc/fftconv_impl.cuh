@@ -457,7 +457,9 @@ adsp_status FftConv<T>::run(const T *d_x, long long n, long long channels, long 
     const long long mb = env_ll("ADSP_SCRATCH_MB", 0);  // tuning override
     if (mb > 0) budget = (size_t)mb << 20;
 
-    int nstreams = (int)env_ll("ADSP_STREAMS", 4);
+    // four groups in flight; three once a pair's intermediate reaches 16 MB (N = 2^20 in fp64), where a fourth evicts
+    // spectrum and scratch lines from L2 (measured round 2, 16 ch x 14.4 M x 288k taps: 71.9 vs 69.0 Gsamples/s)
+    int nstreams = (int)env_ll("ADSP_STREAMS", per_pair >= ((size_t)16 << 20) ? 3 : 4);
     if (nstreams < 1) nstreams = 1;
     if (nstreams > kWorkerStreams) nstreams = kWorkerStreams;
     if (per_pair * 2 >= budget && nstreams > 2) nstreams = 2;   // pairs that alone fill the budget (N >= 2^21): two in flight
