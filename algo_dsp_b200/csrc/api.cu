@@ -218,9 +218,28 @@ static std::vector<Segment> plan_segments(long long out_len, long long K, const 
     return segs;
 }
 
+// taps as a kernel parameter, NCH chunks of 64 (aux_kernels.cuh); h_b: the caller's host copy of the taps, if it has one
+template <typename T, int NCH>
+static adsp_status direct_ctapsn(adsp_ctx *ctx, const T *d_a, long long n, long long a_stride, const T *d_b, const T *h_b, long long m, T *d_out,
+                                 long long out_stride, long long tiles, unsigned grid, bool exact) {
+    DirectTapsN<T, NCH> taps;
+    if (h_b) memcpy(taps.v, h_b, (size_t)m * sizeof(T));
+    else {
+        ADSP_CUDA(cudaMemcpyAsync(taps.v, d_b, (size_t)m * sizeof(T), cudaMemcpyDeviceToHost, ctx->main));
+        ADSP_CUDA(cudaStreamSynchronize(ctx->main));
+    }
+    for (long long i = m; i < NCH * DIRECT_MC; i++) taps.v[i] = (T)0;
+    LaunchTimer lt(ctx, ctx->main, KK_DIRECT);
+    if (exact) direct_conv_ctapsn_kernel<T, false, NCH><<<grid, DIRECT_THREADS, 0, ctx->main>>>(d_a, n, a_stride, taps, (int)m, d_out, out_stride, tiles);
+    else direct_conv_ctapsn_kernel<T, true, NCH><<<grid, DIRECT_THREADS, 0, ctx->main>>>(d_a, n, a_stride, taps, (int)m, d_out, out_stride, tiles);
+    count_launch(ctx);
+    ADSP_CUDA(cudaGetLastError());
+    return ADSP_OK;
+}
+
 template <typename T>
 adsp_status direct_device(adsp_ctx *ctx, const T *d_a, long long n, long long a_stride, const T *d_b, long long m,
-                          long long b_stride, long long batch, T *d_out, long long out_stride) {
+                          long long b_stride, long long batch, T *d_out, long long out_stride, const T *h_b) {
     const long long out_len = n + m - 1;
     static const bool exact = env_ll("ADSP_DIRECT_EXACT", 0) != 0;
     const long long tiles = (out_len + DIRECT_TILE - 1) / DIRECT_TILE;
@@ -232,8 +251,11 @@ adsp_status direct_device(adsp_ctx *ctx, const T *d_a, long long n, long long a_
     if (ctaps && m <= DIRECT_MC && (b_stride == 0 || batch == 1)) {
         DirectTaps<T> taps;
         for (int i = 0; i < DIRECT_MC; i++) taps.v[i] = (T)0;
-        ADSP_CUDA(cudaMemcpyAsync(taps.v, d_b, (size_t)m * sizeof(T), cudaMemcpyDeviceToHost, ctx->main));
-        ADSP_CUDA(cudaStreamSynchronize(ctx->main));
+        if (h_b) memcpy(taps.v, h_b, (size_t)m * sizeof(T));
+        else {
+            ADSP_CUDA(cudaMemcpyAsync(taps.v, d_b, (size_t)m * sizeof(T), cudaMemcpyDeviceToHost, ctx->main));
+            ADSP_CUDA(cudaStreamSynchronize(ctx->main));
+        }
         LaunchTimer lt(ctx, ctx->main, KK_DIRECT);
         const unsigned g = (unsigned)grid;
         if (m == DIRECT_MC) {
@@ -247,6 +269,10 @@ adsp_status direct_device(adsp_ctx *ctx, const T *d_a, long long n, long long a_
         ADSP_CUDA(cudaGetLastError());
         return ADSP_OK;
     }
+    if (ctaps && m <= 16 * DIRECT_MC && (b_stride == 0 || batch == 1)) {
+        if (m <= 4 * DIRECT_MC) return direct_ctapsn<T, 4>(ctx, d_a, n, a_stride, d_b, h_b, m, d_out, out_stride, tiles, (unsigned)grid, exact);
+        return direct_ctapsn<T, 16>(ctx, d_a, n, a_stride, d_b, h_b, m, d_out, out_stride, tiles, (unsigned)grid, exact);
+    }
     LaunchTimer lt(ctx, ctx->main, KK_DIRECT);
     if (exact)
         direct_conv_kernel<T, false><<<(unsigned)grid, DIRECT_THREADS, 0, ctx->main>>>(d_a, n, a_stride, d_b, m, b_stride, d_out, out_stride, tiles);
@@ -256,8 +282,8 @@ adsp_status direct_device(adsp_ctx *ctx, const T *d_a, long long n, long long a_
     ADSP_CUDA(cudaGetLastError());
     return ADSP_OK;
 }
-template adsp_status direct_device<double>(adsp_ctx *, const double *, long long, long long, const double *, long long, long long, long long, double *, long long);
-template adsp_status direct_device<float>(adsp_ctx *, const float *, long long, long long, const float *, long long, long long, long long, float *, long long);
+template adsp_status direct_device<double>(adsp_ctx *, const double *, long long, long long, const double *, long long, long long, long long, double *, long long, const double *);
+template adsp_status direct_device<float>(adsp_ctx *, const float *, long long, long long, const float *, long long, long long, long long, float *, long long, const float *);
 
 // FindPeak on device vectors; results land in d_v[batch], d_i[batch]
 template <typename T>

@@ -184,7 +184,7 @@ adsp_status fft_deconvolve_device(adsp_ctx *ctx, const T *sig, long long n, long
 
 template <typename T>
 adsp_status direct_device(adsp_ctx *ctx, const T *d_a, long long n, long long a_stride, const T *d_b, long long m,
-                          long long b_stride, long long batch, T *d_out, long long out_stride);
+                          long long b_stride, long long batch, T *d_out, long long out_stride, const T *h_b = nullptr);
 
 // Streaming partitioned convolution on a frequency-domain delay line, many channels per launch (fdl.cu)
 struct FdlEngine;

@@ -198,6 +198,41 @@ __global__ void __launch_bounds__(256) resample_kernel(const double *__restrict_
     }
 }
 
+// The same sum with the prototype filter and the tile's input window staged in shared memory: the kernel above gathers
+// taps[ph + k*up] from global memory with a different phase in every lane (32 sectors per warp load).  Here the taps keep the
+// reference's k-major layout, so for a fixed k a warp reads phases ph0 + lane*down (mod up) of one row; the window read
+// x[idx - k] is near-unit-stride (idx advances by down/up per output).  One CTA: `tile` consecutive outputs of one channel.
+__global__ void __launch_bounds__(256) resample_tiled_kernel(const double *__restrict__ work, long long work_stride, long long base, long long last,
+                                                             const double *__restrict__ taps, int ntaps, long long up, long long down, long long g0,
+                                                             long long nout, double *__restrict__ out, long long out_stride, int tile, int maxk) {
+    extern __shared__ double rs_smem[];
+    double *tp_s = rs_smem;                 // [ntaps]
+    double *x_s = rs_smem + ntaps;          // window [lo, hi] of absolute input indices
+    const double *w = work + (long long)blockIdx.y * work_stride;
+    double *o = out + (long long)blockIdx.y * out_stride;
+    const long long j0 = (long long)blockIdx.x * tile;
+    const int jn = (int)((nout - j0 < tile) ? (nout - j0) : tile);
+    const long long lo = ((g0 + j0) * down) / up - maxk, hi = ((g0 + j0 + jn - 1) * down) / up;
+    for (int i = threadIdx.x; i < ntaps; i += blockDim.x) tp_s[i] = taps[i];
+    for (long long i = lo + threadIdx.x; i <= hi; i += blockDim.x)
+        if (i >= base && i <= last) x_s[i - lo] = w[i - base];      // slots outside [base, last] are never read
+    __syncthreads();
+    for (int jj = threadIdx.x; jj < jn; jj += blockDim.x) {
+        const long long acc = (g0 + j0 + jj) * down;
+        const long long idx = acc / up;
+        const int ph = (int)(acc - idx * up);
+        const int xi = (int)(idx - lo);
+        double y = 0.0;
+        int k = 0;
+        for (int tp = ph; tp < ntaps; tp += (int)up, k++) {
+            const long long i = idx - k;
+            if (i < base || i > last) continue;
+            y = ADSP_ADD(y, ADSP_MUL(tp_s[tp], x_s[xi - k]));
+        }
+        o[j0 + jj] = y;
+    }
+}
+
 }  // namespace
 }  // namespace adsp
 
@@ -209,9 +244,15 @@ struct adsp_fir {
     long long ntaps = 0;
     int channels = 1;
     DevBuf taps;        // coefficients in the order the block path applies them (see adsp_fir_create)
-    DevBuf work;        // [channels][ntaps-1 + block]: history in front of the current block
-    DevBuf full;        // direct-convolution output of the work rows
+    std::vector<double> h_taps;   // the same on the host: up to 1024 of them travel as a kernel parameter
+    DevBuf work;        // [channels][ntaps-1 + block]: history in front of the current block (copy path); block rows (host calls)
+    DevBuf full;        // direct-convolution output of the work rows (copy path)
     long long work_cap = 0;
+    // in-place path (up to 1024 taps): the last ntaps-1 samples of every channel, double buffered, and the samples in front
+    // of every segment of the current block
+    bool inplace = false;
+    DevBuf hist[2], halo;
+    int cur = 0;
 };
 
 struct adsp_resampler {
@@ -413,12 +454,72 @@ adsp_status adsp_fir_create(adsp_ctx *ctx, const double *coeffs, int64_t ntaps, 
     if (ntaps > 0) {
         std::vector<double> c(coeffs, coeffs + ntaps);
         if (ntaps >= 32) std::reverse(c.begin(), c.end());           // linearizeThreshold, filter.go:70
+        f->h_taps = c;
+        f->inplace = ntaps <= 16 * DIRECT_MC && channels <= 65535 && env_ll("ADSP_FIR_INPLACE", 1) != 0;
         adsp_status st = f->taps.reserve((size_t)ntaps * 8);
         if (st == ADSP_OK) st = upload(ctx, f->taps.p, c.data(), (size_t)ntaps * 8);
         if (st == ADSP_OK && cudaStreamSynchronize(ctx->main) != cudaSuccess) st = ADSP_ERR_CUDA;
-        if (st != ADSP_OK) { f->taps.release(); delete f; return st; }
+        if (st == ADSP_OK && f->inplace && ntaps > 1) {
+            const size_t hb = (size_t)(ntaps - 1) * channels * 8;
+            for (int i = 0; i < 2 && st == ADSP_OK; i++) {
+                st = f->hist[i].reserve(hb);
+                if (st == ADSP_OK && cudaMemsetAsync(f->hist[i].p, 0, hb, ctx->main) != cudaSuccess) st = ADSP_ERR_CUDA;
+            }
+            if (st == ADSP_OK && cudaStreamSynchronize(ctx->main) != cudaSuccess) st = ADSP_ERR_CUDA;
+        }
+        if (st != ADSP_OK) { f->taps.release(); f->hist[0].release(); f->hist[1].release(); delete f; return st; }
     }
     *out = f;
+    return ADSP_OK;
+}
+
+// in place on device rows (see fir_inplace_kernel): halos and the next history first, then one CTA per 8192-sample segment
+extern "C++" {
+template <int NCH>
+static adsp_status fir_inplace_launch(adsp_fir *f, double *d, long long stride, long long n, int nseg, long long seg_len) {
+    adsp_ctx *ctx = f->ctx;
+    static const bool exact = env_ll("ADSP_DIRECT_EXACT", 0) != 0;
+    DirectTapsN<double, NCH> taps;
+    memcpy(taps.v, f->h_taps.data(), (size_t)f->ntaps * 8);
+    for (long long i = f->ntaps; i < NCH * DIRECT_MC; i++) taps.v[i] = 0.0;
+    const int H = (int)f->ntaps - 1;
+    const unsigned grid = (unsigned)((long long)nseg * f->channels);
+    if (exact) fir_inplace_kernel<double, false, NCH><<<grid, DIRECT_THREADS, 0, ctx->main>>>(d, stride, n, (const double *)f->halo.p, H, taps, (int)f->ntaps, seg_len, nseg);
+    else fir_inplace_kernel<double, true, NCH><<<grid, DIRECT_THREADS, 0, ctx->main>>>(d, stride, n, (const double *)f->halo.p, H, taps, (int)f->ntaps, seg_len, nseg);
+    count_launch(ctx);
+    return ADSP_OK;
+}
+}  // extern "C++"
+
+static adsp_status fir_run_inplace(adsp_fir *f, double *buf, long long n, long long stride, bool host) {
+    adsp_ctx *ctx = f->ctx;
+    const int H = (int)f->ntaps - 1;
+    const long long seg_len = (long long)FIR_SEG_TILES * DIRECT_TILE;
+    const long long nseg_ll = (n + seg_len - 1) / seg_len;
+    if (nseg_ll * f->channels > 0x7fffffffLL || nseg_ll > 0x7ffffffeLL) { set_error("fir: block too large"); return ADSP_ERR_INVALID_ARG; }
+    const int nseg = (int)nseg_ll;
+    double *d = buf;
+    long long ds = stride;
+    if (host) {
+        ds = ((n + 31) / 32) * 32;
+        ADSP_TRY(f->work.reserve((size_t)ds * f->channels * 8));
+        d = (double *)f->work.p;
+        ADSP_TRY(upload2d(ctx, d, (size_t)ds * 8, buf, (size_t)stride * 8, (size_t)n * 8, (size_t)f->channels));
+    }
+    if (H > 0) {
+        ADSP_TRY(f->halo.reserve((size_t)nseg * f->channels * H * 8));
+        fir_halo_kernel<double><<<dim3((unsigned)nseg + 1, (unsigned)f->channels), 256, 0, ctx->main>>>(d, ds, n, (const double *)f->hist[f->cur].p, (double *)f->hist[f->cur ^ 1].p,
+                                                                                                         (double *)f->halo.p, H, seg_len, nseg);
+        count_launch(ctx);
+        f->cur ^= 1;
+    }
+    if (f->ntaps <= 4 * DIRECT_MC) ADSP_TRY(fir_inplace_launch<4>(f, d, ds, n, nseg, seg_len));
+    else ADSP_TRY(fir_inplace_launch<16>(f, d, ds, n, nseg, seg_len));
+    ADSP_CUDA(cudaGetLastError());
+    if (host) {
+        ADSP_TRY(download2d(ctx, buf, (size_t)stride * 8, d, (size_t)ds * 8, (size_t)n * 8, (size_t)f->channels));
+        ADSP_CUDA(cudaStreamSynchronize(ctx->main));
+    }
     return ADSP_OK;
 }
 
@@ -447,13 +548,14 @@ static adsp_status fir_run(adsp_fir *f, double *buf, long long n, long long stri
     adsp_ctx *ctx = f->ctx;
     std::lock_guard<std::mutex> lk(ctx->mu);
     ADSP_CUDA(cudaSetDevice(ctx->device));
+    if (f->inplace) return fir_run_inplace(f, buf, n, stride, host);
     ADSP_TRY(fir_reserve(f, n));
     const long long H = f->ntaps - 1, ws = H + f->work_cap, L = H + n, fs = ws + f->ntaps;
     double *work = (double *)f->work.p, *full = (double *)f->full.p;
     // work rows = [history | block]
     if (host) ADSP_TRY(upload2d(ctx, work + H, (size_t)ws * 8, buf, (size_t)stride * 8, (size_t)n * 8, (size_t)f->channels));
     else ADSP_CUDA(cudaMemcpy2DAsync(work + H, (size_t)ws * 8, buf, (size_t)stride * 8, (size_t)n * 8, (size_t)f->channels, cudaMemcpyDeviceToDevice, ctx->main));
-    ADSP_TRY(direct_device<double>(ctx, work, L, ws, (const double *)f->taps.p, f->ntaps, 0, f->channels, full, fs));
+    ADSP_TRY(direct_device<double>(ctx, work, L, ws, (const double *)f->taps.p, f->ntaps, 0, f->channels, full, fs, f->h_taps.data()));
     // y[t] = full[H + t]; next history = last H samples of the work row
     if (host) ADSP_TRY(download2d(ctx, buf, (size_t)stride * 8, full + H, (size_t)fs * 8, (size_t)n * 8, (size_t)f->channels));
     else ADSP_CUDA(cudaMemcpy2DAsync(buf, (size_t)stride * 8, full + H, (size_t)fs * 8, (size_t)n * 8, (size_t)f->channels, cudaMemcpyDeviceToDevice, ctx->main));
@@ -473,17 +575,18 @@ adsp_status adsp_fir_process_block(adsp_fir *f, double *buf, int64_t n, int64_t 
 adsp_status adsp_fir_process_block_device(adsp_fir *f, double *buf_dev, int64_t n, int64_t stride) { return fir_run(f, buf_dev, n, stride, false); }
 int64_t adsp_fir_order(const adsp_fir *f) { return f ? f->ntaps - 1 : 0; }                           // Order(), filter.go
 void adsp_fir_reset(adsp_fir *f) {                                                                    // Reset()
-    if (!f || !f->work.p) return;
+    if (!f) return;
     std::lock_guard<std::mutex> lk(f->ctx->mu);
     cudaSetDevice(f->ctx->device);
-    cudaMemsetAsync(f->work.p, 0, f->work.cap, f->ctx->main);
+    if (f->inplace) { if (f->hist[f->cur].p) cudaMemsetAsync(f->hist[f->cur].p, 0, (size_t)(f->ntaps - 1) * f->channels * 8, f->ctx->main); }
+    else if (f->work.p) cudaMemsetAsync(f->work.p, 0, f->work.cap, f->ctx->main);
     cudaStreamSynchronize(f->ctx->main);
 }
 void adsp_fir_destroy(adsp_fir *f) {
     if (!f) return;
     cudaSetDevice(f->ctx->device);
     cudaStreamSynchronize(f->ctx->main);
-    f->taps.release(); f->work.release(); f->full.release();
+    f->taps.release(); f->work.release(); f->full.release(); f->hist[0].release(); f->hist[1].release(); f->halo.release();
     delete f;
 }
 
@@ -603,9 +706,21 @@ static adsp_status resample_run(adsp_resampler *r, const double *in, long long n
         dout = (double *)r->outbuf.p;
     }
     if (nout > 0) {
-        dim3 grid(gx(nout, 256), (unsigned)r->channels);
-        resample_kernel<<<grid, 256, 0, ctx->main>>>(work, wst, base, last, (const double *)r->d_taps.p, (int)r->taps.size(), r->up, r->down, r->out_count, nout, dout,
-                                                     dstride);
+        // tiled kernel when the prototype and a tile's window fit shared memory (two CTAs per SM), else the gather kernel
+        const int ntaps = (int)r->taps.size(), maxk = std::max(0, r->max_phase_len - 1);
+        int tile = 4096;
+        auto need = [&](int t) { return ((size_t)ntaps + (size_t)((long long)t * r->down / r->up) + (size_t)maxk + 4) * 8; };
+        while (tile > 512 && need(tile) > (size_t)100 * 1024) tile /= 2;
+        static const bool tiled = env_ll("ADSP_RESAMPLE_TILED", 1) != 0;
+        if (tiled && need(tile) <= (size_t)100 * 1024 && (nout + tile - 1) / tile <= 0x7fffffffLL) {
+            ADSP_CUDA(cudaFuncSetAttribute(resample_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));   // per device
+            dim3 grid((unsigned)((nout + tile - 1) / tile), (unsigned)r->channels);
+            resample_tiled_kernel<<<grid, 256, need(tile), ctx->main>>>(work, wst, base, last, (const double *)r->d_taps.p, ntaps, r->up, r->down, r->out_count, nout,
+                                                                        dout, dstride, tile, maxk);
+        } else {
+            dim3 grid(gx(nout, 256), (unsigned)r->channels);
+            resample_kernel<<<grid, 256, 0, ctx->main>>>(work, wst, base, last, (const double *)r->d_taps.p, ntaps, r->up, r->down, r->out_count, nout, dout, dstride);
+        }
         count_launch(ctx);
         if (host) ADSP_TRY(download2d(ctx, out, (size_t)out_stride * 8, dout, (size_t)dstride * 8, (size_t)nout * 8, (size_t)r->channels));
     }

@@ -119,6 +119,26 @@ def test_direct_long_kernel_and_f32(conv, oracle):
     assert rel(conv.Convolve32(a32, b.astype(np.float32)), oracle.convolve(a, b)) <= TOL32
 
 
+@pytest.mark.parametrize("m", [63, 64, 65, 128, 255, 256, 257, 1000, 1024, 1025, 1300])
+def test_direct_kernel_families_by_tap_count(conv, oracle, m):
+    """Up to 64 taps, 65..256, 257..1024 (taps as kernel parameters) and beyond (taps in shared memory), shared and per-channel
+    kernels, both precisions; a tile boundary inside the result (1024 outputs per CTA) and a signal shorter than the kernel."""
+    ch, n = 3, 2500
+    x = np.stack([G.white(n, seed=10 + c) for c in range(ch)])
+    k = G.white(m, seed=99)
+    y = conv.DirectBatch(x, k)
+    assert y.shape == (ch, n + m - 1)
+    for c in range(ch):
+        assert rel(y[c], oracle.direct(x[c], k)) <= TOL64
+    ks = np.stack([k * (c + 1) for c in range(ch)])               # per-channel kernels: the shared-memory-tap kernel
+    y2 = conv.DirectBatch(x, ks)
+    assert np.array_equal(y2[0], y[0])                            # same accumulation order in both kernels: bit identical
+    assert rel(y2[2], oracle.direct(x[2], ks[2])) <= TOL64
+    short = G.white(40, seed=5)
+    assert rel(conv.Direct(short, k), oracle.direct(short, k)) <= TOL64
+    assert rel(conv.Direct32(x[1].astype(np.float32), k.astype(np.float32)), oracle.direct(x[1], k, np.float32)) <= TOL32
+
+
 def test_direct_batch_config2_shape(conv, oracle):
     """Config 2 shape (channels x samples, 64-tap Hann-windowed sinc), reduced channel count."""
     ch, n = 8, 1 << 16
