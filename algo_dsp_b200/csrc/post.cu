@@ -198,38 +198,70 @@ __global__ void __launch_bounds__(256) resample_kernel(const double *__restrict_
     }
 }
 
-// The same sum with the prototype filter and the tile's input window staged in shared memory: the kernel above gathers
-// taps[ph + k*up] from global memory with a different phase in every lane (32 sectors per warp load).  Here the taps keep the
-// reference's k-major layout, so for a fixed k a warp reads phases ph0 + lane*down (mod up) of one row; the window read
-// x[idx - k] is near-unit-stride (idx advances by down/up per output).  One CTA: `tile` consecutive outputs of one channel.
-__global__ void __launch_bounds__(256) resample_tiled_kernel(const double *__restrict__ work, long long work_stride, long long base, long long last,
-                                                             const double *__restrict__ taps, int ntaps, long long up, long long down, long long g0,
-                                                             long long nout, double *__restrict__ out, long long out_stride, int tile, int maxk) {
+// The same sum from shared memory, R outputs of one polyphase branch per thread.  The kernel above gathers
+// taps[ph + k*up] from global memory with a different phase in every lane (32 sectors per warp load) and runs one dependent
+// add chain per thread.  Here a CTA takes P*R consecutive outputs of one channel (P = a multiple of `up`, so outputs
+// t, t+P, t+2P, ... share their phase and sit exactly c*down input samples apart), stages the prototype (the reference's
+// k-major layout: for a fixed k a warp reads phases ph0 + lane*down mod up of one row) and the input window once, and
+// every thread carries R independent accumulators: per tap one coefficient read and R sample reads for R outputs.
+// The input is [hist (H samples) | blk] so that device callers are read where they are (no work-row copy).
+constexpr int RS_R = 8;
+__global__ void __launch_bounds__(512) resample_phase_kernel(const double *__restrict__ hist, long long hist_stride, long long H, const double *__restrict__ blk,
+                                                             long long blk_stride, long long base, long long last, const double *__restrict__ taps, int ntaps,
+                                                             int up, long long down, long long g0, long long nout, double *__restrict__ out,
+                                                             long long out_stride, int P, int lmax) {
     extern __shared__ double rs_smem[];
     double *tp_s = rs_smem;                 // [ntaps]
     double *x_s = rs_smem + ntaps;          // window [lo, hi] of absolute input indices
-    const double *w = work + (long long)blockIdx.y * work_stride;
+    const double *hs = hist + (long long)blockIdx.y * hist_stride;
+    const double *bs = blk + (long long)blockIdx.y * blk_stride;
     double *o = out + (long long)blockIdx.y * out_stride;
+    const long long tile = (long long)P * RS_R;
     const long long j0 = (long long)blockIdx.x * tile;
-    const int jn = (int)((nout - j0 < tile) ? (nout - j0) : tile);
-    const long long lo = ((g0 + j0) * down) / up - maxk, hi = ((g0 + j0 + jn - 1) * down) / up;
+    const long long jn = (nout - j0 < tile) ? (nout - j0) : tile;
+    const long long lo = ((g0 + j0) * down) / up - (lmax - 1), hi = ((g0 + j0 + jn - 1) * down) / up;
     for (int i = threadIdx.x; i < ntaps; i += blockDim.x) tp_s[i] = taps[i];
-    for (long long i = lo + threadIdx.x; i <= hi; i += blockDim.x)
-        if (i >= base && i <= last) x_s[i - lo] = w[i - base];      // slots outside [base, last] are never read
+    for (long long i = lo + threadIdx.x; i <= hi; i += blockDim.x) {
+        double v = 0.0;                                         // slots outside [base, last] are never used
+        if (i >= base && i <= last) { const long long off = i - base; v = off < H ? hs[off] : bs[off - H]; }
+        x_s[i - lo] = v;
+    }
     __syncthreads();
-    for (int jj = threadIdx.x; jj < jn; jj += blockDim.x) {
-        const long long acc = (g0 + j0 + jj) * down;
+    const bool interior = lo >= base && hi <= last;
+    const int step = (int)((long long)(P / up) * down);         // input distance between a thread's consecutive outputs
+    for (int t = threadIdx.x; t < P; t += blockDim.x) {
+        if (t >= jn) break;
+        const long long acc = (g0 + j0 + t) * down;
         const long long idx = acc / up;
         const int ph = (int)(acc - idx * up);
         const int xi = (int)(idx - lo);
-        double y = 0.0;
-        int k = 0;
-        for (int tp = ph; tp < ntaps; tp += (int)up, k++) {
-            const long long i = idx - k;
-            if (i < base || i > last) continue;
-            y = ADSP_ADD(y, ADSP_MUL(tp_s[tp], x_s[xi - k]));
+        const int lph = ph < ntaps ? (ntaps - ph + up - 1) / up : 0;          // taps of this branch
+        const int nr = (int)((jn - t + P - 1) / P < RS_R ? (jn - t + P - 1) / P : RS_R);   // outputs of this thread inside the block
+        double y[RS_R];
+#pragma unroll
+        for (int r = 0; r < RS_R; r++) y[r] = 0.0;
+        if (interior && nr == RS_R) {
+            const double *tq = tp_s + ph;
+            const double *xq = x_s + xi;
+#pragma unroll 4
+            for (int k = 0; k < lph; k++) {
+                const double c = tq[k * up];
+#pragma unroll
+                for (int r = 0; r < RS_R; r++) y[r] = ADSP_ADD(y[r], ADSP_MUL(c, xq[r * step - k]));
+            }
+        } else {
+            for (int k = 0; k < lph; k++) {
+                const double c = tp_s[ph + k * up];
+#pragma unroll
+                for (int r = 0; r < RS_R; r++) {
+                    const long long i = idx + (long long)r * step - k;
+                    if (r < nr && i >= base && i <= last) y[r] = ADSP_ADD(y[r], ADSP_MUL(c, x_s[xi + r * step - k]));
+                }
+            }
         }
-        o[j0 + jj] = y;
+#pragma unroll
+        for (int r = 0; r < RS_R; r++)
+            if (r < nr) o[j0 + t + (long long)r * P] = y[r];
     }
 }
 
@@ -682,7 +714,17 @@ static adsp_status resample_run(adsp_resampler *r, const double *in, long long n
     std::lock_guard<std::mutex> lk(ctx->mu);
     ADSP_CUDA(cudaSetDevice(ctx->device));
     const long long H = r->hist_len, keep_max = std::max(0, r->max_phase_len - 1);
-    const long long ws = ((keep_max + n + 31) / 32) * 32;
+    // branch-tiled kernel when the prototype and a tile's window fit shared memory, else the gather kernel
+    const int ntaps = (int)r->taps.size(), lmax = std::max(1, r->max_phase_len);
+    const int cmul = (256 + r->up - 1) / r->up, P = r->up * cmul;              // >= 256 outputs between a thread's outputs
+    const int iters = (P + 511) / 512, bd = (((P + iters - 1) / iters) + 31) / 32 * 32;
+    const long long tile = (long long)P * RS_R;
+    const size_t need = ((size_t)ntaps + (size_t)(tile * r->down / r->up) + (size_t)lmax + 4) * 8;
+    const bool use_phase = env_ll("ADSP_RESAMPLE_TILED", 1) != 0 && need <= (size_t)100 * 1024 && (long long)cmul * r->down * RS_R < (1LL << 30) &&
+                           (nout + tile - 1) / tile <= 0x7fffffffLL;
+    // device rows at least as long as the history are read where they are; otherwise the block is put behind the history
+    const bool direct_src = !host && use_phase && n >= keep_max;
+    const long long ws = ((keep_max + (direct_src ? 0 : n) + 31) / 32) * 32;
     if (ws > r->work_stride) {                                          // grow, carrying the history over
         DevBuf nw;
         ADSP_TRY(nw.reserve((size_t)ws * r->channels * 8));
@@ -696,7 +738,9 @@ static adsp_status resample_run(adsp_resampler *r, const double *in, long long n
     double *work = (double *)r->work.p;
     const long long wst = r->work_stride;
     if (host) ADSP_TRY(upload2d(ctx, work + H, (size_t)wst * 8, in, (size_t)in_stride * 8, (size_t)n * 8, (size_t)r->channels));
-    else ADSP_CUDA(cudaMemcpy2DAsync(work + H, (size_t)wst * 8, in, (size_t)in_stride * 8, (size_t)n * 8, (size_t)r->channels, cudaMemcpyDeviceToDevice, ctx->main));
+    else if (!direct_src) ADSP_CUDA(cudaMemcpy2DAsync(work + H, (size_t)wst * 8, in, (size_t)in_stride * 8, (size_t)n * 8, (size_t)r->channels, cudaMemcpyDeviceToDevice, ctx->main));
+    const double *src_blk = direct_src ? in : work + H;
+    const long long src_blk_stride = direct_src ? in_stride : wst;
     const long long base = r->total_in - H, last = r->total_in + n - 1;
     double *dout = out;
     long long dstride = out_stride;
@@ -706,17 +750,11 @@ static adsp_status resample_run(adsp_resampler *r, const double *in, long long n
         dout = (double *)r->outbuf.p;
     }
     if (nout > 0) {
-        // tiled kernel when the prototype and a tile's window fit shared memory (two CTAs per SM), else the gather kernel
-        const int ntaps = (int)r->taps.size(), maxk = std::max(0, r->max_phase_len - 1);
-        int tile = 4096;
-        auto need = [&](int t) { return ((size_t)ntaps + (size_t)((long long)t * r->down / r->up) + (size_t)maxk + 4) * 8; };
-        while (tile > 512 && need(tile) > (size_t)100 * 1024) tile /= 2;
-        static const bool tiled = env_ll("ADSP_RESAMPLE_TILED", 1) != 0;
-        if (tiled && need(tile) <= (size_t)100 * 1024 && (nout + tile - 1) / tile <= 0x7fffffffLL) {
-            ADSP_CUDA(cudaFuncSetAttribute(resample_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));   // per device
+        if (use_phase) {
+            ADSP_CUDA(cudaFuncSetAttribute(resample_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));   // per device
             dim3 grid((unsigned)((nout + tile - 1) / tile), (unsigned)r->channels);
-            resample_tiled_kernel<<<grid, 256, need(tile), ctx->main>>>(work, wst, base, last, (const double *)r->d_taps.p, ntaps, r->up, r->down, r->out_count, nout,
-                                                                        dout, dstride, tile, maxk);
+            resample_phase_kernel<<<grid, bd, need, ctx->main>>>(work, wst, H, src_blk, src_blk_stride, base, last, (const double *)r->d_taps.p, ntaps, r->up, r->down,
+                                                                 r->out_count, nout, dout, dstride, P, lmax);
         } else {
             dim3 grid(gx(nout, 256), (unsigned)r->channels);
             resample_kernel<<<grid, 256, 0, ctx->main>>>(work, wst, base, last, (const double *)r->d_taps.p, ntaps, r->up, r->down, r->out_count, nout, dout, dstride);
@@ -726,7 +764,9 @@ static adsp_status resample_run(adsp_resampler *r, const double *in, long long n
     }
     // history = the last min(maxPhaseLn - 1, len(work)) samples (:288-290)
     const long long have = H + n, keep = std::min(keep_max, have);
-    if (keep > 0 && have - keep > 0) {
+    if (direct_src) {
+        if (keep > 0) ADSP_CUDA(cudaMemcpy2DAsync(work, (size_t)wst * 8, in + (n - keep), (size_t)in_stride * 8, (size_t)keep * 8, (size_t)r->channels, cudaMemcpyDeviceToDevice, ctx->main));
+    } else if (keep > 0 && have - keep > 0) {
         if (have - keep >= keep) ADSP_CUDA(cudaMemcpy2DAsync(work, (size_t)wst * 8, work + (have - keep), (size_t)wst * 8, (size_t)keep * 8, (size_t)r->channels, cudaMemcpyDeviceToDevice, ctx->main));
         else {   // overlapping slide: through a scratch row set
             ADSP_TRY(ctx->d_tmp.reserve((size_t)keep * r->channels * 8));

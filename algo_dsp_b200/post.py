@@ -173,6 +173,13 @@ class Resampler:
         out = out[:, : got.value]
         return out[0] if one else out
 
+    def process_device(self, in_ptr, n, in_stride, out_ptr, out_cap, out_stride):
+        """Device rows in, device rows out (adsp_resampler_process_device); returns the output samples per channel."""
+        got = C.c_int64()
+        _check(L.load().adsp_resampler_process_device(self._h, C.c_void_p(in_ptr), int(n), int(in_stride), C.c_void_p(out_ptr), int(out_cap), int(out_stride),
+                                                      C.byref(got)))
+        return got.value
+
     def Reset(self):
         L.load().adsp_resampler_reset(self._h)
 

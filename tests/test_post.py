@@ -308,3 +308,38 @@ def test_gpu_resampler_matches_the_reference_loop(conv):
     y2 = post.NewRational(3, 2, channels=4).Process(x2)
     for c in range(4):
         assert np.array_equal(y2[c], PO.Resampler(3, 2).process(x2[c]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("up,down", [(160, 147), (147, 160), (2, 1), (1, 4), (3, 2), (640, 441), (7, 1000)])
+def test_gpu_resampler_device_rows_streaming(conv, up, down):
+    """Device rows read where they are (no work-row copy), several tiles per call, blocks shorter than the history, and the
+    host entry point on the same stream of samples: all bit identical to one whole-signal host call, which the test above pins
+    to the reference loop."""
+    torch = pytest.importorskip("torch")
+    from algo_dsp_b200 import post
+    ch, blocks = 3, (30000, 19990, 10, 3, 5000)
+    total = sum(blocks)
+    x = np.stack([G.white(total, seed=90 + c) for c in range(ch)])
+    whole = post.NewRational(up, down, channels=ch).Process(x)
+    ref1 = PO.Resampler(up, down).process(x[1][:3000])
+    assert np.array_equal(whole[1][: len(ref1)], ref1)
+    r = post.NewRational(up, down, channels=ch)
+    d = torch.tensor(x, device="cuda")
+    cap = whole.shape[1] + 64
+    o = torch.zeros((ch, cap), device="cuda", dtype=torch.float64)
+    pos = opos = 0
+    for i, blk in enumerate(blocks):
+        if i == 3:                                      # one block through the host entry point in the middle of the stream
+            y = r.Process(np.ascontiguousarray(x[:, pos:pos + blk]))
+            got = 0 if y.size == 0 else y.shape[1]
+            if got:
+                o[:, opos:opos + got] = torch.tensor(y, device="cuda")
+        else:
+            got = r.process_device(d.data_ptr() + pos * 8, blk, d.stride(0), o.data_ptr() + opos * 8, cap - opos, o.stride(0))
+        pos += blk
+        opos += got
+    conv.default_context().sync()
+    assert opos == whole.shape[1]
+    assert np.array_equal(o[:, :opos].cpu().numpy(), whole)
+
