@@ -3,7 +3,7 @@
  * dsp/conv hot path of CWBudde/algo-dsp.
  *
  * The reference has no FFI boundary of its own: the boundary it replaces is the exported Go
- * API of package conv (dsp/conv/*.go).  Each entry point below cites the Go symbol
+ * API of package conv (dsp/conv, all .go files).  Each entry point below cites the Go symbol
  * (file:line under /root/reference) whose behaviour it reproduces; a cgo shim with the
  * unchanged Go signatures sits directly on top.
  *

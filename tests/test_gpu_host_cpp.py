@@ -8,19 +8,22 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _compile(tmp_path):
-    exe = str(tmp_path / "conv_host_test")
+def _compile(tmp_path, name="conv_host_test"):
+    exe = str(tmp_path / name)
     pkg = os.path.join(ROOT, "algo_dsp_b200")
-    subprocess.run(["g++", "-std=c++17", os.path.join(pkg, "host", "conv_host_test.cpp"), "-o", exe, "-L" + pkg, "-lalgodsp_cuda",
+    subprocess.run(["g++", "-std=c++17", "-Wall", os.path.join(pkg, "host", name + ".cpp"), "-o", exe, "-L" + pkg, "-lalgodsp_cuda",
                     "-Wl,-rpath," + pkg], check=True)
     return exe
 
 
-def test_cpp_host_mirror_compiles_and_links(tmp_path):
-    _compile(tmp_path)
+@pytest.mark.parametrize("name", ["conv_host_test", "post_host_test"])
+def test_cpp_host_mirror_compiles_and_links(tmp_path, name):
+    _compile(tmp_path, name)
 
 
 @pytest.mark.gpu
-def test_cpp_host_mirror_runs(tmp_path):
-    r = subprocess.run([_compile(tmp_path)], capture_output=True, text=True)
-    assert r.returncode == 0 and "conv_host_test: ok" in r.stdout, r.stdout + r.stderr
+@pytest.mark.parametrize("name", ["conv_host_test", "post_host_test"])
+def test_cpp_host_mirror_runs(tmp_path, name):
+    """conv.hpp (dsp/conv) and post.hpp (measure/ir, measure/sweep, dsp/filter/fir, dsp/resample, dsp/signal)."""
+    r = subprocess.run([_compile(tmp_path, name)], capture_output=True, text=True)
+    assert r.returncode == 0 and name + ": ok" in r.stdout, r.stdout + r.stderr
