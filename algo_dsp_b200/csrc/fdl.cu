@@ -50,11 +50,49 @@ struct StageGeom {
     long long off;    // IR offset of the stage = output delay of its blocks
 };
 
+// Window of firing m of a stage with partition size B: x[(m-1)B, (m+1)B), zero before the stream start.  The input rows are
+// RINGS: the sample of stream time t sits at index t & xmask (xmask = -1: a plain row that starts at time 0), so a call
+// only appends its samples -- no history slide.
+template <typename T, int L2>
+__device__ __forceinline__ void fdl_load_window(cpx<T> (&e)[16], const T *__restrict__ xbuf, long long xstride, long long xmask, int channels, int pair,
+                                                long long m, int j, bool active) {
+    constexpr int TPF = FftShape<L2>::TPF, B = L2 / 2;
+    const long long w0 = (m - 1) * B;
+    const int ca = 2 * pair, cb = 2 * pair + 1;
+    const T *xa = xbuf + (long long)ca * xstride;
+    const T *xb = xbuf + (long long)cb * xstride;
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        const long long t = w0 + j + q * TPF;
+        e[q].x = (active && t >= 0) ? xa[t & xmask] : (T)0;
+        e[q].y = (active && t >= 0 && cb < channels) ? xb[t & xmask] : (T)0;
+    }
+}
+
+// overlap-save extraction of an inverse transform: position i >= B of the circular result is stream time (m-1)B + off + i
+template <typename T, int L2>
+__device__ __forceinline__ void fdl_accumulate(const cpx<T> (&e)[16], T *__restrict__ acc, long long acc_stride, long long acc_mask, int channels, int pair,
+                                               long long m, long long off, int j) {
+    constexpr int TPF = FftShape<L2>::TPF, B = L2 / 2;
+    const int ca = 2 * pair, cb = 2 * pair + 1;
+    T *aa = acc + (long long)ca * acc_stride;
+    T *ab = acc + (long long)cb * acc_stride;
+    const long long tbase = m * B + off - B;
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        const int i = j + q * TPF;
+        if (i >= B) {
+            const long long t = (tbase + i) & acc_mask;
+            aa[t] += e[q].x;
+            if (cb < channels) ab[t] += e[q].y;
+        }
+    }
+}
+
 // Forward transforms of the blocks of one stage that complete inside this chunk.
-// window of firing m: x[(m-1)B, (m+1)B); xbuf row holds x[t0, t0 + len), zero before the stream start.
 template <typename T, int L2>
 __global__ void __launch_bounds__(FdlShape<L2>::THREADS, FdlShape<L2>::MIN_CTAS)
-fdl_forward(const T *__restrict__ xbuf, long long xstride, long long t0, int channels, long long m0, int nfire, int ring,
+fdl_forward(const T *__restrict__ xbuf, long long xstride, long long xmask, int channels, long long m0, int nfire, int ring,
             cpx<T> *__restrict__ fdl, const cpx<T> *__restrict__ tw) {
     using C = cpx<T>;
     using Sh = FftShape<L2>;
@@ -69,17 +107,8 @@ fdl_forward(const T *__restrict__ xbuf, long long xstride, long long t0, int cha
     const int f = blockIdx.x * FS::ROWS + row;          // firing inside this launch
     const bool active = f < nfire;
     const long long m = m0 + (active ? f : 0);
-    const long long w0 = (m - 1) * B - t0;               // window start inside the xbuf row (may be < 0 only before the stream start)
-    const int ca = 2 * pair, cb = 2 * pair + 1;
-    const T *xa = xbuf + (long long)ca * xstride;
-    const T *xb = xbuf + (long long)cb * xstride;
     C e[16];
-#pragma unroll
-    for (int q = 0; q < 16; q++) {
-        const long long i = w0 + j + q * TPF;
-        e[q].x = (active && i >= 0) ? xa[i] : (T)0;
-        e[q].y = (active && i >= 0 && cb < channels) ? xb[i] : (T)0;
-    }
+    fdl_load_window<T, L2>(e, xbuf, xstride, xmask, channels, pair, m, j, active);
     RowAddr<T, Sh::R0> addr{row * L2};
     CtaGate gate;
     cta_fft<T, L2, false>(e, buf, addr, stw, j, gate);
@@ -88,6 +117,43 @@ fdl_forward(const T *__restrict__ xbuf, long long xstride, long long t0, int cha
 #pragma unroll
         for (int q = 0; q < 16; q++) dst[q * TPF] = e[q];
     }
+}
+
+// A stage with ONE partition needs no delay line: window -> forward transform -> x H -> inverse transform -> accumulate, in
+// one launch (the short stages of a low-latency layout: a 128-sample real-time block fires stage 0 on every call).
+// The forward transform leaves every thread with the 16 bins the inverse starts from, so the product stays in registers.
+template <typename T, int L2>
+__global__ void __launch_bounds__(FdlShape<L2>::THREADS, FdlShape<L2>::MIN_CTAS)
+fdl_fused_single(const T *__restrict__ xbuf, long long xstride, long long xmask, int channels, long long m0, int nfire, const cpx<T> *__restrict__ H,
+                 long long off, T *__restrict__ acc, long long acc_stride, long long acc_mask, const cpx<T> *__restrict__ tw) {
+    using C = cpx<T>;
+    using Sh = FftShape<L2>;
+    using FS = FdlShape<L2>;
+    constexpr int TPF = Sh::TPF;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C *buf = reinterpret_cast<C *>(smem_raw);
+    C *stw = buf + FS::ROWS * L2;
+    load_tw_smem<T, L2>(stw, tw, threadIdx.x, FS::THREADS);
+    const int row = threadIdx.x / TPF, j = threadIdx.x % TPF;
+    const int pair = blockIdx.y;
+    const int f = blockIdx.x * FS::ROWS + row;
+    const bool active = f < nfire;
+    const long long m = m0 + (active ? f : 0);
+    C e[16];
+    fdl_load_window<T, L2>(e, xbuf, xstride, xmask, channels, pair, m, j, active);
+    RowAddr<T, Sh::R0> addr{row * L2};
+    CtaGate gate;
+    cta_fft<T, L2, false>(e, buf, addr, stw, j, gate);
+#pragma unroll
+    for (int q0 = 0; q0 < 16; q0 += 4) {              // four spectrum values in flight: the kernel stays inside 128 registers
+        C h[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) h[q] = __ldg(&H[j + (q0 + q) * TPF]);
+#pragma unroll
+        for (int q = 0; q < 4; q++) e[q0 + q] = cmul(e[q0 + q], h[q]);
+    }
+    cta_fft<T, L2, true>(e, buf, addr, stw, j, gate);
+    if (active) fdl_accumulate<T, L2>(e, acc, acc_stride, acc_mask, channels, pair, m, off, j);
 }
 
 // Fused spectral multiply-accumulate over the stage's partitions + inverse transform + overlap-save extraction:
@@ -140,21 +206,7 @@ fdl_mac_inverse(const cpx<T> *__restrict__ fdl, const cpx<T> *__restrict__ H, in
     RowAddr<T, Sh::R0> addr{row * L2};
     CtaGate gate;
     cta_fft<T, L2, true>(e, buf, addr, stw, j, gate);
-    if (active) {
-        const int ca = 2 * pair, cb = 2 * pair + 1;
-        T *aa = acc + (long long)ca * acc_stride;
-        T *ab = acc + (long long)cb * acc_stride;
-        const long long tbase = m * B + off - B;      // position i of the circular result maps to time tbase + i, i >= B
-#pragma unroll
-        for (int q = 0; q < 16; q++) {
-            const int i = j + q * TPF;
-            if (i >= B) {
-                const long long t = (tbase + i) & acc_mask;
-                aa[t] += e[q].x;
-                if (cb < channels) ab[t] += e[q].y;
-            }
-        }
-    }
+    if (active) fdl_accumulate<T, L2>(e, acc, acc_stride, acc_mask, channels, pair, m, off, j);
 }
 
 // Spectral multiply-accumulate of a long stage, tiled over BINS instead of firings: one thread owns one bin of FT
@@ -212,7 +264,8 @@ fdl_mac_bins(const cpx<T> *__restrict__ fdl, const cpx<T> *__restrict__ H, int c
 // the dry input:  out = dry * x + wet * y   (ConvolutionReverb.ProcessInPlace, convolution.go:76-80)
 template <typename T>
 __global__ void fdl_emit(T *__restrict__ acc, long long acc_stride, long long acc_mask, long long tout, long long n,
-                         const T *__restrict__ xin, long long xstride, T *__restrict__ out, long long out_stride, int mix, T wet, T dry) {
+                         const T *__restrict__ xring, long long xstride, long long xmask, long long tin, T *__restrict__ out, long long out_stride, int mix,
+                         T wet, T dry) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int c = blockIdx.y;
     if (i >= n) return;
@@ -223,7 +276,7 @@ __global__ void fdl_emit(T *__restrict__ acc, long long acc_stride, long long ac
         y = *a;
         *a = (T)0;
     }
-    if (mix) y = dry * xin[(long long)c * xstride + i] + wet * y;
+    if (mix) y = dry * xring[(long long)c * xstride + ((tin + i) & xmask)] + wet * y;   // the call's own input, from the ring
     out[(long long)c * out_stride + i] = y;
 }
 
@@ -242,8 +295,9 @@ struct FdlEngine {
     std::vector<StageGeom> stages;
     std::vector<void *> d_H, d_fdl;           // per stage: spectra [count][2B], delay line [pairs][ring][2B]
     std::vector<const void *> d_tw;           // per stage: twiddle table of the 2B-point transform
-    long long HX = 0;                         // input history kept in front of each chunk (2*B_max)
-    DevBuf xbuf, xbuf_alt, acc, d_io_out, yscratch;   // xbuf / xbuf_alt: input rows [history | chunk], ping-pong
+    long long HX = 0;                         // input history a firing may reach back to (2*B_max)
+    long long XL = 0;                         // ring length of an input row: power of two >= HX + FDL_CHUNK
+    DevBuf xbuf, acc, d_io_out, yscratch;     // xbuf: input rows as rings, time t at index t & (XL - 1)
     long long acc_len = 0;
     long long pos = 0;                        // samples consumed so far
     double wet = 1.0, dry = 1.0;
@@ -252,7 +306,11 @@ struct FdlEngine {
 namespace {
 
 struct FwdArgs {
-    const void *xbuf; long long xstride, t0; int channels, pairs; long long m0; int nfire, ring; void *fdl; const void *tw;
+    const void *xbuf; long long xstride, xmask; int channels, pairs; long long m0; int nfire, ring; void *fdl; const void *tw;
+};
+struct FusedArgs {
+    const void *xbuf; long long xstride, xmask; int channels, pairs; long long m0; int nfire; const void *H; long long off; void *acc; long long acc_len;
+    const void *tw;
 };
 struct MacArgs {
     const void *fdl, *H; int count, ring; long long m0; int nfire; long long off; void *acc; long long acc_len; int channels, pairs;
@@ -267,7 +325,7 @@ template <typename T, int L2> adsp_status fdl_forward_launch(adsp_ctx *ctx, cons
         ADSP_CUDA(cudaFuncSetAttribute(fdl_forward<T, L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((a.nfire + FS::ROWS - 1) / FS::ROWS), (unsigned)a.pairs);
     LaunchTimer lt(ctx, ctx->main, KK_OTHER);
-    fdl_forward<T, L2><<<grid, FS::THREADS, smem, ctx->main>>>((const T *)a.xbuf, a.xstride, a.t0, a.channels, a.m0, a.nfire, a.ring,
+    fdl_forward<T, L2><<<grid, FS::THREADS, smem, ctx->main>>>((const T *)a.xbuf, a.xstride, a.xmask, a.channels, a.m0, a.nfire, a.ring,
                                                              (cpx<T> *)a.fdl, (const cpx<T> *)a.tw);
     count_launch(ctx);
     ADSP_CUDA(cudaGetLastError());
@@ -290,6 +348,21 @@ template <typename T, int L2> adsp_status fdl_mac_launch(adsp_ctx *ctx, const Ma
     return ADSP_OK;
 }
 
+template <typename T, int L2> adsp_status fdl_fused_launch(adsp_ctx *ctx, const FusedArgs &a) {
+    using FS = FdlShape<L2>;
+    const size_t smem = ((size_t)FS::ROWS * L2 + FftShape<L2>::TW_ENTRIES) * sizeof(cpx<T>);
+    static AttrFlags once;
+    if (once.need(ctx->device) && smem > 48 * 1024)
+        ADSP_CUDA(cudaFuncSetAttribute(fdl_fused_single<T, L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((a.nfire + FS::ROWS - 1) / FS::ROWS), (unsigned)a.pairs);
+    LaunchTimer lt(ctx, ctx->main, KK_OTHER);
+    fdl_fused_single<T, L2><<<grid, FS::THREADS, smem, ctx->main>>>((const T *)a.xbuf, a.xstride, a.xmask, a.channels, a.m0, a.nfire, (const cpx<T> *)a.H, a.off,
+                                                                  (T *)a.acc, a.acc_len, a.acc_len - 1, (const cpx<T> *)a.tw);
+    count_launch(ctx);
+    ADSP_CUDA(cudaGetLastError());
+    return ADSP_OK;
+}
+
 #define ADSP_FDL_DISPATCH(FN, L2v, ...)                                                      \
     switch (L2v) {                                                                           \
     case 16:   return FN<T, 16>(__VA_ARGS__);                                                \
@@ -306,14 +379,13 @@ template <typename T, int L2> adsp_status fdl_mac_launch(adsp_ctx *ctx, const Ma
 
 template <typename T> adsp_status fdl_forward_any(adsp_ctx *ctx, int L2, const FwdArgs &a) { ADSP_FDL_DISPATCH(fdl_forward_launch, L2, ctx, a) }
 template <typename T> adsp_status fdl_mac_any(adsp_ctx *ctx, int L2, const MacArgs &a) { ADSP_FDL_DISPATCH(fdl_mac_launch, L2, ctx, a) }
+template <typename T> adsp_status fdl_fused_any(adsp_ctx *ctx, int L2, const FusedArgs &a) { ADSP_FDL_DISPATCH(fdl_fused_launch, L2, ctx, a) }
 
 template <typename T> adsp_status fdl_build(FdlEngine *e, const T *d_kernel) {
     adsp_ctx *ctx = e->ctx;
     const size_t ns = e->stages.size();
     e->d_H.assign(ns, nullptr); e->d_fdl.assign(ns, nullptr); e->d_tw.assign(ns, nullptr);
-    const long long xstride = e->HX + FDL_CHUNK;
-    ADSP_TRY(e->xbuf.reserve((size_t)xstride * (size_t)(2 * e->pairs) * sizeof(T)));
-    ADSP_TRY(e->xbuf_alt.reserve((size_t)xstride * (size_t)(2 * e->pairs) * sizeof(T)));
+    ADSP_TRY(e->xbuf.reserve((size_t)e->XL * (size_t)(2 * e->pairs) * sizeof(T)));
     ADSP_TRY(e->acc.reserve((size_t)e->acc_len * (size_t)(2 * e->pairs) * sizeof(T)));
     for (size_t s = 0; s < ns; s++) {
         const StageGeom &g = e->stages[s];
@@ -322,7 +394,7 @@ template <typename T> adsp_status fdl_build(FdlEngine *e, const T *d_kernel) {
         ADSP_TRY(get_tw_table<T>(ctx, L2, &tw));
         e->d_tw[s] = tw;
         ADSP_CUDA(cudaMalloc(&e->d_H[s], (size_t)g.count * L2 * sizeof(cpx<T>)));
-        ADSP_CUDA(cudaMalloc(&e->d_fdl[s], (size_t)e->pairs * g.ring * L2 * sizeof(cpx<T>)));
+        if (g.count > 1) ADSP_CUDA(cudaMalloc(&e->d_fdl[s], (size_t)e->pairs * g.ring * L2 * sizeof(cpx<T>)));   // one partition: no delay line
         // IR spectra through the same forward kernel: a staging row holds partition p at times [2pB, 2pB + B) and
         // zeros at [2pB + B, 2pB + 2B), so the window of "firing" m = 2p + 1 is exactly [h_p | 0] (partition in the
         // first half, as overlap-save with outputs taken from [B, 2B) needs).
@@ -339,7 +411,7 @@ template <typename T> adsp_status fdl_build(FdlEngine *e, const T *d_kernel) {
             if (len > 0)
                 ADSP_CUDA(cudaMemcpyAsync((T *)row.p + 2LL * p * g.B, d_kernel + k0, (size_t)len * sizeof(T), cudaMemcpyDeviceToDevice, ctx->main));
         }
-        FwdArgs fa{row.p, row_len, 0, 1, 1, 1, 2 * g.count - 1, ring_tmp, spec.p, tw};
+        FwdArgs fa{row.p, row_len, -1LL, 1, 1, 1, 2 * g.count - 1, ring_tmp, spec.p, tw};    // xmask -1: a plain row from time 0
         adsp_status st = fdl_forward_any<T>(ctx, L2, fa);
         for (int p = 0; p < g.count && st == ADSP_OK; p++)
             if (cudaMemcpyAsync((cpx<T> *)e->d_H[s] + (size_t)p * L2, (cpx<T> *)spec.p + (size_t)(2 * p + 1) * L2, (size_t)L2 * sizeof(cpx<T>),
@@ -355,28 +427,31 @@ template <typename T> adsp_status fdl_build(FdlEngine *e, const T *d_kernel) {
 template <typename T> adsp_status fdl_reset_t(FdlEngine *e) {
     adsp_ctx *ctx = e->ctx;
     for (size_t s = 0; s < e->stages.size(); s++)
-        ADSP_CUDA(cudaMemsetAsync(e->d_fdl[s], 0, (size_t)e->pairs * e->stages[s].ring * 2 * e->stages[s].B * sizeof(cpx<T>), ctx->main));
+        if (e->d_fdl[s]) ADSP_CUDA(cudaMemsetAsync(e->d_fdl[s], 0, (size_t)e->pairs * e->stages[s].ring * 2 * e->stages[s].B * sizeof(cpx<T>), ctx->main));
     ADSP_CUDA(cudaMemsetAsync(e->xbuf.p, 0, e->xbuf.cap, ctx->main));
-    ADSP_CUDA(cudaMemsetAsync(e->xbuf_alt.p, 0, e->xbuf_alt.cap, ctx->main));
     ADSP_CUDA(cudaMemsetAsync(e->acc.p, 0, e->acc.cap, ctx->main));
     e->pos = 0;
     ADSP_CUDA(cudaStreamSynchronize(ctx->main));
     return ADSP_OK;
 }
 
-// one chunk (n <= FDL_CHUNK) whose input already sits in xbuf rows at [HX, HX + n)
+// one chunk (n <= FDL_CHUNK) whose input already sits in the rings at times [pos, pos + n)
 template <typename T>
-adsp_status fdl_chunk(FdlEngine *e, long long n, const T *d_in, long long in_stride, T *d_out, long long out_stride, bool mix) {
+adsp_status fdl_chunk(FdlEngine *e, long long n, T *d_out, long long out_stride, bool mix) {
     adsp_ctx *ctx = e->ctx;
-    const long long xstride = e->HX + FDL_CHUNK;
-    const long long t0 = e->pos - e->HX;                         // stream time of xbuf[.][0]
+    const long long xstride = e->XL, xmask = e->XL - 1;
     for (size_t s = 0; s < e->stages.size(); s++) {
         const StageGeom &g = e->stages[s];
         const long long m_first = e->pos / g.B;                  // blocks with (m+1)*B in (pos, pos+n]
         const long long m_last = (e->pos + n) / g.B - 1;
         const long long nf = m_last - m_first + 1;
         if (nf <= 0) continue;
-        FwdArgs fa{e->xbuf.p, xstride, t0, e->channels, e->pairs, m_first, (int)nf, g.ring, e->d_fdl[s], e->d_tw[s]};
+        if (g.count == 1) {
+            FusedArgs ua{e->xbuf.p, xstride, xmask, e->channels, e->pairs, m_first, (int)nf, e->d_H[s], g.off, e->acc.p, e->acc_len, e->d_tw[s]};
+            ADSP_TRY(fdl_fused_any<T>(ctx, 2 * g.B, ua));
+            continue;
+        }
+        FwdArgs fa{e->xbuf.p, xstride, xmask, e->channels, e->pairs, m_first, (int)nf, g.ring, e->d_fdl[s], e->d_tw[s]};
         ADSP_TRY(fdl_forward_any<T>(ctx, 2 * g.B, fa));
         if (g.count >= FDL_SPLIT_MIN_COUNT && 2 * g.B >= 128) {
             // long stage: bin-tiled MAC into a scratch spectrum, then the inverse kernel on Y (H == null, one "tap")
@@ -402,15 +477,10 @@ adsp_status fdl_chunk(FdlEngine *e, long long n, const T *d_in, long long in_str
         const int nc = std::min(65535, e->channels - c0);
         dim3 grid((unsigned)((n + 255) / 256), (unsigned)nc);
         fdl_emit<T><<<grid, 256, 0, ctx->main>>>((T *)e->acc.p + (long long)c0 * e->acc_len, e->acc_len, e->acc_len - 1, e->pos - e->latency, n,
-                                                 d_in + (long long)c0 * in_stride, in_stride, d_out + (long long)c0 * out_stride, out_stride,
-                                                 mix ? 1 : 0, (T)e->wet, (T)e->dry);
+                                                 (const T *)e->xbuf.p + (long long)c0 * xstride, xstride, xmask, e->pos, d_out + (long long)c0 * out_stride,
+                                                 out_stride, mix ? 1 : 0, (T)e->wet, (T)e->dry);
         count_launch(ctx);
     }
-    // keep the last HX input samples as the history of the next chunk: one strided copy into the other buffer
-    T *xb = (T *)e->xbuf.p;
-    ADSP_CUDA(cudaMemcpy2DAsync(e->xbuf_alt.p, (size_t)xstride * sizeof(T), xb + n, (size_t)xstride * sizeof(T), (size_t)e->HX * sizeof(T),
-                                (size_t)e->channels, cudaMemcpyDeviceToDevice, ctx->main));
-    std::swap(e->xbuf, e->xbuf_alt);
     e->pos += n;
     ADSP_CUDA(cudaGetLastError());
     return ADSP_OK;
@@ -419,22 +489,26 @@ adsp_status fdl_chunk(FdlEngine *e, long long n, const T *d_in, long long in_str
 template <typename T>
 adsp_status fdl_process_t(FdlEngine *e, const T *in, long long n, long long in_stride, T *out, long long out_stride, bool host, bool mix) {
     adsp_ctx *ctx = e->ctx;
-    const long long xstride = e->HX + FDL_CHUNK;
+    const long long xstride = e->XL;
     for (long long o = 0; o < n; o += FDL_CHUNK) {
-        T *xb = (T *)e->xbuf.p;                 // ping-pongs with xbuf_alt every chunk
+        T *xb = (T *)e->xbuf.p;
         const long long len = std::min(FDL_CHUNK, n - o);
         const cudaMemcpyKind kin = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
-        ADSP_CUDA(cudaMemcpy2DAsync(xb + e->HX, (size_t)xstride * sizeof(T), in + o, (size_t)in_stride * sizeof(T), (size_t)len * sizeof(T),
+        // append the chunk to the rings at time pos (two pieces when it crosses the end of the ring)
+        const long long at = e->pos & (e->XL - 1), first = std::min(len, e->XL - at);
+        ADSP_CUDA(cudaMemcpy2DAsync(xb + at, (size_t)xstride * sizeof(T), in + o, (size_t)in_stride * sizeof(T), (size_t)first * sizeof(T),
                                     (size_t)e->channels, kin, ctx->main));
+        if (first < len)
+            ADSP_CUDA(cudaMemcpy2DAsync(xb, (size_t)xstride * sizeof(T), in + o + first, (size_t)in_stride * sizeof(T), (size_t)(len - first) * sizeof(T),
+                                        (size_t)e->channels, kin, ctx->main));
         if (host) {
             ADSP_TRY(e->d_io_out.reserve((size_t)FDL_CHUNK * (size_t)e->channels * sizeof(T)));
             T *dout = (T *)e->d_io_out.p;
-            ADSP_TRY(fdl_chunk<T>(e, len, xb + e->HX, xstride, dout, FDL_CHUNK, mix));
-            // NB: fdl_emit reads the dry signal from xbuf BEFORE the history slide (stream order) -> pass xbuf rows as xin
+            ADSP_TRY(fdl_chunk<T>(e, len, dout, FDL_CHUNK, mix));
             ADSP_CUDA(cudaMemcpy2DAsync(out + o, (size_t)out_stride * sizeof(T), dout, (size_t)FDL_CHUNK * sizeof(T), (size_t)len * sizeof(T),
                                         (size_t)e->channels, cudaMemcpyDeviceToHost, ctx->main));
         } else {
-            ADSP_TRY(fdl_chunk<T>(e, len, xb + e->HX, xstride, out + o, out_stride, mix));
+            ADSP_TRY(fdl_chunk<T>(e, len, out + o, out_stride, mix));
         }
     }
     if (host) ADSP_CUDA(cudaStreamSynchronize(ctx->main));
@@ -479,6 +553,8 @@ adsp_status fdl_create(adsp_ctx *ctx, const void *d_kernel, long long K, int min
     const long long L = e->latency;
     const long long bl = e->stages.back().B;
     e->HX = 2 * bl;
+    e->XL = 1;
+    while (e->XL < e->HX + FDL_CHUNK) e->XL *= 2;
     long long need = FDL_CHUNK + e->stages.back().off + 2 * bl + L + 64;
     long long al = 1;
     while (al < need) al *= 2;
@@ -494,7 +570,7 @@ void fdl_destroy(FdlEngine *e) {
     if (!e) return;
     for (void *p : e->d_H) if (p) cudaFree(p);
     for (void *p : e->d_fdl) if (p) cudaFree(p);
-    e->xbuf.release(); e->xbuf_alt.release(); e->acc.release(); e->d_io_out.release(); e->yscratch.release();
+    e->xbuf.release(); e->acc.release(); e->d_io_out.release(); e->yscratch.release();
     delete e;
 }
 
