@@ -382,6 +382,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     else:
         dist = None
+    if world > 1:
+        # N ranks share the host's cores: the library's copy threads (default 3/4 of the cores, for one process) are divided
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+        os.environ.setdefault("ADSP_STAGE_THREADS", str(max(2, (3 * (os.cpu_count() or 8)) // (4 * max(1, local_world)))))
     from algo_dsp_b200 import _lib as L, conv, siggen as G
     lib = L.load()
 
