@@ -9,8 +9,10 @@ namespace adsp {
 // Sliding-window direct convolution.  Replaces the n*m MAC loop of the reference
 // (dsp/conv/conv.go:117-154: dst[i+j] += a[i]*b[j]).  For each output k the products are
 // accumulated in the reference's order (input index i ascending, i.e. tap index descending).
-// CTA = 128 threads, each thread produces RO consecutive outputs from a register window;
-// the signal tile and the tap chunk are staged in shared memory.
+// CTA = 128 threads, each thread produces RO consecutive outputs from a register window over a signal tile staged in
+// shared memory; the outputs leave through the same tile (direct_store_tile).  Three tap sources: kernel parameters for up
+// to 64 taps (direct_conv_ctaps_kernel) and up to 1024 taps (direct_conv_ctapsn_kernel) shared by all channels, shared memory
+// for per-channel or longer kernels (direct_conv_kernel).  fir_inplace_kernel is the second one walking a row in place.
 constexpr int DIRECT_THREADS = 128;
 #ifndef ADSP_DIRECT_RO
 #define ADSP_DIRECT_RO 8
