@@ -54,6 +54,14 @@ __device__ __forceinline__ void direct_chunk(T (&acc)[DIRECT_RO], const T *sa, c
 // conflict free, and every warp store covers 32 consecutive samples (2 wavefronts).  No alignment requirement.
 template <typename T>
 __device__ __forceinline__ void direct_store_tile(const T (&acc)[DIRECT_RO], T *sa, T *__restrict__ oc, long long k0, long long out_len, int t) {
+#if defined(ADSP_DIRECT_STORE_STRIDED)                  // the round-1 store, kept for the ncu A/B in profiles/: RO outputs per lane, 64 bytes apart
+#pragma unroll
+    for (int r = 0; r < DIRECT_RO; r++) {
+        const long long k = k0 + (long long)t * DIRECT_RO + r;
+        if (k < out_len) oc[k] = acc[r];
+    }
+    return;
+#endif
 #define ADSP_SA(i) sa[(i) + ((i) >> DIRECT_PAD_SHIFT)]
     __syncthreads();                                   // every thread has finished reading its window
 #pragma unroll
