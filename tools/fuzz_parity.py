@@ -1,0 +1,173 @@
+"""Randomised parity sweep through the public Python mirror (-> C ABI -> CUDA) against the CPU oracle: random lengths, kernel
+sizes, block splits and batch shapes for every family on the path.  Not part of the test suite (the suite pins fixed shapes);
+a soak run for a GPU box:
+    python tools/fuzz_parity.py [seconds=120] [seed=1]
+Prints one line per family with the case count and the worst relative L2 error; exits 1 on the first violation."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from algo_dsp_b200 import conv, post, siggen as G
+from oracle import oracle as O, post_oracle as PO
+
+budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+TOL64, TOL32 = 1e-12, 1e-5
+worst, count = {}, {}
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    d = np.linalg.norm(b)
+    return float(np.linalg.norm(a - b) / d) if d > 0 else float(np.linalg.norm(a - b))
+
+
+def note(fam, err, tol, what):
+    worst[fam] = max(worst.get(fam, 0.0), err)
+    count[fam] = count.get(fam, 0) + 1
+    if not err <= tol:
+        print(f"FAIL {fam}: rel L2 {err:.3e} > {tol:g} for {what}", flush=True)
+        sys.exit(1)
+
+
+def logint(lo, hi):
+    return int(round(np.exp(rng.uniform(np.log(lo), np.log(hi)))))
+
+
+def sig(n):
+    return rng.uniform(-1, 1, n)
+
+
+def case_convolve():
+    n, m = logint(1, 300000), logint(1, 40000)
+    a, b = sig(n), sig(m)
+    note("Convolve", rel(conv.Convolve(a, b), O.convolve(a, b)), TOL64, (n, m))
+
+
+def case_ols():
+    K, n = logint(1, 60000), logint(1, 400000)
+    h, x = sig(K), sig(n)
+    fam = rng.choice(["OverlapSave", "OverlapAdd", "OverlapSave32"])
+    if fam == "OverlapSave":
+        note(fam, rel(conv.NewOverlapSave(h, 0).Process(x), O.overlap_save(h, 0, x)), TOL64, (K, n))
+    elif fam == "OverlapAdd":
+        note(fam, rel(conv.NewOverlapAdd(h, 0).Process(x), O.overlap_add(h, 0, x)), TOL64, (K, n))
+    else:
+        h32, x32 = h.astype(np.float32), x.astype(np.float32)
+        got = conv.NewOverlapSave(h32, 0, dtype=np.float32).Process(x32)
+        note(fam, rel(got, O.overlap_save(h32.astype(np.float64), 0, x32.astype(np.float64))), TOL32, (K, n))
+
+
+def case_correlate():
+    n, m = logint(1, 200000), logint(1, 200000)
+    a, b = sig(n), sig(m)
+    ref = O.correlate(a, b)
+    got = conv.Correlate(a, b)
+    note("Correlate", rel(got, ref), TOL64, (n, m))
+    gi, _ = conv.FindPeak(got)
+    ri, _ = O.find_peak(ref)
+    if gi != ri and abs(ref[gi] - ref[ri]) > 1e-9 * abs(ref[ri]):
+        print(f"FAIL FindPeak: {gi} vs {ri} for {(n, m)}")
+        sys.exit(1)
+
+
+def case_correlate_batch():
+    pairs, n, m = int(rng.integers(2, 9)), logint(65, 60000), logint(65, 60000)
+    a = rng.uniform(-1, 1, (pairs, n))
+    shared = bool(rng.integers(0, 2))
+    b = rng.uniform(-1, 1, (pairs, m))
+    if shared:
+        b[:] = b[0]
+    out, pi, pv = conv.CorrelateBatch(a, b)
+    p = int(rng.integers(0, pairs))
+    ref = O.correlate(a[p], b[p])
+    note("CorrelateBatch", rel(out[p], ref), TOL64, (pairs, n, m, shared))
+    ri, rv = O.find_peak(ref)
+    if int(pi[p]) != ri and abs(ref[int(pi[p])] - rv) > 1e-9 * abs(rv):
+        print(f"FAIL CorrelateBatch peak: {int(pi[p])} vs {ri}")
+        sys.exit(1)
+
+
+def case_direct():
+    ch, n, m = int(rng.integers(1, 6)), logint(1, 20000), logint(1, 1500)
+    x = rng.uniform(-1, 1, (ch, n))
+    per_ch = bool(rng.integers(0, 2))
+    k = rng.uniform(-1, 1, (ch, m)) if per_ch else sig(m)
+    y = conv.DirectBatch(x, k)
+    c = int(rng.integers(0, ch))
+    note("Direct", rel(y[c], O.direct(x[c], k[c] if per_ch else k)), TOL64, (ch, n, m, per_ch))
+
+
+def case_fir():
+    ch, taps = int(rng.integers(1, 4)), logint(1, 1400)
+    h = sig(taps)
+    c = h[::-1] if taps >= 32 else h
+    f = post.New(h, channels=ch)
+    total, pos = logint(1, 60000), 0
+    x = rng.uniform(-1, 1, (ch, total))
+    got = np.empty_like(x)
+    while pos < total:
+        blk = min(total - pos, logint(1, 30000))
+        part = x[:, pos:pos + blk].copy()               # ProcessBlock works in place: never hand it a view of x
+        f.ProcessBlock(part)
+        got[:, pos:pos + blk] = part
+        pos += blk
+    r = int(rng.integers(0, ch))
+    note("fir.ProcessBlock", rel(got[r], np.convolve(x[r], c)[:total]), 1e-12, (ch, taps, total))
+    f.Close()
+
+
+def case_resample():
+    up, down = int(rng.integers(1, 200)), int(rng.integers(1, 200))
+    ch, total = int(rng.integers(1, 4)), logint(1, 40000)
+    x = rng.uniform(-1, 1, (ch, total))
+    whole = post.NewRational(up, down, channels=ch).Process(x)
+    r = post.NewRational(up, down, channels=ch)
+    parts, pos = [], 0
+    while pos < total:
+        blk = min(total - pos, logint(1, 20000))
+        y = r.Process(np.ascontiguousarray(x[:, pos:pos + blk]))
+        if y.size:
+            parts.append(y.reshape(ch, -1))
+        pos += blk
+    cat = np.concatenate(parts, axis=1) if parts else np.empty((ch, 0))
+    whole2 = np.asarray(whole).reshape(ch, -1) if np.asarray(whole).size else np.empty((ch, 0))
+    if cat.shape != whole2.shape or not np.array_equal(cat, whole2):
+        print(f"FAIL resample: chunked != whole for {(up, down, ch, total)}")
+        sys.exit(1)
+    small = min(total, 1500)
+    ref = PO.Resampler(up, down).process(x[0][:small])
+    if not np.array_equal(whole2[0][:len(ref)], ref):
+        print(f"FAIL resample: != reference loop for {(up, down, small)}")
+        sys.exit(1)
+    count["resample.Process"] = count.get("resample.Process", 0) + 1
+    worst["resample.Process"] = 0.0
+
+
+def case_partitioned():
+    K, mn = logint(1, 30000), int(rng.integers(5, 9))
+    h = sig(K)
+    total = logint(1, 40000)
+    x = sig(total)
+    p = conv.NewPartitionedConvolution(h, mn, 13)
+    ref = O.Partitioned(h, mn, 13)
+    pos, got, want = 0, [], []
+    while pos < total:
+        blk = min(total - pos, logint(1, 9000))
+        out = np.empty(blk)
+        p.ProcessBlock(np.ascontiguousarray(x[pos:pos + blk]), out)
+        got.append(out)
+        want.append(ref.process_block(x[pos:pos + blk]))
+        pos += blk
+    note("Partitioned.ProcessBlock", rel(np.concatenate(got), np.concatenate(want)), TOL64, (K, mn, total))
+
+
+cases = [case_convolve, case_ols, case_correlate, case_correlate_batch, case_direct, case_fir, case_resample, case_partitioned]
+t0 = time.time()
+i = 0
+while time.time() - t0 < budget:
+    cases[i % len(cases)]()
+    i += 1
+for fam in sorted(count):
+    print(f"{fam:28s} {count[fam]:5d} cases, worst rel L2 {worst[fam]:.2e}")
+print(f"fuzz_parity: ok ({i} cases in {time.time() - t0:.0f} s)")
