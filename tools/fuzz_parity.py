@@ -12,7 +12,7 @@ from oracle import oracle as O, post_oracle as PO
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 TOL64, TOL32 = 1e-12, 1e-5
-worst, count = {}, {}
+worst, count, worst_case = {}, {}, {}
 
 
 def rel(a, b):
@@ -23,7 +23,8 @@ def rel(a, b):
 
 
 def note(fam, err, tol, what):
-    worst[fam] = max(worst.get(fam, 0.0), err)
+    if err >= worst.get(fam, -1.0):
+        worst[fam], worst_case[fam] = err, what
     count[fam] = count.get(fam, 0) + 1
     if not err <= tol:
         print(f"FAIL {fam}: rel L2 {err:.3e} > {tol:g} for {what}", flush=True)
@@ -162,12 +163,46 @@ def case_partitioned():
     note("Partitioned.ProcessBlock", rel(np.concatenate(got), np.concatenate(want)), TOL64, (K, mn, total))
 
 
-cases = [case_convolve, case_ols, case_correlate, case_correlate_batch, case_direct, case_fir, case_resample, case_partitioned]
+def case_ols_batch():
+    ch, K, n = int(rng.integers(1, 12)), logint(1, 40000), logint(1, 200000)
+    h = sig(K)
+    x = rng.uniform(-1, 1, (ch, n))
+    y = conv.NewOverlapSave(h, 0).ProcessBatch(x)
+    c = int(rng.integers(0, ch))
+    note("OverlapSave.ProcessBatch", rel(y[c], O.overlap_save(h, 0, x[c])), TOL64, (ch, K, n))
+
+
+def case_streaming():
+    K = logint(1, 5000)
+    B = 1 << int(rng.integers(4, 13))
+    ols = bool(rng.integers(0, 2))
+    h = sig(K)
+    s = (conv.StreamingOverlapSave if ols else conv.StreamingOverlapAdd)(h, B)
+    ref = O.Streaming(h, B, ols)
+    B = s.BlockSize()
+    worst_e = 0.0
+    for _ in range(int(rng.integers(1, 6))):
+        blk = sig(B)
+        worst_e = max(worst_e, rel(s.ProcessBlock(blk), ref.process_block(blk)))
+    note("Streaming.ProcessBlock", worst_e, 1e-11, (K, B, ols))
+
+
+def case_deconvolve():
+    n, m = logint(8, 50000), logint(1, 2000)
+    x, k = sig(n), sig(m)
+    k[0] += 2.0                                            # well conditioned
+    y = O.convolve(x, k)
+    got = conv.Deconvolve(y, k, conv.DeconvOptions(conv.DeconvRegularized, 1e-9))
+    ref = O.deconvolve(y, k, O.DECONV_REGULARIZED, 1e-9)
+    note("Deconvolve", rel(got, ref), 1e-9, (n, m))
+
+
+cases = [case_ols_batch, case_streaming, case_deconvolve, case_convolve, case_ols, case_correlate, case_correlate_batch, case_direct, case_fir, case_resample, case_partitioned]
 t0 = time.time()
 i = 0
 while time.time() - t0 < budget:
     cases[i % len(cases)]()
     i += 1
 for fam in sorted(count):
-    print(f"{fam:28s} {count[fam]:5d} cases, worst rel L2 {worst[fam]:.2e}")
+    print(f"{fam:28s} {count[fam]:5d} cases, worst rel L2 {worst[fam]:.2e} at {worst_case.get(fam)}")
 print(f"fuzz_parity: ok ({i} cases in {time.time() - t0:.0f} s)")
