@@ -591,6 +591,10 @@ class PartitionedConvolution(_Plan):
             raise ValueError("block must have one row per channel")
         _check(L.load().adsp_partitioned_process_in_place_batch(self._h, _p(block), n, n))
 
+    def process_in_place_device(self, ptr, n, stride):
+        """ProcessInPlace on device rows ([channels] rows of n samples, `stride` elements apart); asynchronous."""
+        _check(L.load().adsp_partitioned_process_in_place_batch_device(self._h, C.c_void_p(ptr), int(n), int(stride)))
+
     def Latency(self):
         return int(L.load().adsp_partitioned_latency(self._h))
 

@@ -197,7 +197,66 @@ def case_deconvolve():
     note("Deconvolve", rel(got, ref), 1e-9, (n, m))
 
 
-cases = [case_ols_batch, case_streaming, case_deconvolve, case_convolve, case_ols, case_correlate, case_correlate_batch, case_direct, case_fir, case_resample, case_partitioned]
+def case_device_rows():
+    """Device entry points with row strides larger than the rows: OLS plan, block FIR, resampler, reverb wet/dry in place."""
+    import torch
+    ctx = conv.default_context()
+    ch, n = int(rng.integers(1, 7)), logint(1, 60000)
+    pad_in, pad_out = int(rng.integers(0, 70)), int(rng.integers(0, 70))
+    x = rng.uniform(-1, 1, (ch, n))
+    xd = torch.zeros((ch, n + pad_in), device="cuda", dtype=torch.float64)
+    xd[:, :n] = torch.tensor(x, device="cuda")
+    which = int(rng.integers(0, 4))
+    if which == 0:
+        K = logint(1, 20000)
+        h = sig(K)
+        plan = conv.NewOverlapSave(h, 0)
+        ol = n + K - 1
+        yd = torch.full((ch, ol + pad_out), 7.0, device="cuda", dtype=torch.float64)
+        plan.process_device(xd.data_ptr(), n, ch, xd.stride(0), yd.data_ptr(), yd.stride(0))
+        plan.sync()
+        c = int(rng.integers(0, ch))
+        note("OverlapSave.process_device", rel(yd[c, :ol].cpu().numpy(), O.overlap_save(h, 0, x[c])), TOL64, (ch, K, n, pad_in, pad_out))
+        assert pad_out == 0 or bool((yd[:, ol:] == 7.0).all()), "wrote beyond the row"
+    elif which == 1:
+        taps = logint(1, 1400)
+        h = sig(taps)
+        f = post.New(h, channels=ch)
+        f.process_block_device(xd.data_ptr(), n, xd.stride(0))
+        ctx.sync()
+        c = int(rng.integers(0, ch))
+        cc = h[::-1] if taps >= 32 else h
+        note("fir.process_block_device", rel(xd[c, :n].cpu().numpy(), np.convolve(x[c], cc)[:n]), TOL64, (ch, taps, n, pad_in))
+        assert pad_in == 0 or bool((xd[:, n:] == 0).all()), "wrote beyond the row"
+        f.Close()
+    elif which == 2:
+        up, down = int(rng.integers(1, 200)), int(rng.integers(1, 200))
+        r = post.NewRational(up, down, channels=ch)
+        want = np.asarray(post.NewRational(up, down, channels=ch).Process(x)).reshape(ch, -1) if n else np.empty((ch, 0))
+        cap = want.shape[1] + pad_out
+        od = torch.full((ch, max(cap, 1)), 7.0, device="cuda", dtype=torch.float64)
+        got = r.process_device(xd.data_ptr(), n, xd.stride(0), od.data_ptr(), cap, od.stride(0))
+        ctx.sync()
+        if got != want.shape[1] or not np.array_equal(od[:, :got].cpu().numpy(), want):
+            print(f"FAIL resample.process_device: {(up, down, ch, n)}")
+            sys.exit(1)
+        count["resample.process_device"] = count.get("resample.process_device", 0) + 1
+        worst["resample.process_device"] = 0.0
+    else:
+        K, mn = logint(1, 20000), int(rng.integers(5, 9))
+        h = sig(K)
+        wet, dry = float(rng.uniform(0, 1)), float(rng.uniform(0, 1))
+        rv = conv.NewConvolutionReverb(h, mn, channels=ch)
+        rv.SetWetDry(wet, dry)
+        rv.process_in_place_device(xd.data_ptr(), n, xd.stride(0))
+        ctx.sync()
+        c = int(rng.integers(0, ch))
+        wet_sig = np.concatenate([np.zeros(rv.Latency()), O.convolve(x[c], h)])[:n]
+        ref = dry * x[c] + wet * wet_sig                    # convolution.go:76-80
+        note("reverb device rows", rel(xd[c, :n].cpu().numpy(), ref), 1e-11, (ch, K, mn, n, pad_in))
+
+
+cases = [case_device_rows, case_ols_batch, case_streaming, case_deconvolve, case_convolve, case_ols, case_correlate, case_correlate_batch, case_direct, case_fir, case_resample, case_partitioned]
 t0 = time.time()
 i = 0
 while time.time() - t0 < budget:
