@@ -14,6 +14,7 @@ libalgodsp_cuda on the GPU -- there is no CPU path in this module.
 from __future__ import annotations
 
 import ctypes as C
+import threading
 
 import numpy as np
 
@@ -158,12 +159,18 @@ def pinned_empty(shape, dtype=np.float64):
 
 
 _default_ctx: dict[int, Context] = {}
+_default_ctx_lock = threading.Lock()
 
 
 def default_context(device: int = 0) -> Context:
+    """The process-wide context of a device (sync.Once in the Go shim).  Created under a lock: two threads racing here would
+    each build a context, and the loser's would be destroyed while its handle is already on its way into a call."""
     ctx = _default_ctx.get(device)
     if ctx is None:
-        ctx = _default_ctx[device] = Context(device)
+        with _default_ctx_lock:
+            ctx = _default_ctx.get(device)
+            if ctx is None:
+                ctx = _default_ctx[device] = Context(device)
     return ctx
 
 

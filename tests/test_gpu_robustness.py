@@ -78,6 +78,77 @@ def test_concurrent_one_shot_calls(conv, oracle):
         assert G.rel_l2(y, oracle.convolve(x, h)) <= 1e-12
 
 
+def test_concurrent_mixed_families_on_one_context(conv, oracle):
+    """Eight host threads, each hammering a different family (plans, direct, correlation + peak, block FIR, resampler,
+    streaming reverb, device generator + plan) on the SAME context: every entry point takes the context lock, so all
+    answers must equal the single-threaded ones."""
+    from algo_dsp_b200 import post
+    h = G.decaying_ir(3000)
+    x = G.white(40000, seed=11)
+    fir_h = G.white(200, seed=12)
+    errs = []
+
+    def check(name, got, want, tol=1e-12):
+        e = G.rel_l2(got, want)
+        if not e <= tol:
+            errs.append((name, e))
+
+    def t_ols():
+        p = conv.NewOverlapSave(h, 0)
+        for _ in range(6):
+            check("ols", p.Process(x), oracle.overlap_save(h, 0, x))
+
+    def t_direct():
+        k = G.white(300, seed=13)
+        for _ in range(6):
+            check("direct", conv.Direct(x[:9000], k), oracle.direct(x[:9000], k))
+
+    def t_corr():
+        for _ in range(6):
+            c = conv.Correlate(x[:20000], x[500:4500])
+            check("corr", c, oracle.correlate(x[:20000], x[500:4500]))
+            if conv.FindPeak(c)[0] != oracle.find_peak(oracle.correlate(x[:20000], x[500:4500]))[0]:
+                errs.append(("peak", 0))
+
+    def t_fir():
+        want = np.convolve(x, fir_h[::-1])[: len(x)]
+        for _ in range(6):
+            f = post.New(fir_h)
+            y = x.copy()
+            f.ProcessBlock(y[:15000]); f.ProcessBlock(y[15000:])
+            check("fir", y, want)
+            f.Close()
+
+    def t_resample():
+        want = post.NewRational(160, 147).Process(x)
+        for _ in range(6):
+            r = post.NewRational(160, 147)
+            got = np.concatenate([r.Process(x[:17000]), r.Process(x[17000:])])
+            if not np.array_equal(got, want):
+                errs.append(("resample", 0))
+
+    def t_reverb():
+        want = np.concatenate([np.zeros(128), oracle.convolve(x, h)])[: len(x)]
+        for _ in range(3):
+            p = conv.NewPartitionedConvolution(h, 7, 13)
+            out = np.empty(len(x))
+            for a in range(0, len(x), 5000):
+                p.ProcessBlock(np.ascontiguousarray(x[a:a + 5000]), out[a:a + 5000])
+            check("partitioned", out, want, 1e-11)
+
+    def t_convolve():
+        for i in range(6):
+            a, b = G.white(7000 + i, seed=20 + i), G.white(50 + i, seed=30 + i)
+            check("convolve", conv.Convolve(a, b), oracle.convolve(a, b))
+
+    ts = [threading.Thread(target=f) for f in (t_ols, t_direct, t_corr, t_fir, t_resample, t_reverb, t_convolve, t_ols)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+
+
 def test_two_contexts_are_independent(conv, oracle):
     a, b = conv.Context(0), conv.Context(0)
     h, x = G.decaying_ir(5000), G.white(60000, seed=3)
