@@ -772,6 +772,8 @@ int64_t adsp_index_from_lag(int64_t lag, int64_t len_b) { return lag + (len_b - 
 
 }  // extern "C"
 
+extern "C" { static void plan_free(adsp_plan *p); }   // frees a plan; the caller holds the context lock
+
 // ---------------------------------------------------------------- one-shot implementations
 namespace {
 
@@ -845,7 +847,7 @@ adsp_status plan_create(adsp_ctx *ctx, PlanKind kind, const T *kernel, int64_t K
     p->ctx = ctx; p->kind = kind; p->prec = sizeof(T) == 8 ? ADSP_F64 : ADSP_F32; p->K = K;
     p->ref_fft = f; p->ref_step = s; p->ref_block = bsz;
     adsp_status st = plan_build<T>(p, kernel);
-    if (st != ADSP_OK) { adsp_plan_destroy(p); return st; }
+    if (st != ADSP_OK) { plan_free(p); return st; }
     *out = p;
     return ADSP_OK;
 }
@@ -1194,6 +1196,13 @@ adsp_status adsp_overlap_add_create(adsp_ctx *ctx, const void *kernel, int64_t K
 
 void adsp_plan_destroy(adsp_plan *p) {
     if (!p) return;
+    // finalizers run on arbitrary threads (runtime.SetFinalizer in the Go shim): serialise with calls in flight on the context
+    std::lock_guard<std::mutex> lk(p->ctx->mu);
+    plan_free(p);
+}
+
+// caller holds the context lock (error paths of the constructors, adsp_plan_destroy)
+static void plan_free(adsp_plan *p) {
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->main);
     for (auto &f : p->fc64) f.destroy();
@@ -1516,7 +1525,7 @@ adsp_status part_create(adsp_ctx *ctx, const T *kernel, int64_t K, int min_order
             if (st == ADSP_OK && cudaMemsetAsync(p->hist[i].p, 0, (size_t)p->hist_len * sizeof(T), ctx->main) != cudaSuccess) st = ADSP_ERR_CUDA;
         }
     }
-    if (st != ADSP_OK) { adsp_plan_destroy(p); return st; }
+    if (st != ADSP_OK) { plan_free(p); return st; }
     *out = p;
     return ADSP_OK;
 }
@@ -1642,7 +1651,7 @@ static adsp_status stream_create(adsp_ctx *ctx, const void *kernel, int64_t K, i
         st = p->hist[i].reserve((size_t)std::max<long long>(p->hist_len, 1) * es);
         if (st == ADSP_OK && cudaMemsetAsync(p->hist[i].p, 0, (size_t)std::max<long long>(p->hist_len, 1) * es, ctx->main) != cudaSuccess) st = ADSP_ERR_CUDA;
     }
-    if (st != ADSP_OK) { adsp_plan_destroy(p); return st; }
+    if (st != ADSP_OK) { plan_free(p); return st; }
     *out = p;
     return ADSP_OK;
 }

@@ -616,6 +616,7 @@ void adsp_fir_reset(adsp_fir *f) {                                              
 }
 void adsp_fir_destroy(adsp_fir *f) {
     if (!f) return;
+    std::lock_guard<std::mutex> lk(f->ctx->mu);
     cudaSetDevice(f->ctx->device);
     cudaStreamSynchronize(f->ctx->main);
     f->taps.release(); f->work.release(); f->full.release(); f->hist[0].release(); f->hist[1].release(); f->halo.release();
@@ -794,6 +795,7 @@ adsp_status adsp_resampler_process_device(adsp_resampler *r, const double *in_de
 void adsp_resampler_reset(adsp_resampler *r) { if (r) { r->total_in = 0; r->out_count = 0; r->hist_len = 0; } }      // Reset(), resample.go:241-246
 void adsp_resampler_destroy(adsp_resampler *r) {
     if (!r) return;
+    std::lock_guard<std::mutex> lk(r->ctx->mu);
     cudaSetDevice(r->ctx->device);
     cudaStreamSynchronize(r->ctx->main);
     r->d_taps.release(); r->work.release(); r->outbuf.release();

@@ -1,10 +1,10 @@
 """Randomised parity sweep through the public Python mirror (-> C ABI -> CUDA) against the CPU oracle: random lengths, kernel
 sizes, block splits and batch shapes for every family on the path.  Not part of the test suite (the suite pins fixed shapes);
 a soak run for a GPU box:
-    python tools/fuzz_parity.py [seconds=120] [seed=1]
+    python tests/tools/fuzz_parity.py [seconds=120] [seed=1]
 Prints one line per family with the case count and the worst relative L2 error; exits 1 on the first violation."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from algo_dsp_b200 import conv, post, siggen as G
 from oracle import oracle as O, post_oracle as PO
