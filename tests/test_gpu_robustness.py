@@ -158,6 +158,48 @@ def test_two_contexts_are_independent(conv, oracle):
     assert a.launch_count() > 0 and b.launch_count() > 0
 
 
+def test_two_contexts_concurrently(conv, oracle):
+    """Two contexts on the same device share no lock: their calls really overlap (plans, host pipeline with copy threads,
+    block FIR, device generators)."""
+    from algo_dsp_b200 import post
+    h, x = G.decaying_ir(4000), G.white(300000, seed=5)
+    want = oracle.overlap_save(h, 0, x)
+    fh = G.white(100, seed=6)
+    fwant = np.convolve(x, fh[::-1])[: len(x)]
+    errs = []
+
+    def work(seed):
+        try:
+            c = conv.Context(0)
+            p = conv.OverlapSave(h, 0, ctx=c)
+            xs = np.stack([x, x[::-1].copy(), x * 0.5, x])          # 9.6 MB: the staged host pipeline with copy threads
+            for _ in range(4):
+                y = p.ProcessBatch(xs)
+                if G.rel_l2(y[0], want) > 1e-12 or G.rel_l2(y[2], 0.5 * want) > 1e-12:
+                    errs.append(("ols", seed))
+                f = post.New(fh, ctx=c)
+                z = x.copy()
+                f.ProcessBlock(z)
+                if G.rel_l2(z, fwant) > 1e-12:
+                    errs.append(("fir", seed))
+                f.Close()
+                w = G.DeviceArray(c, 1, 4096)
+                G.white_device(c, w.ptr, 4096, 1, 4096, amp=1.0, seed0=seed)
+                if not np.array_equal(w.get()[0], G.white(4096, seed=seed)):
+                    errs.append(("gen", seed))
+            p.Close()
+            c.close()
+        except Exception as e:                                        # noqa: BLE001 - reported below
+            errs.append((repr(e), seed))
+
+    ts = [threading.Thread(target=work, args=(s,)) for s in (1, 2, 3)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+
+
 def test_nan_and_inf_propagate_like_ieee(conv):
     """No clamping or flushing: a NaN sample poisons exactly the outputs it touches in the direct path."""
     x = np.ones(100)
