@@ -1,7 +1,7 @@
 """Randomised parity sweep through the public Python mirror (-> C ABI -> CUDA) against the CPU oracle: random lengths, kernel
 sizes, block splits and batch shapes for every family on the path.  Not part of the test suite (the suite pins fixed shapes);
 a soak run for a GPU box:
-    python tests/tools/fuzz_parity.py [seconds=120] [seed=1]
+    python tests/tools/fuzz_parity.py [seconds=120] [seed=1] [big]
 Prints one line per family with the case count and the worst relative L2 error; exits 1 on the first violation."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
@@ -31,7 +31,12 @@ def note(fam, err, tol, what):
         sys.exit(1)
 
 
+BIG = len(sys.argv) > 3 and sys.argv[3] == "big"     # draw every size from the top decade and a half of its range
+
+
 def logint(lo, hi):
+    if BIG:
+        lo = max(lo, hi // 30)
     return int(round(np.exp(rng.uniform(np.log(lo), np.log(hi)))))
 
 
